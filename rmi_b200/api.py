@@ -1,0 +1,232 @@
+"""ctypes binding of include/rmi_b200.h, shaped like the reference's Rust API."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "librmi_b200.so")
+
+KEY_U64, KEY_U32, KEY_F64 = 0, 1, 2
+FLAG_STATS_ONLY, FLAG_TOP_FIT_EXACT = 1, 2
+_NP_OF_KEY = {KEY_U64: np.uint64, KEY_U32: np.uint32, KEY_F64: np.float64}
+MODEL_NAMES = ["linear", "robust_linear", "linear_spline", "cubic", "loglinear", "normal", "lognormal", "radix",
+               "radix_table", "bradix", "histogram"]
+
+
+class RMIError(RuntimeError):
+    """A failure at the C-ABI boundary (bad argument, CUDA error, unsupported request)."""
+
+
+class RMIPanic(RMIError):
+    """The reference would have panicked on this input (assert!/unwrap/panic!)."""
+
+
+class _Result(C.Structure):
+    """struct rmi_result (include/rmi_b200.h), mirror of TrainedRMI (train/mod.rs:18-33)."""
+    _fields_ = [
+        ("num_rmi_rows", C.c_uint64), ("num_data_rows", C.c_uint64), ("branching_factor", C.c_uint64),
+        ("model_avg_error", C.c_double), ("model_avg_l2_error", C.c_double), ("model_avg_log2_error", C.c_double),
+        ("model_max_log2_error", C.c_double), ("model_max_error", C.c_uint64), ("model_max_error_idx", C.c_uint64),
+        ("build_time_ns", C.c_uint64), ("device_time_ns", C.c_uint64), ("phase_device_ns", C.c_uint64 * 4),
+        ("l0_model_id", C.c_uint32), ("l0_bradix_high", C.c_uint32), ("l0_table_bits", C.c_uint32),
+        ("l0_num_fparams", C.c_uint32), ("l0_fparams", C.c_double * 4), ("l0_num_iparams", C.c_uint32),
+        ("_pad0", C.c_uint32), ("l0_iparams", C.c_uint64 * 4),
+        ("l0_table32_len", C.c_uint64), ("l0_table32", C.POINTER(C.c_uint32)),
+        ("l0_array1_len", C.c_uint64), ("l0_array1", C.POINTER(C.c_uint64)),
+        ("l0_array2_len", C.c_uint64), ("l0_array2", C.POINTER(C.c_uint64)),
+        ("l1_model_id", C.c_uint32), ("l1_params_per_model", C.c_uint32),
+        ("l1_params", C.POINTER(C.c_double)), ("l1_errors", C.POINTER(C.c_uint64)),
+        ("l1_counts", C.POINTER(C.c_uint64)), ("could_not_replace", C.c_uint32), ("top_fit_exact", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load_library():
+    """Load librmi_b200.so (built in-tree by rmi_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RMIError(f"{_LIB_PATH} is missing: run `python -m rmi_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        L.rmi_last_error.restype = C.c_char_p
+        L.rmi_version.restype = C.c_char_p
+        L.rmi_kernel_launch_count.restype = C.c_uint64
+        L.rmi_dataset_create.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rmi_dataset_wrap_device.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rmi_dataset_load_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rmi_dataset_len.restype = C.c_uint64
+        L.rmi_dataset_len.argtypes = [C.c_void_p]
+        L.rmi_dataset_key_type.argtypes = [C.c_void_p]
+        L.rmi_dataset_destroy.argtypes = [C.c_void_p]
+        L.rmi_train.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.POINTER(_Result))]
+        L.rmi_train_with_top.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32,
+                                         C.POINTER(C.POINTER(_Result))]
+        L.rmi_result_free.argtypes = [C.POINTER(_Result)]
+        _lib = L
+    return _lib
+
+
+def version() -> str:
+    return load_library().rmi_version().decode()
+
+
+def kernel_launch_count() -> int:
+    return int(load_library().rmi_kernel_launch_count())
+
+
+def _check(rc: int):
+    if rc == 0:
+        return
+    msg = load_library().rmi_last_error().decode()
+    if rc == 1:
+        raise RMIPanic(msg)
+    raise RMIError(f"rmi_b200 error {rc}: {msg}")
+
+
+def _key_type_of(dtype) -> int:
+    dtype = np.dtype(dtype)
+    for kt, nd in _NP_OF_KEY.items():
+        if dtype == np.dtype(nd):
+            return kt
+    raise TypeError(f"unsupported key dtype {dtype} (uint64, uint32, float64)")
+
+
+class RMITrainingData:
+    """A sorted key set resident in HBM (reference RMITrainingData, models/mod.rs:233-317).
+
+    ``RMITrainingData(host_array)`` copies a numpy array to the device;
+    ``RMITrainingData.from_device(ptr, n, key_type)`` borrows device memory (e.g. a torch
+    tensor's ``data_ptr()``), no copy.
+    """
+
+    def __init__(self, keys: np.ndarray, device: int = 0):
+        keys = np.ascontiguousarray(keys)
+        self._h = C.c_void_p()
+        self.key_type = _key_type_of(keys.dtype)
+        self._keep = None
+        _check(load_library().rmi_dataset_create(keys.ctypes.data_as(C.c_void_p), keys.size, self.key_type, device,
+                                                 C.byref(self._h)))
+
+    @classmethod
+    def from_device(cls, ptr: int, n: int, key_type: int, device: int = 0, keep_alive=None) -> "RMITrainingData":
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.key_type = key_type
+        self._keep = keep_alive
+        _check(load_library().rmi_dataset_wrap_device(C.c_void_p(ptr), n, key_type, device, C.byref(self._h)))
+        return self
+
+    @classmethod
+    def from_file(cls, path: str, key_type: int = -1, device: int = 0) -> "RMITrainingData":
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self._keep = None
+        _check(load_library().rmi_dataset_load_file(path.encode(), key_type, device, C.byref(self._h)))
+        self.key_type = int(load_library().rmi_dataset_key_type(self._h))
+        return self
+
+    def __len__(self) -> int:
+        return int(load_library().rmi_dataset_len(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            load_library().rmi_dataset_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def load_data(path: str, key_type: int = -1, device: int = 0) -> RMITrainingData:
+    """src/load.rs:132 load_data: header = u64 LE count, then packed keys; lands in HBM."""
+    return RMITrainingData.from_file(path, key_type, device)
+
+
+@dataclass
+class TrainedRMI:
+    """Owned copy of struct rmi_result; field names follow TrainedRMI (train/mod.rs:18-33)."""
+    num_rmi_rows: int
+    num_data_rows: int
+    branching_factor: int
+    model_avg_error: float
+    model_avg_l2_error: float
+    model_avg_log2_error: float
+    model_max_log2_error: float
+    model_max_error: int
+    model_max_error_idx: int
+    build_time: int               # ns, wall clock of the call
+    device_time_ns: int
+    phase_device_ns: tuple        # (top fit, leaf bounds, leaf fit+error pass, statistics)
+    models: str
+    l0_model: str
+    l0_fparams: np.ndarray
+    l0_iparams: np.ndarray
+    l0_bradix_high: bool
+    l0_table_bits: int
+    l0_table32: np.ndarray | None
+    l0_radix_index: np.ndarray | None
+    l0_pivots: np.ndarray | None
+    l1_model: str
+    l1_params: np.ndarray | None   # (N, ppm)
+    last_layer_max_l1s: np.ndarray | None
+    l1_counts: np.ndarray | None
+    could_not_replace: bool
+    top_fit_exact: bool
+
+
+def _arr(ptr, n, dtype):
+    if not ptr or n == 0:
+        return None
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
+
+
+def train(data: RMITrainingData, model_spec: str, branch_factor: int, flags: int = 0,
+          l0_params=None) -> TrainedRMI:
+    """rmi_lib::train (train/mod.rs:100-126) on the GPU.  Raises RMIPanic where the reference panics."""
+    L = load_library()
+    res = C.POINTER(_Result)()
+    if l0_params is None:
+        rc = L.rmi_train(data._h, model_spec.encode(), int(branch_factor), int(flags), C.byref(res))
+    else:
+        p = np.ascontiguousarray(l0_params, dtype=np.float64)
+        rc = L.rmi_train_with_top(data._h, model_spec.encode(), int(branch_factor), int(flags),
+                                  p.ctypes.data_as(C.c_void_p), p.size, C.byref(res))
+    _check(rc)
+    try:
+        r = res.contents
+        N, ppm = int(r.branching_factor), int(r.l1_params_per_model)
+        params = _arr(r.l1_params, N * ppm, np.float64)
+        out = TrainedRMI(
+            num_rmi_rows=int(r.num_rmi_rows), num_data_rows=int(r.num_data_rows), branching_factor=N,
+            model_avg_error=float(r.model_avg_error), model_avg_l2_error=float(r.model_avg_l2_error),
+            model_avg_log2_error=float(r.model_avg_log2_error), model_max_log2_error=float(r.model_max_log2_error),
+            model_max_error=int(r.model_max_error), model_max_error_idx=int(r.model_max_error_idx),
+            build_time=int(r.build_time_ns), device_time_ns=int(r.device_time_ns),
+            phase_device_ns=tuple(int(x) for x in r.phase_device_ns), models=model_spec,
+            l0_model=MODEL_NAMES[int(r.l0_model_id)],
+            l0_fparams=np.array(list(r.l0_fparams)[: int(r.l0_num_fparams)], dtype=np.float64),
+            l0_iparams=np.array(list(r.l0_iparams)[: int(r.l0_num_iparams)], dtype=np.uint64),
+            l0_bradix_high=bool(r.l0_bradix_high), l0_table_bits=int(r.l0_table_bits),
+            l0_table32=_arr(r.l0_table32, r.l0_table32_len, np.uint32),
+            l0_radix_index=_arr(r.l0_array1, r.l0_array1_len, np.uint64),
+            l0_pivots=_arr(r.l0_array2, r.l0_array2_len, np.uint64),
+            l1_model=MODEL_NAMES[int(r.l1_model_id)],
+            l1_params=None if params is None else params.reshape(N, ppm),
+            last_layer_max_l1s=_arr(r.l1_errors, N, np.uint64), l1_counts=_arr(r.l1_counts, N, np.uint64),
+            could_not_replace=bool(r.could_not_replace), top_fit_exact=bool(r.top_fit_exact))
+    finally:
+        L.rmi_result_free(res)
+    return out

@@ -1,0 +1,451 @@
+// api.cu — the C ABI of librmi_b200.so (include/rmi_b200.h): datasets in HBM, the
+// rmi_lib::train replacement, result marshalling, error text.
+//
+// One rmi_train call = one CUDA stream + one stream-ordered scratch arena; the dataset is
+// read-only and may be shared by concurrent calls (reference optimizer.rs:224 trains many
+// configurations on one shared RMITrainingData).  No host synchronisation happens between
+// the first kernel and the final result copy.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rmi_b200.h"
+#include "kernels.h"
+
+using namespace rmi;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(RMI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+size_t key_bytes(int kt) { return kt == RMI_KEY_U32 ? 4 : 8; }
+
+struct DeviceInfo { int num_sms = 0; };
+int device_info(int device, DeviceInfo* out) {
+  static std::mutex mu;
+  static std::vector<DeviceInfo> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)cache.size() <= device) cache.resize(device + 1);
+  if (cache[device].num_sms == 0) {
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    cache[device].num_sms = sms;
+  }
+  *out = cache[device];
+  return RMI_OK;
+}
+
+struct ModelName { const char* name; int kind; int table_bits; };
+const ModelName kModels[] = {   // reference train/mod.rs:37-54
+    {"linear", M_LINEAR, 0},          {"robust_linear", M_ROBUST_LINEAR, 0}, {"linear_spline", M_LINEAR_SPLINE, 0},
+    {"cubic", M_CUBIC, 0},            {"loglinear", M_LOGLINEAR, 0},         {"normal", M_NORMAL, 0},
+    {"lognormal", M_LOGNORMAL, 0},    {"radix", M_RADIX, 0},                 {"radix8", M_RADIX_TABLE, 8},
+    {"radix18", M_RADIX_TABLE, 18},   {"radix22", M_RADIX_TABLE, 22},        {"radix26", M_RADIX_TABLE, 26},
+    {"radix28", M_RADIX_TABLE, 28},   {"bradix", M_BRADIX, 0},               {"histogram", M_HISTOGRAM, 0}};
+
+const ModelName* find_model(const std::string& s) {
+  for (const auto& m : kModels) if (s == m.name) return &m;
+  return nullptr;
+}
+
+std::string status_text(unsigned st) {
+  struct { unsigned bit; const char* text; } table[] = {
+      {ST_NOT_SORTED, "keys are not sorted in ascending order"},
+      {ST_NON_MONOTONE, "assertion failed: target >= last_target (top model is not monotonic on this data)"},
+      {ST_SPLIT_AT_ZERO, "start index was 0 but end index was 0"},
+      {ST_SPLIT_AT_END, "start index was n but end index was n (split at the last key)"},
+      {ST_TOP_OUT_OF_BOUNDS, "Top model gave an index which is out of bounds"},
+      {ST_NUM_BITS, "assertion failed: nbits >= 1"},
+      {ST_CUBIC_UNWRAP, "called `Option::unwrap()` on a `None` value (cubic: no interior point)"},
+      {ST_ROBUST_TOO_SMALL, "assertion failed: bnd * 2 + 1 < data.len()"},
+      {ST_HIST_BINS, "not enough items for equidepth histogram"},
+      {ST_NEG_VARIANCE, "variance of model was negative"},
+      {ST_BRADIX_OOB, "index out of bounds (bradix chi2 counts)"},
+      {ST_RADIX_TABLE_OOB, "assertion failed: current_radix < hint_table.len()"}};
+  std::string out;
+  for (auto& e : table)
+    if (st & e.bit) { if (!out.empty()) out += "; "; out += e.text; }
+  return out;
+}
+
+}  // namespace
+
+namespace rmi {
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace rmi
+
+struct rmi_dataset {
+  void* d_keys = nullptr;
+  uint64_t n = 0;
+  int key_type = 0;
+  int device = 0;
+  bool owned = false;
+};
+
+// The allocation behind an rmi_result: the public struct first, then the owned buffers.
+struct ResultBox {
+  rmi_result pub;
+  std::vector<double> l1_params;
+  std::vector<uint64_t> l1_errors, l1_counts;
+  std::vector<uint32_t> table32;
+  std::vector<uint64_t> arr1, arr2;
+};
+
+extern "C" {
+
+const char* rmi_last_error(void) { return g_last_error.c_str(); }
+uint64_t rmi_kernel_launch_count(void) { return g_launches.load(); }
+const char* rmi_version(void) { return "rmi_b200 0.1 (sm_100a)"; }
+
+int rmi_dataset_create(const void* host_keys, uint64_t n, rmi_key_type key_type, int device, rmi_dataset** out) {
+  if (!out || (!host_keys && n) || (int)key_type < 0 || (int)key_type > 2)
+    return fail(RMI_ERR_INVALID, "rmi_dataset_create: bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  auto* ds = new rmi_dataset();
+  ds->n = n; ds->key_type = key_type; ds->device = device; ds->owned = true;
+  size_t bytes = (size_t)n * key_bytes(key_type);
+  if (bytes) {
+    cudaError_t e = cudaMalloc(&ds->d_keys, bytes);
+    if (e != cudaSuccess) { delete ds; return fail(RMI_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    e = cudaMemcpy(ds->d_keys, host_keys, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(ds->d_keys); delete ds; return fail(RMI_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e)); }
+  }
+  *out = ds;
+  return RMI_OK;
+}
+
+int rmi_dataset_wrap_device(const void* device_keys, uint64_t n, rmi_key_type key_type, int device, rmi_dataset** out) {
+  if (!out || (!device_keys && n) || (int)key_type < 0 || (int)key_type > 2)
+    return fail(RMI_ERR_INVALID, "rmi_dataset_wrap_device: bad argument");
+  auto* ds = new rmi_dataset();
+  ds->d_keys = const_cast<void*>(device_keys);
+  ds->n = n; ds->key_type = key_type; ds->device = device; ds->owned = false;
+  *out = ds;
+  return RMI_OK;
+}
+
+int rmi_dataset_load_file(const char* path, int key_type_or_negative, int device, rmi_dataset** out) {
+  if (!path || !out) return fail(RMI_ERR_INVALID, "rmi_dataset_load_file: bad argument");
+  int kt = key_type_or_negative;
+  if (kt < 0) {   // src/main.rs:122-132: type from the file-name suffix
+    std::string p(path);
+    auto ends = [&](const char* s) { size_t l = strlen(s); return p.size() >= l && p.compare(p.size() - l, l, s) == 0; };
+    if (ends("uint64")) kt = RMI_KEY_U64;
+    else if (ends("uint32")) kt = RMI_KEY_U32;
+    else if (ends("f64")) kt = RMI_KEY_F64;
+    else return fail(RMI_ERR_PANIC, "Data file must end in .uint64, .uint32, or .f64");
+  }
+  if (kt > 2) return fail(RMI_ERR_INVALID, "rmi_dataset_load_file: bad key type");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(RMI_ERR_PANIC, std::string("Unable to open data file at ") + path);
+  uint64_t n = 0;
+  if (fread(&n, 8, 1, f) != 1) { fclose(f); return fail(RMI_ERR_PANIC, "data file too short for its header"); }
+  if (cudaSetDevice(device) != cudaSuccess) { fclose(f); return fail(RMI_ERR_CUDA, "cudaSetDevice failed"); }
+  auto* ds = new rmi_dataset();
+  ds->n = n; ds->key_type = kt; ds->device = device; ds->owned = true;
+  size_t kb = key_bytes(kt), bytes = (size_t)n * kb;
+  cudaStream_t st = nullptr;
+  void* stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  const size_t CHUNK = (size_t)64 << 20;
+  int rc = RMI_OK;
+  auto cleanup = [&]() {
+    for (int b = 0; b < 2; ++b) { if (stage[b]) cudaFreeHost(stage[b]); if (ev[b]) cudaEventDestroy(ev[b]); }
+    if (st) cudaStreamDestroy(st);
+    fclose(f);
+  };
+  if (bytes) {
+    if (cudaMalloc(&ds->d_keys, bytes) != cudaSuccess || cudaStreamCreate(&st) != cudaSuccess ||
+        cudaMallocHost(&stage[0], CHUNK) != cudaSuccess || cudaMallocHost(&stage[1], CHUNK) != cudaSuccess ||
+        cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess) {
+      rc = fail(RMI_ERR_CUDA, "rmi_dataset_load_file: allocation failed");
+    } else {
+      // double-buffered: fread into one pinned buffer while the other is in flight to HBM
+      size_t off = 0; int b = 0;
+      while (off < bytes) {
+        size_t len = std::min(CHUNK, bytes - off);
+        cudaEventSynchronize(ev[b]);
+        if (fread(stage[b], 1, len, f) != len) { rc = fail(RMI_ERR_PANIC, "data file shorter than its header says"); break; }
+        cudaMemcpyAsync((char*)ds->d_keys + off, stage[b], len, cudaMemcpyHostToDevice, st);
+        cudaEventRecord(ev[b], st);
+        off += len; b ^= 1;
+      }
+      if (cudaStreamSynchronize(st) != cudaSuccess && rc == RMI_OK) rc = fail(RMI_ERR_CUDA, "H2D copy failed");
+    }
+  }
+  cleanup();
+  if (rc != RMI_OK) { if (ds->d_keys) cudaFree(ds->d_keys); delete ds; return rc; }
+  *out = ds;
+  return RMI_OK;
+}
+
+uint64_t rmi_dataset_len(const rmi_dataset* ds) { return ds ? ds->n : 0; }
+int rmi_dataset_key_type(const rmi_dataset* ds) { return ds ? ds->key_type : -1; }
+void rmi_dataset_destroy(rmi_dataset* ds) {
+  if (!ds) return;
+  if (ds->owned && ds->d_keys) { cudaSetDevice(ds->device); cudaFree(ds->d_keys); }
+  delete ds;
+}
+
+void rmi_result_free(rmi_result* r) { delete reinterpret_cast<ResultBox*>(r); }
+
+}  // extern "C"
+
+namespace {
+
+struct Arena {   // stream-ordered scratch; everything is released when the call ends
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  cudaError_t err = cudaSuccess;
+  explicit Arena(cudaStream_t s) : st(s) {}
+  template <class P> P* get(size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count * sizeof(P), 16), st);
+    if (e != cudaSuccess) { err = e; return nullptr; }
+    ptrs.push_back(p);
+    return (P*)p;
+  }
+  ~Arena() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+};
+
+template <class T>
+int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& leaf, uint64_t N, uint32_t flags,
+                const double* l0_over, uint32_t n_over, rmi_result** out) {
+  auto t_start = std::chrono::steady_clock::now();
+  const uint64_t n = ds->n;
+  const T* keys = (const T*)ds->d_keys;
+  CUDA_TRY(cudaSetDevice(ds->device));
+  DeviceInfo di;
+  if (int rc = device_info(ds->device, &di)) return rc;
+
+  cudaStream_t st;
+  CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[3] = {nullptr, nullptr, nullptr};
+  cudaEventCreate(&ev0);
+  cudaEventCreate(&ev1);
+  for (auto& e : evp) cudaEventCreate(&e);
+  int rc = RMI_OK;
+  auto box = new ResultBox();
+  {
+    Arena A(st);
+    Launch L{st, di.num_sms};
+    const int ppm = leaf_params_per_model(leaf.kind);
+    TopModel* d_top = A.get<TopModel>(1);
+    BuildAux* d_aux = A.get<BuildAux>(1);
+    u64* d_S = A.get<u64>(N + 1);
+    double* d_params = A.get<double>(N * ppm);
+    u64* d_errors = A.get<u64>(N);
+    u64* d_counts = A.get<u64>(N);
+    void* d_scratch = A.get<char>(top_scratch_bytes(N));
+    void* d_stats = A.get<char>(stats_scratch_bytes(N));
+    u32* d_table = nullptr;
+    u64 *d_pivots = nullptr, *d_ri = nullptr;
+    u64 hist_bins = 0, hist_ipb = 0;
+    if (top.kind == M_RADIX_TABLE) d_table = A.get<u32>((size_t)1 << top.table_bits);
+    if (top.kind == M_HISTOGRAM) {
+      histogram_bins(n, N, &hist_bins, &hist_ipb);
+      d_pivots = A.get<u64>(hist_bins + 1);
+      d_ri = A.get<u64>(((size_t)1 << 20) + 1);
+    }
+    if (A.err != cudaSuccess) {
+      rc = fail(RMI_ERR_CUDA, std::string("scratch allocation: ") + cudaGetErrorString(A.err));
+    } else {
+      TopModel h_top;
+      memset(&h_top, 0, sizeof(h_top));
+      h_top.kind = top.kind;
+      h_top.high = 1;
+      h_top.table_bits = top.table_bits;
+      h_top.t32 = d_table;
+      h_top.pivots = d_pivots;
+      h_top.radix_index = d_ri;
+      h_top.npivots = hist_bins;
+      if (top.kind == M_HISTOGRAM) h_top.ip[0] = hist_bins;
+      if (l0_over) for (uint32_t q = 0; q < n_over && q < 4; ++q) h_top.f[q] = l0_over[q];
+      cudaEventRecord(ev0, st);
+      cudaMemcpyAsync(d_top, &h_top, sizeof(h_top), cudaMemcpyHostToDevice, st);
+      cudaMemsetAsync(d_aux, 0, sizeof(BuildAux), st);
+      unsigned host_status = 0;
+      bool exact = (flags & RMI_FLAG_TOP_FIT_EXACT) != 0;
+      if (!l0_over)
+        host_status = fit_top_model<T>(L, keys, n, top.kind, top.table_bits, N, exact, d_top, d_aux, d_scratch, d_table,
+                                       d_pivots, d_ri);
+      cudaEventRecord(evp[0], st);
+      if (host_status == 0) {
+        compute_leaf_bounds<T>(L, keys, n, top.kind, d_top, N, d_S, d_aux);
+        cudaEventRecord(evp[1], st);
+        fit_leaves<T>(L, keys, n, leaf.kind, N, d_S, d_aux, d_params, d_errors, d_counts);
+        cudaEventRecord(evp[2], st);
+        leaf_statistics(L, n, N, d_errors, d_counts, d_aux, d_stats);
+      } else {
+        cudaEventRecord(evp[1], st);
+        cudaEventRecord(evp[2], st);
+      }
+      cudaEventRecord(ev1, st);
+      // ---- results to the host --------------------------------------------------------------
+      BuildAux h_aux;
+      memset(&h_aux, 0, sizeof(h_aux));
+      cudaMemcpyAsync(&h_aux, d_aux, sizeof(h_aux), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(&h_top, d_top, sizeof(h_top), cudaMemcpyDeviceToHost, st);
+      const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0;
+      if (host_status == 0 && !stats_only) {
+        box->l1_params.resize((size_t)N * ppm);
+        box->l1_errors.resize(N);
+        box->l1_counts.resize(N);
+        cudaMemcpyAsync(box->l1_params.data(), d_params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(box->l1_errors.data(), d_errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(box->l1_counts.data(), d_counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
+      }
+      if (host_status == 0 && top.kind == M_RADIX_TABLE) {
+        box->table32.resize((size_t)1 << top.table_bits);
+        cudaMemcpyAsync(box->table32.data(), d_table, sizeof(u32) * box->table32.size(), cudaMemcpyDeviceToHost, st);
+      }
+      if (host_status == 0 && top.kind == M_HISTOGRAM) {
+        box->arr1.resize(((size_t)1 << 20) + 1);
+        box->arr2.resize(hist_bins);
+        cudaMemcpyAsync(box->arr1.data(), d_ri, sizeof(u64) * box->arr1.size(), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(box->arr2.data(), d_pivots, sizeof(u64) * hist_bins, cudaMemcpyDeviceToHost, st);
+      }
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        rc = fail(RMI_ERR_CUDA, std::string("rmi_train: ") + cudaGetErrorString(e));
+      } else if (host_status | h_aux.status) {
+        rc = fail(RMI_ERR_PANIC, status_text(host_status | h_aux.status));
+      } else {
+        rmi_result& R = box->pub;
+        memset(&R, 0, sizeof(R));
+        R.num_rmi_rows = n; R.num_data_rows = n; R.branching_factor = N;
+        // two_layer.rs:267-284
+        R.model_max_error = h_aux.max_error;
+        R.model_max_error_idx = h_aux.max_error_idx;
+        R.model_avg_error = (double)h_aux.sum_n_err / (double)n;
+        R.model_avg_l2_error = h_aux.sum_l2;
+        R.model_avg_log2_error = h_aux.sum_log2 / (double)n;
+        R.model_max_log2_error = std::log2((double)h_aux.max_error);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        R.device_time_ns = (uint64_t)((double)ms * 1e6);
+        cudaEvent_t seq[5] = {ev0, evp[0], evp[1], evp[2], ev1};
+        for (int q = 0; q < 4; ++q) {
+          cudaEventElapsedTime(&ms, seq[q], seq[q + 1]);
+          R.phase_device_ns[q] = (uint64_t)((double)ms * 1e6);
+        }
+        R.l0_model_id = top.kind;
+        R.l0_bradix_high = h_top.high;
+        R.l0_table_bits = top.table_bits;
+        switch (top.kind) {
+          case M_CUBIC: R.l0_num_fparams = 4; break;
+          case M_NORMAL: case M_LOGNORMAL: R.l0_num_fparams = 3; break;
+          case M_LINEAR: case M_ROBUST_LINEAR: case M_LINEAR_SPLINE: case M_LOGLINEAR: R.l0_num_fparams = 2; break;
+          case M_RADIX: R.l0_num_iparams = 2; break;
+          case M_BRADIX: R.l0_num_iparams = 3; break;
+          case M_RADIX_TABLE: R.l0_num_iparams = 1; break;   // prefix (the table itself is l0_table32)
+          case M_HISTOGRAM: R.l0_num_iparams = 1; break;
+        }
+        for (int q = 0; q < 4; ++q) { R.l0_fparams[q] = h_top.f[q]; R.l0_iparams[q] = h_top.ip[q]; }
+        R.l0_table32_len = box->table32.size();
+        R.l0_table32 = box->table32.empty() ? nullptr : box->table32.data();
+        R.l0_array1_len = box->arr1.size();
+        R.l0_array1 = box->arr1.empty() ? nullptr : box->arr1.data();
+        R.l0_array2_len = box->arr2.size();
+        R.l0_array2 = box->arr2.empty() ? nullptr : box->arr2.data();
+        R.l1_model_id = leaf.kind;
+        R.l1_params_per_model = ppm;
+        R.l1_params = stats_only ? nullptr : box->l1_params.data();
+        R.l1_errors = stats_only ? nullptr : box->l1_errors.data();
+        R.l1_counts = stats_only ? nullptr : box->l1_counts.data();
+        R.could_not_replace = h_aux.could_not_replace ? 1 : 0;
+        R.top_fit_exact = (exact && !l0_over) ? 1 : 0;
+      }
+    }
+  }   // arena frees (stream-ordered)
+  cudaStreamSynchronize(st);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  for (auto& e : evp) cudaEventDestroy(e);
+  cudaStreamDestroy(st);
+  if (rc != RMI_OK) { delete box; return rc; }
+  box->pub.build_time_ns =
+      (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_start).count();
+  *out = &box->pub;
+  return RMI_OK;
+}
+
+int train_entry(const rmi_dataset* ds, const char* model_spec, uint64_t N, uint32_t flags, const double* l0_over,
+                uint32_t n_over, rmi_result** out) {
+  g_last_error.clear();
+  if (!ds || !model_spec || !out) return fail(RMI_ERR_INVALID, "rmi_train: null argument");
+  // train/mod.rs:104-109: split the spec on ',', validate, last = leaf type
+  std::vector<std::string> layers;
+  {
+    std::string s(model_spec);
+    size_t pos = 0;
+    for (;;) {
+      size_t c = s.find(',', pos);
+      if (c == std::string::npos) { layers.push_back(s.substr(pos)); break; }
+      layers.push_back(s.substr(pos, c - pos));
+      pos = c + 1;
+    }
+  }
+  std::vector<const ModelName*> models;
+  for (size_t i = 0; i < layers.size(); ++i) {
+    const ModelName* m = find_model(layers[i]);
+    if (!m) return fail(RMI_ERR_PANIC, "Unknown model type: " + layers[i]);
+    // train/mod.rs:59-85 validate: radix / bradix / histogram must be the root model
+    bool must_be_top = m->kind == M_RADIX || m->kind == M_BRADIX || m->kind == M_HISTOGRAM;
+    if (must_be_top && i != 0)
+      return fail(RMI_ERR_PANIC, "if used, model type " + layers[i] + " must be the root model");
+    models.push_back(m);
+  }
+  if (models.size() != 2)   // train/mod.rs:123-125 panic!() for anything but two layers
+    return fail(RMI_ERR_PANIC, "only two-layer RMIs can be trained (the reference panics on other depths)");
+  const ModelName& top = *models[0];
+  const ModelName& leaf = *models[1];
+  if (leaf.kind == M_RADIX_TABLE)
+    return fail(RMI_ERR_UNSUPPORTED, "radix tables are only offered as the top model in this build");
+  if (N < 1) return fail(RMI_ERR_PANIC, "branching factor must be at least 1");
+  if (ds->n == 0) return fail(RMI_ERR_PANIC, "start index was 0 but end index was 0");
+  if (l0_over) {
+    uint32_t need = top.kind == M_CUBIC ? 4 : (top.kind == M_NORMAL || top.kind == M_LOGNORMAL) ? 3 : 2;
+    if (top.kind > M_LOGNORMAL || n_over != need)
+      return fail(RMI_ERR_INVALID, "rmi_train_with_top: top model has no float parameters or wrong count");
+  }
+  switch (ds->key_type) {
+    case RMI_KEY_U64: return train_typed<u64>(ds, top, leaf, N, flags, l0_over, n_over, out);
+    case RMI_KEY_U32: return train_typed<u32>(ds, top, leaf, N, flags, l0_over, n_over, out);
+    case RMI_KEY_F64: return train_typed<double>(ds, top, leaf, N, flags, l0_over, n_over, out);
+  }
+  return fail(RMI_ERR_INVALID, "bad key type");
+}
+
+}  // namespace
+
+extern "C" {
+
+int rmi_train(const rmi_dataset* ds, const char* model_spec, uint64_t branch_factor, uint32_t flags, rmi_result** out) {
+  return train_entry(ds, model_spec, branch_factor, flags, nullptr, 0, out);
+}
+int rmi_train_with_top(const rmi_dataset* ds, const char* model_spec, uint64_t branch_factor, uint32_t flags,
+                       const double* l0_fparams, uint32_t n_fparams, rmi_result** out) {
+  if (!l0_fparams) return fail(RMI_ERR_INVALID, "rmi_train_with_top: null parameters");
+  return train_entry(ds, model_spec, branch_factor, flags, l0_fparams, n_fparams, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// kernels.h — host-callable launchers of the CUDA kernels (kernels_top.cu, kernels_leaf.cu)
+// used by the C-ABI layer (api.cu).  Internal; the public surface is include/rmi_b200.h.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "models.cuh"
+
+namespace rmi {
+
+// Conditions under which the reference panics (or this build gives up); set by kernels in a
+// device status word, decoded by api.cu into rmi_last_error() text.
+enum StatusBit : unsigned {
+  ST_NOT_SORTED = 1u << 0,        // keys[i] < keys[i-1]
+  ST_NON_MONOTONE = 1u << 1,      // two_layer.rs:50  assert!(target >= last_target)
+  ST_SPLIT_AT_ZERO = 1u << 2,     // two_layer.rs:27  build_models_from(0, 0, ..): end_idx > start_idx
+  ST_SPLIT_AT_END = 1u << 3,      // two_layer.rs:27  build_models_from(n, n, ..)
+  ST_TOP_OUT_OF_BOUNDS = 1u << 4, // two_layer.rs:45  top model index out of bounds
+  ST_NUM_BITS = 1u << 5,          // utils.rs:18      assert!(nbits >= 1)
+  ST_CUBIC_UNWRAP = 1u << 6,      // cubic_spline.rs:50,61  find(..).unwrap() on None
+  ST_ROBUST_TOO_SMALL = 1u << 7,  // linear.rs:248    assert!(bnd*2+1 < data.len())
+  ST_HIST_BINS = 1u << 8,         // histogram.rs:25-27 division by zero / items_per_bin >= 1
+  ST_NEG_VARIANCE = 1u << 9,      // linear.rs:48     assert!(var >= 0.0)
+  ST_BRADIX_OOB = 1u << 10,       // balanced_radix.rs:28 counts[] index out of bounds
+  ST_RADIX_TABLE_OOB = 1u << 11   // radix.rs:103     assert!(current_radix < hint_table.len())
+};
+
+// Small device-resident scalars shared between kernels of one build.
+struct BuildAux {
+  unsigned status;        // OR of StatusBit
+  int has_split;          // two_layer.rs:147-175: 0 = single range, 1 = two halves
+  u64 split_idx;          // first index whose clamped top prediction >= N/2
+  u64 split_target;       // clamped prediction of keys[split_idx]
+  u64 max_scaled_y;       // largest scaled offset (radix / bradix)
+  // summary statistics (two_layer.rs:267-284)
+  u64 max_error, max_error_idx, sum_n_err;
+  double sum_l2, sum_log2;
+  // bradix search state
+  double best_score;
+  int best_valid, _pad;
+  u64 could_not_replace;
+};
+
+struct Launch {
+  cudaStream_t stream;
+  int num_sms;
+};
+
+void count_launch();   // bumps the process-wide kernel launch counter (api.cu)
+
+// ---- top-model fits (kernels_top.cu) -------------------------------------------------------
+// All write the fitted model into *d_top (device) and OR failure bits into d_aux->status.
+// `scratch` must hold at least top_scratch_bytes() bytes.
+size_t top_scratch_bytes(u64 num_leaves);
+// Returns host-detected StatusBits (0 = launched); device-detected ones land in d_aux->status.
+void histogram_bins(u64 n, u64 num_leaves, u64* num_bins, u64* items_per_bin);
+template <class T>
+unsigned fit_top_model(const Launch& L, const T* keys, u64 n, int kind, int table_bits, u64 num_leaves, bool exact,
+                       TopModel* d_top, BuildAux* d_aux, void* scratch, u32* d_table32, u64* d_pivots,
+                       u64* d_radix_index);
+
+// ---- leaf layer (kernels_leaf.cu) ----------------------------------------------------------
+// S[j] = first index whose clamped top prediction is >= j, for j in [0, N]; also verifies
+// sortedness and monotonicity and derives the split (two_layer.rs:131-175).
+template <class T>
+void compute_leaf_bounds(const Launch& L, const T* keys, u64 n, int top_kind, const TopModel* d_top, u64 num_leaves,
+                         u64* d_S, BuildAux* d_aux);
+// Fused per-leaf pass: closed-form fit (build_models_from), empty-leaf constants, forward
+// pass / max error, lower-bound widening (two_layer.rs:20-99, :186-259,
+// lower_bound_correction.rs:91-137).  Writes N x ppm params, N errors, N counts.
+template <class T>
+void fit_leaves(const Launch& L, const T* keys, u64 n, int leaf_kind, u64 num_leaves, const u64* d_S,
+                BuildAux* d_aux, double* d_params, u64* d_errors, u64* d_counts);
+// Summary statistics over the N leaves (two_layer.rs:267-284) into d_aux.
+void leaf_statistics(const Launch& L, u64 n, u64 num_leaves, const u64* d_errors, const u64* d_counts,
+                     BuildAux* d_aux, void* scratch);
+size_t stats_scratch_bytes(u64 num_leaves);
+
+}  // namespace rmi

@@ -1,0 +1,31 @@
+"""Developer timing probe (not the contract bench): per-phase device times at full size."""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import rmi_b200
+
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 200_000_000
+torch.manual_seed(42)
+dev = torch.device("cuda:0")
+k = torch.randint(0, 2**63 - 1, (n,), dtype=torch.int64, device=dev)
+k, _ = torch.sort(k)
+torch.cuda.synchronize()
+ds = rmi_b200.RMITrainingData.from_device(k.data_ptr(), n, rmi_b200.KEY_U64, 0, keep_alive=k)
+configs = [("linear,linear", 1 << 20, 0), ("radix,linear", 1 << 19, 0), ("cubic,linear", 1 << 18, 0),
+           ("linear,linear", 1 << 20, rmi_b200.FLAG_STATS_ONLY), ("linear_spline,cubic", 1 << 18, 0),
+           ("radix18,linear", 1 << 16, 0), ("bradix,linear", 1 << 18, 0), ("histogram,linear", 1 << 16, 0)]
+if "--exact" in sys.argv:
+    configs.append(("linear,linear", 1 << 20, rmi_b200.FLAG_TOP_FIT_EXACT))
+for spec, bf, flags in configs:
+    try:
+        for it in range(3):
+            t0 = time.perf_counter()
+            r = rmi_b200.train(ds, spec, bf, flags)
+            t1 = time.perf_counter()
+        print(json.dumps({"spec": spec, "bf": bf, "flags": flags, "wall_ms": (t1 - t0) * 1e3,
+                          "lib_wall_ms": r.build_time / 1e6, "device_ms": r.device_time_ns / 1e6,
+                          "phases_ms": [p / 1e6 for p in r.phase_device_ns], "max_err": r.model_max_error,
+                          "avg_log2": r.model_avg_log2_error, "keys_per_s_device": n / (r.device_time_ns / 1e9)}))
+    except rmi_b200.RMIError as e:
+        print(json.dumps({"spec": spec, "bf": bf, "error": str(e)}))
+    sys.stdout.flush()
