@@ -185,12 +185,32 @@ class TrainedRMI:
     l1_counts: np.ndarray | None
     could_not_replace: bool
     top_fit_exact: bool
+    _res: object = None            # keeps the underlying struct rmi_result alive
 
 
-def _arr(ptr, n, dtype):
+class _ResultOwner:
+    """Owns a struct rmi_result*; freed (rmi_result_free) when the last array view is gone."""
+
+    def __init__(self, res):
+        self.res = res
+
+    def __del__(self):
+        try:
+            if self.res is not None:
+                load_library().rmi_result_free(self.res)
+                self.res = None
+        except Exception:
+            pass
+
+
+def _arr(ptr, n, ctype, dtype, owner):
+    """Zero-copy numpy view of result memory owned by the library (keeps `owner` alive)."""
+    n = int(n)
     if not ptr or n == 0:
         return None
-    return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
+    buf = (ctype * n).from_address(C.addressof(ptr.contents))
+    buf._owner = owner
+    return np.frombuffer(buf, dtype=dtype)
 
 
 def train(data: RMITrainingData, model_spec: str, branch_factor: int, flags: int = 0,
@@ -205,10 +225,11 @@ def train(data: RMITrainingData, model_spec: str, branch_factor: int, flags: int
         rc = L.rmi_train_with_top(data._h, model_spec.encode(), int(branch_factor), int(flags),
                                   p.ctypes.data_as(C.c_void_p), p.size, C.byref(res))
     _check(rc)
-    try:
+    if True:
         r = res.contents
+        owner = _ResultOwner(res)
         N, ppm = int(r.branching_factor), int(r.l1_params_per_model)
-        params = _arr(r.l1_params, N * ppm, np.float64)
+        params = _arr(r.l1_params, N * ppm, C.c_double, np.float64, owner)
         out = TrainedRMI(
             num_rmi_rows=int(r.num_rmi_rows), num_data_rows=int(r.num_data_rows), branching_factor=N,
             model_avg_error=float(r.model_avg_error), model_avg_l2_error=float(r.model_avg_l2_error),
@@ -220,13 +241,12 @@ def train(data: RMITrainingData, model_spec: str, branch_factor: int, flags: int
             l0_fparams=np.array(list(r.l0_fparams)[: int(r.l0_num_fparams)], dtype=np.float64),
             l0_iparams=np.array(list(r.l0_iparams)[: int(r.l0_num_iparams)], dtype=np.uint64),
             l0_bradix_high=bool(r.l0_bradix_high), l0_table_bits=int(r.l0_table_bits),
-            l0_table32=_arr(r.l0_table32, r.l0_table32_len, np.uint32),
-            l0_radix_index=_arr(r.l0_array1, r.l0_array1_len, np.uint64),
-            l0_pivots=_arr(r.l0_array2, r.l0_array2_len, np.uint64),
+            l0_table32=_arr(r.l0_table32, r.l0_table32_len, C.c_uint32, np.uint32, owner),
+            l0_radix_index=_arr(r.l0_array1, r.l0_array1_len, C.c_uint64, np.uint64, owner),
+            l0_pivots=_arr(r.l0_array2, r.l0_array2_len, C.c_uint64, np.uint64, owner),
             l1_model=MODEL_NAMES[int(r.l1_model_id)],
             l1_params=None if params is None else params.reshape(N, ppm),
-            last_layer_max_l1s=_arr(r.l1_errors, N, np.uint64), l1_counts=_arr(r.l1_counts, N, np.uint64),
-            could_not_replace=bool(r.could_not_replace), top_fit_exact=bool(r.top_fit_exact))
-    finally:
-        L.rmi_result_free(res)
+            last_layer_max_l1s=_arr(r.l1_errors, N, C.c_uint64, np.uint64, owner),
+            l1_counts=_arr(r.l1_counts, N, C.c_uint64, np.uint64, owner),
+            could_not_replace=bool(r.could_not_replace), top_fit_exact=bool(r.top_fit_exact), _res=owner)
     return out

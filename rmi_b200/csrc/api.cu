@@ -48,6 +48,13 @@ int device_info(int device, DeviceInfo* out) {
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     cache[device].num_sms = sms;
+    // keep the stream-ordered scratch pool's memory mapped between builds instead of
+    // returning it to the driver at every synchronisation
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
   }
   *out = cache[device];
   return RMI_OK;
@@ -100,13 +107,71 @@ struct rmi_dataset {
   bool owned = false;
 };
 
+// Page-locked host buffers for results: D2H copies land directly in the memory the caller
+// reads (no pageable staging), and freed buffers are recycled because cudaMallocHost /
+// cudaFreeHost cost far more than a build.
+class PinnedCache {
+ public:
+  void* get(size_t bytes) {
+    if (bytes == 0) return nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      size_t best = free_.size();
+      for (size_t i = 0; i < free_.size(); ++i)
+        if (free_[i].second >= bytes && (best == free_.size() || free_[i].second < free_[best].second)) best = i;
+      if (best != free_.size() && free_[best].second <= 2 * bytes + 4096) {
+        auto e = free_[best];
+        free_.erase(free_.begin() + best);
+        live_.push_back(e);
+        return e.first;
+      }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu_);
+    live_.push_back({p, bytes});
+    return p;
+  }
+  void put(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu_);
+    for (size_t i = 0; i < live_.size(); ++i)
+      if (live_[i].first == p) {
+        free_.push_back(live_[i]);
+        live_.erase(live_.begin() + i);
+        break;
+      }
+    while (free_.size() > 16) { cudaFreeHost(free_.front().first); free_.erase(free_.begin()); }
+  }
+ private:
+  std::mutex mu_;
+  std::vector<std::pair<void*, size_t>> free_, live_;
+};
+PinnedCache g_pinned;
+
+template <class P> struct PinnedArray {
+  P* ptr = nullptr;
+  size_t count = 0;
+  bool resize(size_t n) {
+    g_pinned.put(ptr);
+    ptr = (P*)g_pinned.get(n * sizeof(P));
+    count = ptr ? n : 0;
+    return n == 0 || ptr != nullptr;
+  }
+  P* data() { return ptr; }
+  size_t size() const { return count; }
+  bool empty() const { return count == 0; }
+  ~PinnedArray() { g_pinned.put(ptr); }
+};
+
 // The allocation behind an rmi_result: the public struct first, then the owned buffers.
 struct ResultBox {
   rmi_result pub;
-  std::vector<double> l1_params;
-  std::vector<uint64_t> l1_errors, l1_counts;
-  std::vector<uint32_t> table32;
-  std::vector<uint64_t> arr1, arr2;
+  PinnedArray<double> l1_params;
+  PinnedArray<uint64_t> l1_errors, l1_counts;
+  PinnedArray<uint32_t> table32;
+  PinnedArray<uint64_t> arr1, arr2;
+  PinnedArray<char> scalars;   // BuildAux + TopModel read-back
 };
 
 extern "C" {
@@ -265,8 +330,17 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
       d_pivots = A.get<u64>(hist_bins + 1);
       d_ri = A.get<u64>(((size_t)1 << 20) + 1);
     }
+    // pinned host buffers the results are copied into (and that the caller then reads)
+    const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0;
+    bool host_ok = box->scalars.resize(sizeof(BuildAux) + sizeof(TopModel));
+    if (!stats_only)
+      host_ok = host_ok && box->l1_params.resize((size_t)N * ppm) && box->l1_errors.resize(N) && box->l1_counts.resize(N);
+    if (top.kind == M_RADIX_TABLE) host_ok = host_ok && box->table32.resize((size_t)1 << top.table_bits);
+    if (top.kind == M_HISTOGRAM) host_ok = host_ok && box->arr1.resize(((size_t)1 << 20) + 1) && box->arr2.resize(hist_bins);
     if (A.err != cudaSuccess) {
       rc = fail(RMI_ERR_CUDA, std::string("scratch allocation: ") + cudaGetErrorString(A.err));
+    } else if (!host_ok) {
+      rc = fail(RMI_ERR_CUDA, "pinned host allocation for the results failed");
     } else {
       TopModel h_top;
       memset(&h_top, 0, sizeof(h_top));
@@ -289,7 +363,8 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
                                        d_pivots, d_ri);
       cudaEventRecord(evp[0], st);
       if (host_status == 0) {
-        compute_leaf_bounds<T>(L, keys, n, top.kind, d_top, N, d_S, d_aux);
+        // injected top parameters are not known to be monotone: take the streaming pass, which checks
+        compute_leaf_bounds<T>(L, keys, n, top.kind, d_top, N, d_S, d_aux, /*allow_search=*/l0_over == nullptr);
         cudaEventRecord(evp[1], st);
         fit_leaves<T>(L, keys, n, leaf.kind, N, d_S, d_aux, d_params, d_errors, d_counts);
         cudaEventRecord(evp[2], st);
@@ -300,26 +375,20 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
       }
       cudaEventRecord(ev1, st);
       // ---- results to the host --------------------------------------------------------------
-      BuildAux h_aux;
+      BuildAux& h_aux = *reinterpret_cast<BuildAux*>(box->scalars.data());
+      TopModel& h_top_back = *reinterpret_cast<TopModel*>(box->scalars.data() + sizeof(BuildAux));
       memset(&h_aux, 0, sizeof(h_aux));
       cudaMemcpyAsync(&h_aux, d_aux, sizeof(h_aux), cudaMemcpyDeviceToHost, st);
-      cudaMemcpyAsync(&h_top, d_top, sizeof(h_top), cudaMemcpyDeviceToHost, st);
-      const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0;
+      cudaMemcpyAsync(&h_top_back, d_top, sizeof(h_top), cudaMemcpyDeviceToHost, st);
       if (host_status == 0 && !stats_only) {
-        box->l1_params.resize((size_t)N * ppm);
-        box->l1_errors.resize(N);
-        box->l1_counts.resize(N);
         cudaMemcpyAsync(box->l1_params.data(), d_params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(box->l1_errors.data(), d_errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(box->l1_counts.data(), d_counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
       }
       if (host_status == 0 && top.kind == M_RADIX_TABLE) {
-        box->table32.resize((size_t)1 << top.table_bits);
         cudaMemcpyAsync(box->table32.data(), d_table, sizeof(u32) * box->table32.size(), cudaMemcpyDeviceToHost, st);
       }
       if (host_status == 0 && top.kind == M_HISTOGRAM) {
-        box->arr1.resize(((size_t)1 << 20) + 1);
-        box->arr2.resize(hist_bins);
         cudaMemcpyAsync(box->arr1.data(), d_ri, sizeof(u64) * box->arr1.size(), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(box->arr2.data(), d_pivots, sizeof(u64) * hist_bins, cudaMemcpyDeviceToHost, st);
       }
@@ -348,6 +417,7 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
           R.phase_device_ns[q] = (uint64_t)((double)ms * 1e6);
         }
         R.l0_model_id = top.kind;
+        h_top = h_top_back;
         R.l0_bradix_high = h_top.high;
         R.l0_table_bits = top.table_bits;
         switch (top.kind) {

@@ -25,6 +25,33 @@ template <class T> __device__ __forceinline__ u64 run_start(const T* __restrict_
   return lo;
 }
 
+// Four consecutive keys starting at `base` (base % 4 == 0): two 128-bit loads for 8-byte
+// keys, one for 4-byte keys, when the array is 16-byte aligned and all four are in range;
+// scalar loads otherwise (entries past the end repeat the last key).  Returns how many are valid.
+template <class T>
+__device__ __forceinline__ int load_keys4(const T* __restrict__ keys, u64 base, u64 n, bool aligned16, T (&k)[4]) {
+  int cnt = (n - base) < 4ull ? (int)(n - base) : 4;
+  if (cnt == 4 && aligned16) {
+    if (sizeof(T) == 8) {
+      const ulonglong2* p = reinterpret_cast<const ulonglong2*>(keys + base);
+      ulonglong2 a = __ldg(p), b = __ldg(p + 1);
+      u64 raw[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) k[e] = *reinterpret_cast<T*>(&raw[e]);
+    } else {
+      uint4 a = __ldg(reinterpret_cast<const uint4*>(keys + base));
+      u32 raw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) k[e] = *reinterpret_cast<T*>(&raw[e]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) k[e] = keys[base + (u64)(e < cnt ? e : cnt - 1)];
+  }
+  return cnt;
+}
+__device__ __forceinline__ bool is_aligned16(const void* p) { return (reinterpret_cast<unsigned long long>(p) & 15ull) == 0; }
+
 // map_scale! (reference models/mod.rs:238-250): (offset as f64 * sf) as usize when the
 // scale differs from 1.0 by more than f64::EPSILON.
 __device__ __forceinline__ u64 scale_offset(u64 off, double sf, int use_sf) {

@@ -64,7 +64,7 @@ unsigned fit_top_model(const Launch& L, const T* keys, u64 n, int kind, int tabl
 // sortedness and monotonicity and derives the split (two_layer.rs:131-175).
 template <class T>
 void compute_leaf_bounds(const Launch& L, const T* keys, u64 n, int top_kind, const TopModel* d_top, u64 num_leaves,
-                         u64* d_S, BuildAux* d_aux);
+                         u64* d_S, BuildAux* d_aux, bool allow_search);
 // Fused per-leaf pass: closed-form fit (build_models_from), empty-leaf constants, forward
 // pass / max error, lower-bound widening (two_layer.rs:20-99, :186-259,
 // lower_bound_correction.rs:91-137).  Writes N x ppm params, N errors, N counts.

@@ -46,109 +46,189 @@ __global__ void k_fill(u64* __restrict__ p, u64 len, u64 v) {
 }
 
 // S[j] = first index i with min(N-1, top(key_i)) >= j.  S is pre-filled with n.
+// Each thread owns BOUNDS_E consecutive keys (one or two 128-bit loads) plus the key before
+// them, so every key is predicted once (+1 per thread for the neighbour).
+constexpr int BOUNDS_E = 4;
 template <class T, int TOP>
 __global__ void __launch_bounds__(BOUNDS_THREADS)
 k_bounds(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr, u64 N, u64* __restrict__ S,
          BuildAux* aux) {
   TopModel m = *top_ptr;
-  u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    T k = keys[i];
-    u64 p = top_predict<TOP>(m, k);
-    if (!top_needs_bounds_check(TOP) && p >= N) set_status(aux, ST_TOP_OUT_OF_BOUNDS);
-    u64 t = p < N - 1 ? p : N - 1;
-    if (i == 0) {
-      for (u64 q = 0; q <= t; ++q) S[q] = 0;
-    } else {
-      T kp = keys[i - 1];
-      if (k < kp) set_status(aux, ST_NOT_SORTED);
-      u64 pp = top_predict<TOP>(m, kp);
-      u64 tp = pp < N - 1 ? pp : N - 1;
-      if (t < tp) set_status(aux, ST_NON_MONOTONE);
-      for (u64 q = tp + 1; q <= t; ++q) S[q] = i;
+  const bool aligned = is_aligned16(keys);
+  u64 stride = (u64)gridDim.x * blockDim.x * BOUNDS_E;
+  unsigned bad = 0;
+  for (u64 base = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * BOUNDS_E; base < n; base += stride) {
+    T k[BOUNDS_E];
+    int cnt = load_keys4(keys, base, n, aligned, k);
+    T kp = base > 0 ? keys[base - 1] : k[0];
+    u64 pp = top_predict<TOP>(m, kp);
+    u64 tp = pp < N - 1 ? pp : N - 1;
+#pragma unroll
+    for (int e = 0; e < BOUNDS_E; ++e) {
+      if (e >= cnt) break;
+      u64 i = base + e;
+      u64 p = top_predict<TOP>(m, k[e]);
+      if (!top_needs_bounds_check(TOP) && p >= N) bad |= ST_TOP_OUT_OF_BOUNDS;
+      u64 t = p < N - 1 ? p : N - 1;
+      if (i == 0) {
+        for (u64 q = 0; q <= t; ++q) S[q] = 0;
+      } else {
+        if (k[e] < kp) bad |= ST_NOT_SORTED;
+        if (t < tp) bad |= ST_NON_MONOTONE;
+        for (u64 q = tp + 1; q <= t; ++q) S[q] = i;
+      }
+      kp = k[e]; tp = t;
     }
   }
+  if (bad) set_status(aux, bad);
+}
+
+// The same S by N+1 independent binary searches: valid whenever the top prediction is a
+// monotone function of the key (linear family with slope >= 0, radix, radix table, bradix,
+// histogram) — then "first index whose prediction reaches j" is a lower bound over the sorted
+// keys.  ~28 probes per leaf instead of a pass over all n keys; neighbouring leaves share
+// the upper levels of the search in L1/L2.  Sortedness (and with it monotonicity of the
+// targets) is verified by k_leaf, which visits every consecutive key pair anyway.
+template <class T, int TOP>
+__global__ void __launch_bounds__(BOUNDS_THREADS)
+k_bounds_search(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr, u64 N,
+                u64* __restrict__ S) {
+  TopModel m = *top_ptr;
+  u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > N) return;
+  u64 lo = 0, hi = n;
+  if (j == N) lo = n;
+  else if (j > 0) {
+    while (lo < hi) {
+      u64 mid = lo + ((hi - lo) >> 1);
+      if (top_predict<TOP>(m, keys[mid]) >= j) hi = mid; else lo = mid + 1;
+    }
+  }
+  S[j] = lo;
+}
+__host__ __device__ constexpr bool top_is_monotone_by_construction(int kind) {
+  return kind == M_LINEAR || kind == M_ROBUST_LINEAR || kind == M_LINEAR_SPLINE || kind == M_RADIX ||
+         kind == M_RADIX_TABLE || kind == M_BRADIX || kind == M_HISTOGRAM;
 }
 
 // two_layer.rs:131-159
 template <class T, int TOP>
 __global__ void k_split(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr, u64 N,
-                        const u64* __restrict__ S, BuildAux* aux) {
+                        const u64* __restrict__ S, BuildAux* aux, int searched) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  TopModel m = *top_ptr;
+  if (searched && TOP == M_LINEAR && !(m.f[1] >= 0.0)) set_status(aux, ST_NON_MONOTONE);   // slope < 0 or NaN
+  if (!top_needs_bounds_check(TOP) && n > 0 && top_predict<TOP>(m, keys[n - 1]) >= N)
+    set_status(aux, ST_TOP_OUT_OF_BOUNDS);
   u64 split = S[N / 2];
   aux->split_idx = split;
   if (split >= n) { aux->has_split = 0; aux->split_target = 0; return; }
   aux->has_split = 1;
   if (split == 0) set_status(aux, ST_SPLIT_AT_ZERO);
   if (split + 1 >= n) set_status(aux, ST_SPLIT_AT_END);
-  TopModel m = *top_ptr;
   u64 p = top_predict<TOP>(m, keys[split]);
   aux->split_target = p < N - 1 ? p : N - 1;
 }
 
 // ------------------------------------------------------------------------------------------
-// Per-leaf training stream: (key, offset) items in the order train_model sees them.
+// Warp-cooperative key streams.
+//
+// A lane owns one leaf and must visit that leaf's keys strictly in order (the fits are the
+// reference's order-dependent recurrences), but 32 lanes reading 32 different leaves straight
+// from global memory touch 32 different cache lines per instruction.  stream_pass() instead
+// lets the WARP copy, for every lane, the next SW keys of that lane's range into a padded
+// shared-memory row with cp.async (each copy instruction moves two contiguous 128-byte row
+// segments), three chunks deep, and each lane then consumes its own row.  Shared-memory
+// footprint is 32 x SW keys per stage whatever the leaf length, so 8-key and 8-million-key
+// leaves take the same code path, and the keys cross HBM->L2->SM in full lines.
+// ------------------------------------------------------------------------------------------
+constexpr int SW = 16;          // keys per lane per chunk
+constexpr int SROW = SW + 1;    // padded row: 64-bit row reads of a half-warp hit 16 distinct bank pairs
+constexpr int SSTAGES = 3;
+
+template <int BYTES> __device__ __forceinline__ void cp_async_key(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory");
+}
+
+// Calls fn(key, index) for index = b .. e-1 of THIS lane's range, all 32 lanes of the warp
+// taking part in the copies.  Must be called by every lane of the warp (empty ranges allowed).
+template <class T, class Fn>
+__device__ __forceinline__ void stream_pass(const T* __restrict__ keys, T* wbuf, u64 b, u64 e, Fn&& fn) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (e < b) e = b;
+  u64 maxlen = e - b;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    u64 t = __shfl_xor_sync(FULL, maxlen, o);
+    if (t > maxlen) maxlen = t;
+  }
+  if (maxlen == 0) return;
+  const u64 nchunks = (maxlen + SW - 1) / SW;
+  const int sub = lane >> 4, col = lane & 15;   // lane copies key `col` of rows 2q+sub
+  auto issue = [&](u64 c) {
+    T* st = wbuf + (size_t)(c % SSTAGES) * 32 * SROW;
+    const u64 off = c * SW + col;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      int row = 2 * q + sub;
+      u64 rb = __shfl_sync(FULL, b, row), re = __shfl_sync(FULL, e, row);
+      u64 src = rb + off;
+      if (src < re) cp_async_key<sizeof(T)>(st + row * SROW + col, keys + src);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  if (nchunks > 1) issue(1); else cp_async_commit();
+  for (u64 c = 0; c < nchunks; ++c) {
+    if (c + 2 < nchunks) issue(c + 2); else cp_async_commit();   // empty groups keep the count uniform
+    cp_async_wait<2>();
+    __syncwarp();
+    const T* row = wbuf + (size_t)(c % SSTAGES) * 32 * SROW + lane * SROW;
+    u64 base = b + c * SW;
+    int cnt = base < e ? ((e - base) < (u64)SW ? (int)(e - base) : SW) : 0;
+    for (int s = 0; s < cnt; ++s) fn(row[s], base + (u64)s);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-leaf training vector (two_layer.rs:52-82): a contiguous index range [vs, ve) of the key
+// array — [last key of the previous leaf] + own keys + [first key of the next leaf], neither
+// across the half boundary — whose item offsets are the duplicate-fixed global offsets F.
 // ------------------------------------------------------------------------------------------
 template <class T> struct LeafRange {
-  const T* __restrict__ keys;
-  u64 n;
-  u64 lo, hi;          // all keys of the leaf: [S[j], S[j+1])
-  u64 own_lo, own_hi;  // keys in the leaf's training set (the split key excluded)
-  u64 half_lo;         // first index of the leaf's half
-  int mode;            // 0: empty vector, 1: [P] own [Nx], 2: single item keys[half_lo]
-  bool has_prev, has_next;
-  __device__ __forceinline__ u64 vec_len() const {
-    if (mode == 0) return 0;
-    if (mode == 2) return 1;
-    return (own_hi - own_lo) + (has_prev ? 1 : 0) + (has_next ? 1 : 0);
-  }
+  u64 lo, hi;      // all keys of the leaf: [S[j], S[j+1])
+  u64 vs, ve;      // training vector
 };
-
-// Calls fn(key, offset) for every item of the vector (NOT including the drained-iterator
-// repeat).  Offsets are the duplicate-fixed global offsets F.
-template <class T, class Fn> __device__ __forceinline__ void walk_vector(const LeafRange<T>& r, Fn&& fn) {
-  if (r.mode == 0) return;
-  if (r.mode == 2) { fn(r.keys[r.half_lo], run_start(r.keys, r.half_lo)); return; }
-  T pk = T();
-  u64 pF = 0;
-  bool have = false;
-  if (r.own_lo > 0) { pk = r.keys[r.own_lo - 1]; pF = run_start(r.keys, r.own_lo - 1); have = true; }
-  if (r.has_prev) fn(pk, pF);
-  for (u64 i = r.own_lo; i < r.own_hi; ++i) {
-    T k = r.keys[i];
-    u64 F = (have && k == pk) ? pF : i;
-    fn(k, F);
-    pk = k; pF = F; have = true;
-  }
-  if (r.has_next) fn(r.keys[r.own_hi], r.own_hi);
-}
-// First / last raw item of the vector (RMITrainingData::get, models/mod.rs:268-270).
-template <class T> __device__ __forceinline__ void vector_first(const LeafRange<T>& r, T& k, u64& y) {
-  u64 i = r.mode == 2 ? r.half_lo : (r.has_prev ? r.own_lo - 1 : r.own_lo);
-  k = r.keys[i]; y = run_start(r.keys, i);
-}
-template <class T> __device__ __forceinline__ void vector_last(const LeafRange<T>& r, T& k, u64& y) {
-  u64 i = r.mode == 2 ? r.half_lo : (r.has_next ? r.own_hi : r.own_hi - 1);
-  k = r.keys[i]; y = run_start(r.keys, i);
-}
-// Raw item at vector position p (0-based).
-template <class T> __device__ __forceinline__ void vector_at(const LeafRange<T>& r, u64 p, T& k, u64& y) {
-  u64 i = r.mode == 2 ? r.half_lo : (r.has_prev ? r.own_lo - 1 + p : r.own_lo + p);
-  k = r.keys[i]; y = run_start(r.keys, i);
-}
 
 // The reference's Welford step (linear.rs:24-34) with the two count divisions done by
 // div_by_count (rust_math.cuh): bit-identical to IEEE division, 3 FP64 ops instead of ~20.
-struct LeafWelford {
+// CHECKED = false skips div_by_count's range test (integer keys cannot produce operands
+// outside [2^-900, 2^900], and a zero operand is handled exactly by the fast sequence).
+template <bool CHECKED> struct LeafWelford {
   double mean_x, mean_y, c, m2, nf;
+  unsigned ni;
   const double* rcp;
-  __device__ __forceinline__ void init(const double* table) { mean_x = mean_y = c = m2 = nf = 0.0; rcp = table; }
+  __device__ __forceinline__ void init(const double* table) { mean_x = mean_y = c = m2 = nf = 0.0; ni = 0; rcp = table; }
+  __device__ __forceinline__ double dv(double a, double rc) const {
+    if (CHECKED) return div_by_count(a, nf, rc);
+    double q0 = __dmul_rn(a, rc);
+    double rem = __fma_rn(-nf, q0, a);
+    return __fma_rn(rem, rc, q0);
+  }
   __device__ __forceinline__ void push(double x, double y) {
     nf = __dadd_rn(nf, 1.0);
-    double rc = nf < (double)RCP_TABLE ? rcp[(int)nf] : __drcp_rn(nf);
+    ni += 1u;
+    double rc = ni < (unsigned)RCP_TABLE && nf < (double)RCP_TABLE ? rcp[ni] : __drcp_rn(nf);
     double dx = __dadd_rn(x, -mean_x);
-    mean_x = __dadd_rn(mean_x, div_by_count(dx, nf, rc));
-    mean_y = __dadd_rn(mean_y, div_by_count(__dadd_rn(y, -mean_y), nf, rc));
+    mean_x = __dadd_rn(mean_x, dv(dx, rc));
+    mean_y = __dadd_rn(mean_y, dv(__dadd_rn(y, -mean_y), rc));
     c = __dadd_rn(c, __dmul_rn(dx, __dadd_rn(y, -mean_y)));
     double dx2 = __dadd_rn(x, -mean_x);
     m2 = __dadd_rn(m2, __dmul_rn(dx, dx2));
@@ -170,139 +250,177 @@ __device__ __forceinline__ double scale3(double v, double mn, double mx) {
   return __ddiv_rn(__dadd_rn(v, -mn), __dadd_rn(mx, -mn));
 }
 
-// train_model(layer2, vector) for every leaf model type.  f receives Model::params().
+// Item tracker for a pass over a training vector: yields (x, y) with y the duplicate-fixed
+// offset as a double (exact below 2^53), without an int->float conversion per item.
+template <class T> struct ItemTracker {
+  T pk;
+  double pyd, idxd;
+  u64 pF;
+  bool first;
+  __device__ __forceinline__ void init(u64 vs, u64 F0) { first = true; pF = F0; pyd = __ull2double_rn(F0); idxd = __ull2double_rn(vs); pk = T(); }
+  // returns y (double) for item (k, idx); updates state
+  __device__ __forceinline__ double next(T k, u64 idx) {
+    double yd;
+    if (first) { first = false; yd = pyd; }
+    else if (k == pk) { yd = pyd; }
+    else { yd = idxd; pF = idx; }
+    pk = k; pyd = yd;
+    idxd = __dadd_rn(idxd, 1.0);
+    return yd;
+  }
+};
+
+// train_model(layer2, vector) for every leaf model type, as warp-synchronous stream passes.
+// f receives Model::params().  Every lane of the warp must call this (with vs == ve if it has
+// no leaf or an empty vector).
 template <class T, int LEAF>
-__device__ __forceinline__ void fit_leaf(const LeafRange<T>& r, const double* rcp, double* f, BuildAux* aux) {
-  const u64 L = r.vec_len();
+__device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, T* wbuf, const LeafRange<T>& r,
+                                         const double* rcp, double* f, BuildAux* aux) {
+  const u64 L = r.ve - r.vs;
+  const u64 F0 = L ? run_start(keys, r.vs) : 0;
+  constexpr bool CHECKED = Key<T>::is_float;
   if (LEAF == M_LINEAR || LEAF == M_LOGLINEAR) {
     // linear.rs:79-83 / :61-72,169-173 — drained stream: vector + repeat of the final item
-    LeafWelford w;
+    LeafWelford<CHECKED> w;
     w.init(rcp);
-    T lk = T(); u64 ly = 0;
-    walk_vector(r, [&](T k, u64 y) {
-      lk = k; ly = y;
-      double yy = __ull2double_rn(y);
+    ItemTracker<T> it;
+    it.init(r.vs, F0);
+    stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64 idx) {
+      double yy = it.next(k, idx);
       if (LEAF == M_LOGLINEAR) { yy = log(yy); if (!isfinite(yy)) return; }
       w.push(Key<T>::as_float(k), yy);
     });
     if (L > 0) {
-      double yy = __ull2double_rn(ly);
+      double yy = it.pyd;
       if (LEAF == M_LOGLINEAR) yy = log(yy);
-      if (LEAF == M_LINEAR || isfinite(yy)) w.push(Key<T>::as_float(lk), yy);
+      if (LEAF == M_LINEAR || isfinite(yy)) w.push(Key<T>::as_float(it.pk), yy);
     }
     if (!w.finish(f[0], f[1])) set_status(aux, ST_NEG_VARIANCE);
   } else if (LEAF == M_ROBUST_LINEAR) {
     // linear.rs:239-260 — skip(bnd).take(len - 2*bnd): never drains the iterator
-    if (L == 0) { f[0] = 0.0; f[1] = 0.0; return; }
     u64 bnd = f64_to_u64_sat(__dmul_rn(__ull2double_rn(L), 0.0001));
     if (bnd < 1) bnd = 1;
-    if (!(bnd * 2 + 1 < L)) { set_status(aux, ST_ROBUST_TOO_SMALL); f[0] = 0.0; f[1] = 0.0; return; }
-    LeafWelford w;
+    bool ok = L == 0 || (bnd * 2 + 1 < L);
+    if (!ok) set_status(aux, ST_ROBUST_TOO_SMALL);
+    LeafWelford<CHECKED> w;
     w.init(rcp);
+    ItemTracker<T> it;
+    it.init(r.vs, F0);
     u64 pos = 0;
-    walk_vector(r, [&](T k, u64 y) {
-      if (pos >= bnd && pos < L - bnd) w.push(Key<T>::as_float(k), __ull2double_rn(y));
+    stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64 idx) {
+      double yy = it.next(k, idx);
+      if (ok && pos >= bnd && pos < L - bnd) w.push(Key<T>::as_float(k), yy);
       ++pos;
     });
-    if (!w.finish(f[0], f[1])) set_status(aux, ST_NEG_VARIANCE);
+    if (L == 0 || !ok) { f[0] = 0.0; f[1] = 0.0; }
+    else if (!w.finish(f[0], f[1])) set_status(aux, ST_NEG_VARIANCE);
   } else if (LEAF == M_LINEAR_SPLINE || LEAF == M_CUBIC) {
-    // linear_spline.rs:13-35
+    // linear_spline.rs:13-35 on the raw first / last items of the vector
     double la, lb;
-    T k0 = T(), k1 = T(); u64 y0 = 0, y1 = 0;
-    if (L > 0) { vector_first(r, k0, y0); vector_last(r, k1, y1); }
+    T k0 = T(), k1 = T();
+    double y0 = 0.0, y1 = 0.0;
+    if (L > 0) {
+      k0 = keys[r.vs]; y0 = __ull2double_rn(F0);
+      k1 = keys[r.ve - 1]; y1 = __ull2double_rn(run_start(keys, r.ve - 1));
+    }
     if (L == 0) { la = 0.0; lb = 0.0; }
-    else if (L == 1 || k0 == k1) { la = __ull2double_rn(y0); lb = 0.0; }
+    else if (L == 1 || k0 == k1) { la = y0; lb = 0.0; }
     else {
       double x0 = Key<T>::as_float(k0), x1 = Key<T>::as_float(k1);
-      double slope = __ddiv_rn(__dadd_rn(__ull2double_rn(y0), -__ull2double_rn(y1)), __dadd_rn(x0, -x1));
-      la = __dadd_rn(__ull2double_rn(y0), -__dmul_rn(slope, x0));
+      double slope = __ddiv_rn(__dadd_rn(y0, -y1), __dadd_rn(x0, -x1));
+      la = __dadd_rn(y0, -__dmul_rn(slope, x0));
       lb = slope;
     }
     if (LEAF == M_LINEAR_SPLINE) { f[0] = la; f[1] = lb; return; }
     // cubic_spline.rs:18-101
+    const double xmin = Key<T>::as_float(k0), ymin = y0, xmax = Key<T>::as_float(k1), ymax = y1;
+    bool uniq = false, found1 = false;
+    double sxn = 0.0, syn = 0.0;
+    {
+      ItemTracker<T> it;
+      it.init(r.vs, F0);
+      stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64 idx) {
+        double yy = it.next(k, idx);
+        if (k != k0) uniq = true;
+        if (!found1) {
+          double sx = scale3(Key<T>::as_float(k), xmin, xmax);
+          if (sx > 0.0) { found1 = true; sxn = sx; syn = scale3(yy, ymin, ymax); }
+        }
+      });
+    }
     double a, b, c, d;
     if (L == 0) { a = 0.0; b = 0.0; c = 1.0; d = 0.0; }
+    else if (L == 1 || !uniq) { a = b = c = 0.0; d = y0; }
     else {
-      bool uniq = false;
-      if (L > 1) walk_vector(r, [&](T k, u64) { if (k != k0) uniq = true; });
-      if (L == 1 || !uniq) { a = b = c = 0.0; d = __ull2double_rn(y0); }
+      bool found2 = false;
+      double sxp = 0.0, syp = 0.0;
+      for (u64 p = r.ve; p-- > r.vs;) {   // from the back; almost always the second-to-last item
+        double sx = scale3(Key<T>::as_float(keys[p]), xmin, xmax);
+        if (sx < 1.0) { found2 = true; sxp = sx; syp = scale3(__ull2double_rn(run_start(keys, p)), ymin, ymax); break; }
+      }
+      if (!found1 || !found2) { set_status(aux, ST_CUBIC_UNWRAP); a = b = c = d = 0.0; }
       else {
-        double xmin = Key<T>::as_float(k0), ymin = __ull2double_rn(y0);
-        double xmax = Key<T>::as_float(k1), ymax = __ull2double_rn(y1);
-        bool found1 = false; double sxn = 0.0, syn = 0.0;
-        walk_vector(r, [&](T k, u64 y) {
-          if (found1) return;
-          double sx = scale3(Key<T>::as_float(k), xmin, xmax);
-          if (sx > 0.0) { found1 = true; sxn = sx; syn = scale3(__ull2double_rn(y), ymin, ymax); }
-        });
-        bool found2 = false; double sxp = 0.0, syp = 0.0;
-        for (u64 p = L; p-- > 0;) {
-          T k; u64 y;
-          vector_at(r, p, k, y);
-          double sx = scale3(Key<T>::as_float(k), xmin, xmax);
-          if (sx < 1.0) { found2 = true; sxp = sx; syp = scale3(__ull2double_rn(y), ymin, ymax); break; }
+        double m1 = __ddiv_rn(syn, sxn);
+        double m2 = __ddiv_rn(__dadd_rn(1.0, -syp), __dadd_rn(1.0, -sxp));
+        double ss = __dadd_rn(__dmul_rn(m1, m1), __dmul_rn(m2, m2));
+        if (ss > 9.0) {
+          double tau = __ddiv_rn(3.0, __dsqrt_rn(ss));
+          m1 = __dmul_rn(m1, tau);
+          m2 = __dmul_rn(m2, tau);
         }
-        if (!found1 || !found2) { set_status(aux, ST_CUBIC_UNWRAP); a = b = c = d = 0.0; }
-        else {
-          double m1 = __ddiv_rn(syn, sxn);
-          double m2 = __ddiv_rn(__dadd_rn(1.0, -syp), __dadd_rn(1.0, -sxp));
-          double ss = __dadd_rn(__dmul_rn(m1, m1), __dmul_rn(m2, m2));
-          if (ss > 9.0) {
-            double tau = __ddiv_rn(3.0, __dsqrt_rn(ss));
-            m1 = __dmul_rn(m1, tau);
-            m2 = __dmul_rn(m2, tau);
-          }
-          double d3 = cube_dd(__dadd_rn(xmax, -xmin));
-          a = __ddiv_rn(__dadd_rn(__dadd_rn(m1, m2), -2.0), d3);
-          double t1 = __dmul_rn(xmax, __dadd_rn(__dadd_rn(__dmul_rn(2.0, m1), m2), -3.0));
-          double t2 = __dmul_rn(xmin, __dadd_rn(__dadd_rn(m1, __dmul_rn(2.0, m2)), -3.0));
-          b = __ddiv_rn(-__dadd_rn(t1, t2), d3);
-          double xmax2 = __dmul_rn(xmax, xmax), xmin2 = __dmul_rn(xmin, xmin);
-          double u1 = __dmul_rn(m1, xmax2), u2 = __dmul_rn(m2, xmin2);
-          double u3 = __dmul_rn(__dmul_rn(xmax, xmin),
-                                __dadd_rn(__dadd_rn(__dmul_rn(2.0, m1), __dmul_rn(2.0, m2)), -6.0));
-          c = __ddiv_rn(__dadd_rn(__dadd_rn(u1, u2), u3), d3);
-          double v2 = __dmul_rn(__dmul_rn(xmax, xmin), __dadd_rn(m2, -3.0));
-          d = __ddiv_rn(__dmul_rn(-xmin, __dadd_rn(__dadd_rn(u1, v2), xmin2)), d3);
-          double dy = __dadd_rn(ymax, -ymin);
-          a = __dmul_rn(a, dy); b = __dmul_rn(b, dy); c = __dmul_rn(c, dy); d = __dmul_rn(d, dy);
-          d = __dadd_rn(d, ymin);
-        }
+        double d3 = cube_dd(__dadd_rn(xmax, -xmin));
+        a = __ddiv_rn(__dadd_rn(__dadd_rn(m1, m2), -2.0), d3);
+        double t1 = __dmul_rn(xmax, __dadd_rn(__dadd_rn(__dmul_rn(2.0, m1), m2), -3.0));
+        double t2 = __dmul_rn(xmin, __dadd_rn(__dadd_rn(m1, __dmul_rn(2.0, m2)), -3.0));
+        b = __ddiv_rn(-__dadd_rn(t1, t2), d3);
+        double xmax2 = __dmul_rn(xmax, xmax), xmin2 = __dmul_rn(xmin, xmin);
+        double u1 = __dmul_rn(m1, xmax2), u2 = __dmul_rn(m2, xmin2);
+        double u3 = __dmul_rn(__dmul_rn(xmax, xmin),
+                              __dadd_rn(__dadd_rn(__dmul_rn(2.0, m1), __dmul_rn(2.0, m2)), -6.0));
+        c = __ddiv_rn(__dadd_rn(__dadd_rn(u1, u2), u3), d3);
+        double v2 = __dmul_rn(__dmul_rn(xmax, xmin), __dadd_rn(m2, -3.0));
+        d = __ddiv_rn(__dmul_rn(-xmin, __dadd_rn(__dadd_rn(u1, v2), xmin2)), d3);
+        double dy = __dadd_rn(ymax, -ymin);
+        a = __dmul_rn(a, dy); b = __dmul_rn(b, dy); c = __dmul_rn(c, dy); d = __dmul_rn(d, dy);
+        d = __dadd_rn(d, ymin);
       }
     }
     // cubic_spline.rs:113-135: keep the linear spline if its L1 error is strictly lower
     double cf[4] = {a, b, c, d}, lf[2] = {la, lb};
     double our_error = 0.0, lin_error = 0.0;
-    T lk = T(); u64 ly = 0;
-    auto acc = [&](T k, u64 y) {
-      double x = Key<T>::as_float(k), yy = __ull2double_rn(y);
-      our_error = __dadd_rn(our_error, fabs(__dadd_rn(predict_float<M_CUBIC>(cf, x), -yy)));
-      lin_error = __dadd_rn(lin_error, fabs(__dadd_rn(predict_float<M_LINEAR>(lf, x), -yy)));
-      lk = k; ly = y;
-    };
-    walk_vector(r, acc);
-    if (L > 0) acc(lk, ly);
+    {
+      ItemTracker<T> it;
+      it.init(r.vs, F0);
+      auto acc = [&](double x, double yy) {
+        our_error = __dadd_rn(our_error, fabs(__dadd_rn(predict_float<M_CUBIC>(cf, x), -yy)));
+        lin_error = __dadd_rn(lin_error, fabs(__dadd_rn(predict_float<M_LINEAR>(lf, x), -yy)));
+      };
+      stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64 idx) { acc(Key<T>::as_float(k), it.next(k, idx)); });
+      if (L > 0) acc(Key<T>::as_float(it.pk), it.pyd);
+    }
     if (lin_error < our_error) { f[0] = 0.0; f[1] = 0.0; f[2] = lb; f[3] = la; }
     else { f[0] = a; f[1] = b; f[2] = c; f[3] = d; }
   } else {  // M_NORMAL / M_LOGNORMAL — normal.rs:28-76
     double scale = -INFINITY, mean = 0.0, stdev = 0.0;
-    double nf = __ull2double_rn(L);
-    T lk = T(); u64 ly = 0;
+    const double nf = __ull2double_rn(L);
     auto tx = [&](T k) {
       double x = Key<T>::as_float(k);
       if (LEAF == M_LOGNORMAL) { double l = log(x); x = isfinite(l) ? l : 0.0; }
       return x;
     };
-    auto p1 = [&](T k, u64 y) {
+    ItemTracker<T> it;
+    it.init(r.vs, F0);
+    stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64 idx) {
+      double yy = it.next(k, idx);
       mean = __dadd_rn(mean, __ddiv_rn(tx(k), nf));
-      scale = rust_fmax(scale, __ull2double_rn(y));
-      lk = k; ly = y;
-    };
-    walk_vector(r, p1);
-    if (L > 0) p1(lk, ly);
-    auto p2 = [&](T k, u64) { double dlt = __dadd_rn(tx(k), -mean); stdev = __dadd_rn(stdev, __dmul_rn(dlt, dlt)); };
-    walk_vector(r, p2);
-    if (L > 0) p2(lk, ly);
+      scale = rust_fmax(scale, yy);
+    });
+    if (L > 0) { mean = __dadd_rn(mean, __ddiv_rn(tx(it.pk), nf)); scale = rust_fmax(scale, it.pyd); }
+    stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64) {
+      double dlt = __dadd_rn(tx(k), -mean);
+      stdev = __dadd_rn(stdev, __dmul_rn(dlt, dlt));
+    });
+    if (L > 0) { double dlt = __dadd_rn(tx(it.pk), -mean); stdev = __dadd_rn(stdev, __dmul_rn(dlt, dlt)); }
     stdev = __dsqrt_rn(__ddiv_rn(stdev, nf));
     f[0] = mean; f[1] = stdev; f[2] = scale;
   }
@@ -319,77 +437,98 @@ template <int LEAF> __device__ __forceinline__ bool set_constant(double* f, u64 
   return false;
 }
 
+// Model::predict_to_int (models/mod.rs:735-737) = max(0, floor(p)) as u64.  The conversion
+// instruction with round-toward-minus-infinity saturates exactly like Rust's cast (negative
+// -> 0, too large -> u64::MAX), so floor + clamp + cast is one instruction plus a NaN select.
+template <int LEAF> __device__ __forceinline__ u64 leaf_predict(const double* f, double x) {
+  double p = predict_float<LEAF>(f, x);
+  u64 v = (u64)__double2ull_rd(p);
+  return p != p ? 0ull : v;   // the conversion maps NaN to 2^63; Rust's cast maps it to 0
+}
+
+constexpr size_t leaf_smem_bytes(size_t key_size) {
+  return (size_t)RCP_TABLE * sizeof(double) + (size_t)(LEAF_THREADS / 32) * SSTAGES * 32 * SROW * key_size;
+}
+
 template <class T, int LEAF>
 __global__ void __launch_bounds__(LEAF_THREADS)
 k_leaf(const T* __restrict__ keys, u64 n, u64 N, const u64* __restrict__ S, BuildAux* aux,
        double* __restrict__ params, u64* __restrict__ errors, u64* __restrict__ counts) {
-  __shared__ double s_rcp[RCP_TABLE];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_rcp = reinterpret_cast<double*>(smem_raw);
+  T* wbuf = reinterpret_cast<T*>(smem_raw + (size_t)RCP_TABLE * sizeof(double)) +
+            (size_t)(threadIdx.x >> 5) * SSTAGES * 32 * SROW;
   for (int c = threadIdx.x; c < RCP_TABLE; c += blockDim.x) s_rcp[c] = c ? __drcp_rn((double)c) : 0.0;
   __syncthreads();
-  u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
+  const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = j < N;
   constexpr int PPM = leaf_params_per_model(LEAF);
 
   LeafRange<T> r;
-  r.keys = keys; r.n = n;
-  r.lo = S[j]; r.hi = S[j + 1];
+  r.lo = live ? S[j] : 0;
+  r.hi = live ? S[j + 1] : 0;
+  unsigned bad = 0;
+  if (r.hi < r.lo) { bad |= ST_NOT_SORTED; r.hi = r.lo; }   // cannot happen on sorted keys
   // which half does leaf j belong to (two_layer.rs:147-175)
-  u64 half_hi, first_leaf;
+  u64 half_lo, half_hi, first_leaf;
   if (aux->has_split) {
     u64 split = aux->split_idx, st = aux->split_target;
-    if (j < st) { r.half_lo = 0; half_hi = split; first_leaf = 0; }
-    else { r.half_lo = split + 1; half_hi = n; first_leaf = st; }
-  } else { r.half_lo = 0; half_hi = n; first_leaf = 0; }
-  r.own_lo = r.lo > r.half_lo ? r.lo : r.half_lo;
-  r.own_hi = r.hi < half_hi ? r.hi : half_hi;
-  if (r.own_hi > r.own_lo) {
-    r.mode = 1;
-    r.has_prev = r.own_lo > r.half_lo;
-    r.has_next = r.own_hi < half_hi;
-  } else {
-    r.own_hi = r.own_lo;
-    r.has_prev = r.has_next = false;
-    // the half's first leaf, if it owns no key, is trained on the half's first item alone
-    // (two_layer.rs:52-62 with an empty second_layer_data); other empty leaves on empty data.
-    r.mode = (j == first_leaf && r.half_lo < half_hi) ? 2 : 0;
+    if (j < st) { half_lo = 0; half_hi = split; first_leaf = 0; }
+    else { half_lo = split + 1; half_hi = n; first_leaf = st; }
+  } else { half_lo = 0; half_hi = n; first_leaf = 0; }
+  {
+    u64 own_lo = r.lo > half_lo ? r.lo : half_lo;
+    u64 own_hi = r.hi < half_hi ? r.hi : half_hi;
+    if (live && own_hi > own_lo) {
+      r.vs = own_lo > half_lo ? own_lo - 1 : own_lo;     // + last key of the previous leaf
+      r.ve = own_hi < half_hi ? own_hi + 1 : own_hi;     // + first key of the next leaf
+    } else if (live && j == first_leaf && half_lo < half_hi) {
+      // the half's first leaf, if it owns no key, is trained on the half's first item alone
+      // (two_layer.rs:52-62 with an empty second_layer_data); other empty leaves on empty data
+      r.vs = half_lo; r.ve = half_lo + 1;
+    } else { r.vs = r.ve = 0; }
   }
 
   double f[4] = {0.0, 0.0, 0.0, 0.0};
-  fit_leaf<T, LEAF>(r, s_rcp, f, aux);
+  fit_leaf<T, LEAF>(keys, wbuf, r, s_rcp, f, aux);
 
   // two_layer.rs:186-197: empty leaves (lower-bound-correction sense) except the last
-  const u64 next_idx = S[j + 1];                                  // lb.next_index(j)
-  if (j + 1 < N && r.lo == r.hi) {
+  const u64 next_idx = live ? S[j + 1] : 0;                        // lb.next_index(j)
+  if (live && j + 1 < N && r.lo == r.hi) {
     if (!set_constant<LEAF>(f, next_idx)) atomicAdd(&aux->could_not_replace, 1ull);
   }
 
   // two_layer.rs:207-217 forward pass over the leaf's own keys + longest run
   // (lower_bound_correction.rs:101-119: a run is recorded when the NEXT run starts, so the
   // data set's final run never is)
+  const T prev_key = (live && r.lo > 0) ? keys[r.lo - 1] : Key<T>::zero_value();
   u64 max_err = 0, run_max = 0;
   {
-    T pk = T();
+    T pk = prev_key;
+    bool have_pk = live && r.lo > 0;
     u64 F = r.lo, run = 0;
-    for (u64 i = r.lo; i < r.hi; ++i) {
-      T k = keys[i];
-      if (i == r.lo || k != pk) { if (run > run_max) run_max = run; run = 1; F = i; pk = k; }
+    stream_pass(keys, wbuf, r.lo, r.hi, [&](T k, u64 i) {
+      if (have_pk && k < pk) bad |= ST_NOT_SORTED;
+      if (i == r.lo || k != pk) { if (run > run_max) run_max = run; run = 1; F = i; }
       else run += 1;
-      u64 pred = predict_int_f<LEAF>(f, Key<T>::as_float(k));
+      pk = k; have_pk = true;
+      u64 pred = leaf_predict<LEAF>(f, Key<T>::as_float(k));
       u64 e = error_between(pred, F, n);
       if (e > max_err) max_err = e;
-    }
+    });
     if (r.hi < n && run > run_max) run_max = run;
   }
+  if (bad) set_status(aux, bad);
+  if (!live) return;
   u64 cnt = r.hi - r.lo;
   if (r.hi == n && r.lo < r.hi) cnt += 1;   // the drained iterator's repeated final item
 
   // two_layer.rs:226-259 widening
   T next_key = next_idx < n ? keys[next_idx] : Key<T>::max_value();
-  T prev_key = r.lo > 0 ? keys[r.lo - 1] : Key<T>::zero_value();
   u64 first_idx = j == 0 ? S[1] : r.lo;                            // lb.next_index(max(j-1, 0))
-  u64 up = predict_int_f<LEAF>(f, Key<T>::as_float(Key<T>::minus_epsilon(next_key)));
+  u64 up = leaf_predict<LEAF>(f, Key<T>::as_float(Key<T>::minus_epsilon(next_key)));
   u64 upper_error = error_between(up, next_idx + 1, n);
-  u64 lp = predict_int_f<LEAF>(f, Key<T>::as_float(Key<T>::plus_epsilon(prev_key)));
+  u64 lp = leaf_predict<LEAF>(f, Key<T>::as_float(Key<T>::plus_epsilon(prev_key)));
   u64 lower_error = error_between(lp, first_idx, n);
   u64 new_err = max_err;
   if (upper_error > new_err) new_err = upper_error;
@@ -459,17 +598,39 @@ k_stats_partial(u64 n, u64 N, const u64* __restrict__ errors, const u64* __restr
     out[blockIdx.x] = p;
   }
 }
-__global__ void k_stats_finish(const StatsPartial* __restrict__ parts, int nblocks, BuildAux* aux) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(STATS_THREADS)
+k_stats_finish(const StatsPartial* __restrict__ parts, int nblocks, BuildAux* aux) {
+  __shared__ double smd[32];
+  __shared__ u64 smu[32];
+  __shared__ u64 sme[32], smi[32];
   u64 me = 0, mi = 0, sne = 0;
   double l2 = 0.0, lg = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
     stats_merge(me, mi, parts[b].max_err, parts[b].max_idx);
     sne += parts[b].sum_ne;
     l2 += parts[b].l2;
     lg += parts[b].lg;
   }
-  aux->max_error = me; aux->max_error_idx = mi; aux->sum_n_err = sne; aux->sum_l2 = l2; aux->sum_log2 = lg;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    u64 oe = __shfl_down_sync(0xffffffffu, me, o), oi = __shfl_down_sync(0xffffffffu, mi, o);
+    stats_merge(me, mi, oe, oi);
+  }
+  if (lane == 0) { sme[w] = me; smi[w] = mi; }
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    me = lane < nw ? sme[lane] : 0; mi = lane < nw ? smi[lane] : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      u64 oe = __shfl_down_sync(0xffffffffu, me, o), oi = __shfl_down_sync(0xffffffffu, mi, o);
+      stats_merge(me, mi, oe, oi);
+    }
+  }
+  u64 r_ne = block_sum_u64(sne, smu);
+  double r_l2 = block_sum(l2, smd), r_lg = block_sum(lg, smd);
+  if (threadIdx.x == 0) {
+    aux->max_error = me; aux->max_error_idx = mi; aux->sum_n_err = r_ne; aux->sum_l2 = r_l2; aux->sum_log2 = r_lg;
+  }
 }
 
 int grid_cap(u64 n, int threads, int cap) {
@@ -480,12 +641,21 @@ int grid_cap(u64 n, int threads, int cap) {
 }
 
 template <class T, int TOP>
-void launch_bounds(const Launch& L, const T* keys, u64 n, const TopModel* d_top, u64 N, u64* d_S, BuildAux* d_aux) {
+void launch_bounds_impl(const Launch& L, const T* keys, u64 n, const TopModel* d_top, u64 N, u64* d_S, BuildAux* d_aux,
+                   bool allow_search) {
+  if (allow_search && top_is_monotone_by_construction(TOP)) {
+    k_bounds_search<T, TOP><<<(unsigned)((N + 1 + BOUNDS_THREADS - 1) / BOUNDS_THREADS), BOUNDS_THREADS, 0, L.stream>>>(
+        keys, n, d_top, N, d_S);
+    count_launch();
+    k_split<T, TOP><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux, 1);
+    count_launch();
+    return;
+  }
   k_fill<<<grid_cap(N + 1, BOUNDS_THREADS, L.num_sms * 8), BOUNDS_THREADS, 0, L.stream>>>(d_S, N + 1, n);
   count_launch();
-  k_bounds<T, TOP><<<grid_cap(n, BOUNDS_THREADS, L.num_sms * 8), BOUNDS_THREADS, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux);
+  k_bounds<T, TOP><<<grid_cap((n + BOUNDS_E - 1) / BOUNDS_E, BOUNDS_THREADS, L.num_sms * 8), BOUNDS_THREADS, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux);
   count_launch();
-  k_split<T, TOP><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux);
+  k_split<T, TOP><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux, 0);
   count_launch();
 }
 
@@ -493,7 +663,9 @@ template <class T, int LEAF>
 void launch_leaf(const Launch& L, const T* keys, u64 n, u64 N, const u64* d_S, BuildAux* d_aux, double* d_params,
                  u64* d_errors, u64* d_counts) {
   u64 blocks = (N + LEAF_THREADS - 1) / LEAF_THREADS;
-  k_leaf<T, LEAF><<<(unsigned)blocks, LEAF_THREADS, 0, L.stream>>>(keys, n, N, d_S, d_aux, d_params, d_errors, d_counts);
+  constexpr size_t smem = leaf_smem_bytes(sizeof(T));
+  cudaFuncSetAttribute(k_leaf<T, LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_leaf<T, LEAF><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, n, N, d_S, d_aux, d_params, d_errors, d_counts);
   count_launch();
 }
 
@@ -501,19 +673,19 @@ void launch_leaf(const Launch& L, const T* keys, u64 n, u64 N, const u64* d_S, B
 
 template <class T>
 void compute_leaf_bounds(const Launch& L, const T* keys, u64 n, int top_kind, const TopModel* d_top, u64 N, u64* d_S,
-                         BuildAux* d_aux) {
+                         BuildAux* d_aux, bool allow_search) {
   switch (top_kind) {
     case M_LINEAR:
     case M_ROBUST_LINEAR:
-    case M_LINEAR_SPLINE: launch_bounds<T, M_LINEAR>(L, keys, n, d_top, N, d_S, d_aux); break;
-    case M_CUBIC: launch_bounds<T, M_CUBIC>(L, keys, n, d_top, N, d_S, d_aux); break;
-    case M_LOGLINEAR: launch_bounds<T, M_LOGLINEAR>(L, keys, n, d_top, N, d_S, d_aux); break;
-    case M_NORMAL: launch_bounds<T, M_NORMAL>(L, keys, n, d_top, N, d_S, d_aux); break;
-    case M_LOGNORMAL: launch_bounds<T, M_LOGNORMAL>(L, keys, n, d_top, N, d_S, d_aux); break;
-    case M_RADIX: launch_bounds<T, M_RADIX>(L, keys, n, d_top, N, d_S, d_aux); break;
-    case M_RADIX_TABLE: launch_bounds<T, M_RADIX_TABLE>(L, keys, n, d_top, N, d_S, d_aux); break;
-    case M_BRADIX: launch_bounds<T, M_BRADIX>(L, keys, n, d_top, N, d_S, d_aux); break;
-    case M_HISTOGRAM: launch_bounds<T, M_HISTOGRAM>(L, keys, n, d_top, N, d_S, d_aux); break;
+    case M_LINEAR_SPLINE: launch_bounds_impl<T, M_LINEAR>(L, keys, n, d_top, N, d_S, d_aux, allow_search); break;
+    case M_CUBIC: launch_bounds_impl<T, M_CUBIC>(L, keys, n, d_top, N, d_S, d_aux, allow_search); break;
+    case M_LOGLINEAR: launch_bounds_impl<T, M_LOGLINEAR>(L, keys, n, d_top, N, d_S, d_aux, allow_search); break;
+    case M_NORMAL: launch_bounds_impl<T, M_NORMAL>(L, keys, n, d_top, N, d_S, d_aux, allow_search); break;
+    case M_LOGNORMAL: launch_bounds_impl<T, M_LOGNORMAL>(L, keys, n, d_top, N, d_S, d_aux, allow_search); break;
+    case M_RADIX: launch_bounds_impl<T, M_RADIX>(L, keys, n, d_top, N, d_S, d_aux, allow_search); break;
+    case M_RADIX_TABLE: launch_bounds_impl<T, M_RADIX_TABLE>(L, keys, n, d_top, N, d_S, d_aux, allow_search); break;
+    case M_BRADIX: launch_bounds_impl<T, M_BRADIX>(L, keys, n, d_top, N, d_S, d_aux, allow_search); break;
+    case M_HISTOGRAM: launch_bounds_impl<T, M_HISTOGRAM>(L, keys, n, d_top, N, d_S, d_aux, allow_search); break;
     default: break;
   }
 }
@@ -540,12 +712,12 @@ void leaf_statistics(const Launch& L, u64 n, u64 N, const u64* d_errors, const u
   int g = grid_cap(N, STATS_THREADS, STATS_MAX_BLOCKS);
   k_stats_partial<<<g, STATS_THREADS, 0, L.stream>>>(n, N, d_errors, d_counts, (StatsPartial*)scratch);
   count_launch();
-  k_stats_finish<<<1, 32, 0, L.stream>>>((const StatsPartial*)scratch, g, d_aux);
+  k_stats_finish<<<1, STATS_THREADS, 0, L.stream>>>((const StatsPartial*)scratch, g, d_aux);
   count_launch();
 }
 
 #define INST(T)                                                                                                  \
-  template void compute_leaf_bounds<T>(const Launch&, const T*, u64, int, const TopModel*, u64, u64*, BuildAux*); \
+  template void compute_leaf_bounds<T>(const Launch&, const T*, u64, int, const TopModel*, u64, u64*, BuildAux*, bool); \
   template void fit_leaves<T>(const Launch&, const T*, u64, int, u64, const u64*, BuildAux*, double*, u64*, u64*);
 INST(u64)
 INST(u32)

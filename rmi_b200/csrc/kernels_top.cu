@@ -40,21 +40,57 @@ __device__ __forceinline__ void stream_item(const T* __restrict__ keys, u64 i, d
 // ------------------------------------------------------------------------------------------
 template <class T, int MODE>
 __global__ void __launch_bounds__(TOP_THREADS)
-k_slr_partial(const T* __restrict__ keys, u64 i0, u64 i1, double sf, int use_sf, double* __restrict__ partials) {
+k_slr_partial(const T* __restrict__ keys, u64 n, u64 i0, u64 i1, double sf, int use_sf,
+              double* __restrict__ partials) {
   __shared__ double sm[32];
   u64 mid = i0 + ((i1 - i0) >> 1);
   double px = Key<T>::as_float(keys[mid]);
   double py = MODE == 0 ? __ull2double_rn(scale_offset(mid, sf, use_sf)) : 0.0;
   double sx = 0, sy = 0, sxx = 0, sxy = 0, cnt = 0;
-  u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = i0 + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += stride) {
-    double x; u64 yi;
-    stream_item(keys, i, sf, use_sf, x, yi);
-    double y = __ull2double_rn(yi);
-    if (MODE == 1) { y = log(y); if (!isfinite(y)) continue; }
-    double dx = x - px, dy = y - py;
-    sx += dx; sy += dy; sxx += dx * dx; sxy += dx * dy; cnt += 1.0;
+  const bool aligned = is_aligned16(keys);
+  // each thread owns 4 consecutive keys per trip (128-bit loads); [i0, i1) is covered from the
+  // 4-aligned index at or below i0
+  u64 stride = (u64)gridDim.x * blockDim.x * 4;
+  unsigned icnt = 0;
+  for (u64 base = (i0 & ~3ull) + ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < i1; base += stride) {
+    T k[4];
+    int c = load_keys4(keys, base, n, aligned, k);
+    bool interior = MODE == 0 && c == 4 && base >= i0 && base + 4 <= i1;
+    if (interior) {
+      bool dup = (base > 0 && keys[base - 1] == k[0]) || k[1] == k[0] || k[2] == k[1] || k[3] == k[2];
+      if (!dup) {
+        // fast path: every key starts its own run, so the offset of key e is base + e and the
+        // scaled target floor(offset * sf) is taken with the 2^52 trick (0 <= value < 2^51)
+        double bd = __ull2double_rn(base);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          double x = Key<T>::as_float(k[e]);
+          double y = bd + (double)e;
+          if (use_sf) y = __dadd_rn(__dadd_rd(__dmul_rn(y, sf), 4503599627370496.0), -4503599627370496.0);
+          double dx = x - px, dy = y - py;
+          sx += dx; sy += dy; sxx = fma(dx, dx, sxx); sxy = fma(dx, dy, sxy);
+        }
+        icnt += 4;
+        continue;
+      }
+    }
+    // general path: duplicates, range edges, log targets
+    u64 F = run_start(keys, base);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e >= c) break;
+      u64 i = base + e;
+      if (e > 0 && k[e] != k[e - 1]) F = i;
+      if (i < i0 || i >= i1) continue;
+      double x = Key<T>::as_float(k[e]);
+      double y = __ull2double_rn(scale_offset(F, sf, use_sf));
+      if (MODE == 1) { y = log(y); if (!isfinite(y)) continue; }
+      double dx = x - px, dy = y - py;
+      sx += dx; sy += dy; sxx = fma(dx, dx, sxx); sxy = fma(dx, dy, sxy);
+      icnt += 1;
+    }
   }
+  cnt = (double)icnt;
   double r0 = block_sum(sx, sm), r1 = block_sum(sy, sm), r2 = block_sum(sxx, sm), r3 = block_sum(sxy, sm),
          r4 = block_sum(cnt, sm);
   if (threadIdx.x == 0) {
@@ -633,8 +669,8 @@ unsigned fit_top_model(const Launch& L, const T* keys, u64 n, int kind, int tabl
       if (kind == M_LOGLINEAR) {
         if (exact) { k_slr_exact<T, 1><<<1, 32, 0, st>>>(keys, i0, i1, repeat, sf, use_sf, d_top, d_aux); count_launch(); }
         else {
-          int gg = i1 > i0 ? grid_for(i1 - i0, L.num_sms) : 1;
-          if (i1 > i0) { k_slr_partial<T, 1><<<gg, TOP_THREADS, 0, st>>>(keys, i0, i1, sf, use_sf, partials); count_launch(); }
+          int gg = i1 > i0 ? grid_for((i1 - i0 + 3) / 4 + 1, L.num_sms) : 1;
+          if (i1 > i0) { k_slr_partial<T, 1><<<gg, TOP_THREADS, 0, st>>>(keys, n, i0, i1, sf, use_sf, partials); count_launch(); }
           k_slr_finish<T, 1><<<1, TOP_THREADS, 0, st>>>(keys, i0, i1, repeat, sf, use_sf, partials, i1 > i0 ? gg : 0, d_top, d_aux);
           count_launch();
         }
@@ -642,8 +678,8 @@ unsigned fit_top_model(const Launch& L, const T* keys, u64 n, int kind, int tabl
         k_slr_exact<T, 0><<<1, 32, 0, st>>>(keys, i0, i1, repeat, sf, use_sf, d_top, d_aux);
         count_launch();
       } else {
-        int gg = i1 > i0 ? grid_for(i1 - i0, L.num_sms) : 1;
-        if (i1 > i0) { k_slr_partial<T, 0><<<gg, TOP_THREADS, 0, st>>>(keys, i0, i1, sf, use_sf, partials); count_launch(); }
+        int gg = i1 > i0 ? grid_for((i1 - i0 + 3) / 4 + 1, L.num_sms) : 1;
+        if (i1 > i0) { k_slr_partial<T, 0><<<gg, TOP_THREADS, 0, st>>>(keys, n, i0, i1, sf, use_sf, partials); count_launch(); }
         k_slr_finish<T, 0><<<1, TOP_THREADS, 0, st>>>(keys, i0, i1, repeat, sf, use_sf, partials, i1 > i0 ? gg : 0, d_top, d_aux);
         count_launch();
       }
