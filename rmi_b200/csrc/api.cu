@@ -105,7 +105,36 @@ struct rmi_dataset {
   int key_type = 0;
   int device = 0;
   bool owned = false;
+  bool sorted = true;   // verified once, when the dataset is created (the data is immutable)
 };
+
+namespace {
+// The reference requires sorted input (README.md:26-31) and otherwise trips over its own
+// monotonicity assertion (two_layer.rs:50).  The check is one streaming pass, done once per
+// dataset instead of once per build; every build on an unsorted dataset then fails fast.
+int verify_sorted(rmi_dataset* ds) {
+  if (ds->n < 2) return RMI_OK;
+  if ((reinterpret_cast<uintptr_t>(ds->d_keys) & 15u) != 0)
+    return fail(RMI_ERR_INVALID, "device key arrays must be 16-byte aligned");
+  DeviceInfo di;
+  if (int rc = device_info(ds->device, &di)) return rc;
+  unsigned* d_flag = nullptr;
+  CUDA_TRY(cudaMalloc(&d_flag, sizeof(unsigned)));
+  cudaMemset(d_flag, 0, sizeof(unsigned));
+  Launch L{nullptr, di.num_sms};
+  switch (ds->key_type) {
+    case RMI_KEY_U64: check_sorted<u64>(L, (const u64*)ds->d_keys, ds->n, d_flag); break;
+    case RMI_KEY_U32: check_sorted<u32>(L, (const u32*)ds->d_keys, ds->n, d_flag); break;
+    default: check_sorted<double>(L, (const double*)ds->d_keys, ds->n, d_flag); break;
+  }
+  unsigned h = 0;
+  cudaError_t e = cudaMemcpy(&h, d_flag, sizeof(unsigned), cudaMemcpyDeviceToHost);
+  cudaFree(d_flag);
+  if (e != cudaSuccess) return fail(RMI_ERR_CUDA, std::string("sortedness check: ") + cudaGetErrorString(e));
+  ds->sorted = h == 0;
+  return RMI_OK;
+}
+}  // namespace
 
 // Page-locked host buffers for results: D2H copies land directly in the memory the caller
 // reads (no pageable staging), and freed buffers are recycled because cudaMallocHost /
@@ -193,6 +222,7 @@ int rmi_dataset_create(const void* host_keys, uint64_t n, rmi_key_type key_type,
     e = cudaMemcpy(ds->d_keys, host_keys, bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(ds->d_keys); delete ds; return fail(RMI_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e)); }
   }
+  if (int rc = verify_sorted(ds)) { cudaFree(ds->d_keys); delete ds; return rc; }
   *out = ds;
   return RMI_OK;
 }
@@ -203,6 +233,8 @@ int rmi_dataset_wrap_device(const void* device_keys, uint64_t n, rmi_key_type ke
   auto* ds = new rmi_dataset();
   ds->d_keys = const_cast<void*>(device_keys);
   ds->n = n; ds->key_type = key_type; ds->device = device; ds->owned = false;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ds; return fail(RMI_ERR_CUDA, "cudaSetDevice failed"); }
+  if (int rc = verify_sorted(ds)) { delete ds; return rc; }
   *out = ds;
   return RMI_OK;
 }
@@ -257,6 +289,7 @@ int rmi_dataset_load_file(const char* path, int key_type_or_negative, int device
     }
   }
   cleanup();
+  if (rc == RMI_OK) rc = verify_sorted(ds);
   if (rc != RMI_OK) { if (ds->d_keys) cudaFree(ds->d_keys); delete ds; return rc; }
   *out = ds;
   return RMI_OK;
@@ -492,6 +525,7 @@ int train_entry(const rmi_dataset* ds, const char* model_spec, uint64_t N, uint3
     return fail(RMI_ERR_UNSUPPORTED, "radix tables are only offered as the top model in this build");
   if (N < 1) return fail(RMI_ERR_PANIC, "branching factor must be at least 1");
   if (ds->n == 0) return fail(RMI_ERR_PANIC, "start index was 0 but end index was 0");
+  if (!ds->sorted) return fail(RMI_ERR_PANIC, "keys are not sorted in ascending order");
   if (l0_over) {
     uint32_t need = top.kind == M_CUBIC ? 4 : (top.kind == M_NORMAL || top.kind == M_LOGNORMAL) ? 3 : 2;
     if (top.kind > M_LOGNORMAL || n_over != need)

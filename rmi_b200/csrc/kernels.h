@@ -59,6 +59,9 @@ unsigned fit_top_model(const Launch& L, const T* keys, u64 n, int kind, int tabl
                        TopModel* d_top, BuildAux* d_aux, void* scratch, u32* d_table32, u64* d_pivots,
                        u64* d_radix_index);
 
+// Sortedness of a key array (verified once per dataset): *d_flag |= 1 if out of order.
+template <class T> void check_sorted(const Launch& L, const T* keys, u64 n, unsigned* d_flag);
+
 // ---- leaf layer (kernels_leaf.cu) ----------------------------------------------------------
 // S[j] = first index whose clamped top prediction is >= j, for j in [0, N]; also verifies
 // sortedness and monotonicity and derives the split (two_layer.rs:131-175).

@@ -31,7 +31,7 @@ namespace {
 
 constexpr int BOUNDS_THREADS = 256;
 constexpr int LEAF_THREADS = 128;
-constexpr int RCP_TABLE = 1024;
+constexpr int RCP_TABLE = 512;
 
 __device__ __forceinline__ void set_status(BuildAux* aux, unsigned bit) { atomicOr(&aux->status, bit); }
 
@@ -136,63 +136,108 @@ __global__ void k_split(const T* __restrict__ keys, u64 n, const TopModel* __res
 // A lane owns one leaf and must visit that leaf's keys strictly in order (the fits are the
 // reference's order-dependent recurrences), but 32 lanes reading 32 different leaves straight
 // from global memory touch 32 different cache lines per instruction.  stream_pass() instead
-// lets the WARP copy, for every lane, the next SW keys of that lane's range into a padded
-// shared-memory row with cp.async (each copy instruction moves two contiguous 128-byte row
-// segments), three chunks deep, and each lane then consumes its own row.  Shared-memory
-// footprint is 32 x SW keys per stage whatever the leaf length, so 8-key and 8-million-key
-// leaves take the same code path, and the keys cross HBM->L2->SM in full lines.
+// lets the WARP copy, for every lane, the next 128 bytes of that lane's range into a
+// shared-memory row with 16-byte cp.async (8 lanes cover one row, so each copy instruction
+// moves four contiguous 128-byte segments), three chunks deep; each lane then reads its own
+// row back with 128-bit shared loads.  The footprint is 32 rows per stage whatever the leaf
+// length, so 8-key and 8-million-key leaves take the same code path, and the keys cross
+// HBM -> L2 -> SM in full lines exactly once per pass.
 // ------------------------------------------------------------------------------------------
-constexpr int SW = 16;          // keys per lane per chunk
-constexpr int SROW = SW + 1;    // padded row: 64-bit row reads of a half-warp hit 16 distinct bank pairs
+constexpr int ROW_BYTES = 144;   // 128 B of keys + 16 B pad: rows stay 16-byte aligned and the 8 lanes of
+                                 // a 128-bit shared-load phase hit 8 distinct bank quads
 constexpr int SSTAGES = 3;
+constexpr int WARP_STREAM_BYTES = SSTAGES * 32 * ROW_BYTES + 32 * 4 + 32 * 4;
 
-template <int BYTES> __device__ __forceinline__ void cp_async_key(void* smem_dst, const void* gmem_src) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N_> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory");
 }
 
-// Calls fn(key, index) for index = b .. e-1 of THIS lane's range, all 32 lanes of the warp
-// taking part in the copies.  Must be called by every lane of the warp (empty ranges allowed).
-template <class T, class Fn>
-__device__ __forceinline__ void stream_pass(const T* __restrict__ keys, T* wbuf, u64 b, u64 e, Fn&& fn) {
+// Calls fn(key, index) for index = b .. e-1 of THIS lane's range (I = u32 or u64 index type),
+// all 32 lanes of the warp taking part in the copies.  Must be called by every lane of the
+// warp (empty ranges allowed).  `keys` must be 16-byte aligned.
+template <class T, class I, class Fn>
+__device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_keys, unsigned char* wsm, I b, I e,
+                                            Fn&& fn) {
+  constexpr int KPP = 16 / (int)sizeof(T);   // keys per 16-byte piece
+  constexpr int SW = 8 * KPP;                // keys per row per chunk
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  if (e < b) e = b;
-  u64 maxlen = e - b;
+  u32* rowg = reinterpret_cast<u32*>(wsm + SSTAGES * 32 * ROW_BYTES);   // first 16-byte piece of each row
+  u32* rownp = rowg + 32;                                                // pieces in each row
+  const I a = b & ~(I)(KPP - 1);             // 16-byte aligned start of this lane's stream
+  const I skip = b - a;
+  const I rlen = e > b ? (I)(e - a) : (I)0;  // keys from a up to e
+  I maxlen = rlen;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    u64 t = __shfl_xor_sync(FULL, maxlen, o);
+    I t = __shfl_xor_sync(FULL, maxlen, o);
     if (t > maxlen) maxlen = t;
   }
   if (maxlen == 0) return;
-  const u64 nchunks = (maxlen + SW - 1) / SW;
-  const int sub = lane >> 4, col = lane & 15;   // lane copies key `col` of rows 2q+sub
-  auto issue = [&](u64 c) {
-    T* st = wbuf + (size_t)(c % SSTAGES) * 32 * SROW;
-    const u64 off = c * SW + col;
+  // Piece bookkeeping in 16-byte units (32-bit: covers 64 GB of keys).  Rows longer than
+  // 2^32 pieces cannot occur below that size either.
+  __syncwarp();
+  rowg[lane] = (u32)((u64)a / KPP);
+  rownp[lane] = (u32)(((u64)rlen + KPP - 1) / KPP);
+  __syncwarp();
+  const u32 g_full = (u32)(n_keys / KPP);                       // pieces that lie fully inside the array
+  const int tail_bytes = (int)((n_keys % KPP) * sizeof(T));    // bytes of the partial piece at the array end
+  const int prow = lane >> 3, piece = lane & 7;
+  u32 g0[8], np[8];   // this lane's 8 (row, piece) streams: first piece index, pieces available
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      int row = 2 * q + sub;
-      u64 rb = __shfl_sync(FULL, b, row), re = __shfl_sync(FULL, e, row);
-      u64 src = rb + off;
-      if (src < re) cp_async_key<sizeof(T)>(st + row * SROW + col, keys + src);
+  for (int q = 0; q < 8; ++q) {
+    const int row = prow + 4 * q;
+    g0[q] = rowg[row] + (u32)piece;
+    const u32 rp = rownp[row];
+    np[q] = rp > (u32)piece ? (rp - (u32)piece + 7u) / 8u : 0u;   // chunks in which this piece exists
+  }
+  const unsigned char* kb = reinterpret_cast<const unsigned char*>(keys);
+  const unsigned st0 = (unsigned)__cvta_generic_to_shared(wsm) + (unsigned)(prow * ROW_BYTES + piece * 16);
+  const u32 nchunks = (u32)(((u64)maxlen + SW - 1) / SW);
+  auto issue = [&](u32 c) {
+    const unsigned st = st0 + (c % SSTAGES) * (32 * ROW_BYTES);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (c < np[q]) {
+        const u32 g = g0[q] + 8u * c;
+        const int bytes = g < g_full ? 16 : tail_bytes;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)),
+                     "l"(kb + (u64)g * 16u), "r"(bytes) : "memory");
+      }
     }
     cp_async_commit();
   };
   issue(0);
   if (nchunks > 1) issue(1); else cp_async_commit();
-  for (u64 c = 0; c < nchunks; ++c) {
+  for (u32 c = 0; c < nchunks; ++c) {
     if (c + 2 < nchunks) issue(c + 2); else cp_async_commit();   // empty groups keep the count uniform
     cp_async_wait<2>();
     __syncwarp();
-    const T* row = wbuf + (size_t)(c % SSTAGES) * 32 * SROW + lane * SROW;
-    u64 base = b + c * SW;
-    int cnt = base < e ? ((e - base) < (u64)SW ? (int)(e - base) : SW) : 0;
-    for (int s = 0; s < cnt; ++s) fn(row[s], base + (u64)s);
+    const unsigned char* row = wsm + (int)(c % SSTAGES) * (32 * ROW_BYTES) + lane * ROW_BYTES;
+    const I cbase = (I)c * (I)SW;
+    const I lo_k = skip > cbase ? skip : cbase;
+    const I hi_k = rlen < cbase + (I)SW ? rlen : cbase + (I)SW;
+    if (lo_k == cbase && hi_k == cbase + (I)SW) {
+      // full chunk: 8 x 128-bit shared loads, no position tests
+      I idx = a + cbase;
+#pragma unroll 4
+      for (int pp = 0; pp < 8; ++pp) {
+        uint4 v = *reinterpret_cast<const uint4*>(row + pp * 16);
+        T kk[KPP];
+        memcpy(kk, &v, 16);
+#pragma unroll
+        for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(idx + (I)t));
+        idx += (I)KPP;
+      }
+    } else if (lo_k < hi_k) {
+      const int p0 = (int)(lo_k - cbase), p1 = (int)(hi_k - cbase);
+      for (int pos = p0; pos < p1; ++pos) fn(*reinterpret_cast<const T*>(row + pos * (int)sizeof(T)), (I)(a + cbase + (I)pos));
+    }
     __syncwarp();
   }
 }
@@ -202,9 +247,9 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, T* wbuf,
 // array — [last key of the previous leaf] + own keys + [first key of the next leaf], neither
 // across the half boundary — whose item offsets are the duplicate-fixed global offsets F.
 // ------------------------------------------------------------------------------------------
-template <class T> struct LeafRange {
-  u64 lo, hi;      // all keys of the leaf: [S[j], S[j+1])
-  u64 vs, ve;      // training vector
+template <class I> struct LeafRange {
+  I lo, hi;      // all keys of the leaf: [S[j], S[j+1])
+  I vs, ve;      // training vector
 };
 
 // The reference's Welford step (linear.rs:24-34) with the two count divisions done by
@@ -225,7 +270,8 @@ template <bool CHECKED> struct LeafWelford {
   __device__ __forceinline__ void push(double x, double y) {
     nf = __dadd_rn(nf, 1.0);
     ni += 1u;
-    double rc = ni < (unsigned)RCP_TABLE && nf < (double)RCP_TABLE ? rcp[ni] : __drcp_rn(nf);
+    double rc = rcp[ni < (unsigned)RCP_TABLE ? ni : 0u];
+    if (ni >= (unsigned)RCP_TABLE) rc = __drcp_rn(nf);   // leaves longer than the table: rare
     double dx = __dadd_rn(x, -mean_x);
     mean_x = __dadd_rn(mean_x, dv(dx, rc));
     mean_y = __dadd_rn(mean_y, dv(__dadd_rn(y, -mean_y), rc));
@@ -250,20 +296,15 @@ __device__ __forceinline__ double scale3(double v, double mn, double mx) {
   return __ddiv_rn(__dadd_rn(v, -mn), __dadd_rn(mx, -mn));
 }
 
-// Item tracker for a pass over a training vector: yields (x, y) with y the duplicate-fixed
-// offset as a double (exact below 2^53), without an int->float conversion per item.
+// Item tracker for a pass over a training vector: yields y = the duplicate-fixed offset as a
+// double (exact below 2^53) without an int->float conversion per item.  Seeded with the
+// vector's first key and its offset F0, so the first item needs no special case.
 template <class T> struct ItemTracker {
   T pk;
   double pyd, idxd;
-  u64 pF;
-  bool first;
-  __device__ __forceinline__ void init(u64 vs, u64 F0) { first = true; pF = F0; pyd = __ull2double_rn(F0); idxd = __ull2double_rn(vs); pk = T(); }
-  // returns y (double) for item (k, idx); updates state
-  __device__ __forceinline__ double next(T k, u64 idx) {
-    double yd;
-    if (first) { first = false; yd = pyd; }
-    else if (k == pk) { yd = pyd; }
-    else { yd = idxd; pF = idx; }
+  __device__ __forceinline__ void init(T first_key, double vs_d, double f0_d) { pk = first_key; pyd = f0_d; idxd = vs_d; }
+  __device__ __forceinline__ double next(T k) {
+    double yd = (k == pk) ? pyd : idxd;
     pk = k; pyd = yd;
     idxd = __dadd_rn(idxd, 1.0);
     return yd;
@@ -273,20 +314,22 @@ template <class T> struct ItemTracker {
 // train_model(layer2, vector) for every leaf model type, as warp-synchronous stream passes.
 // f receives Model::params().  Every lane of the warp must call this (with vs == ve if it has
 // no leaf or an empty vector).
-template <class T, int LEAF>
-__device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, T* wbuf, const LeafRange<T>& r,
-                                         const double* rcp, double* f, BuildAux* aux) {
-  const u64 L = r.ve - r.vs;
-  const u64 F0 = L ? run_start(keys, r.vs) : 0;
+template <class T, class I, int LEAF>
+__device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, u64 n_keys, unsigned char* wsm,
+                                         const LeafRange<I>& r, const double* rcp, double* f, unsigned& bad) {
+  const I L = r.ve - r.vs;
+  const u64 F0 = L ? run_start(keys, (u64)r.vs) : 0;
+  const T kfirst = L ? keys[r.vs] : T();
+  const double vsd = __ull2double_rn((u64)r.vs), f0d = __ull2double_rn(F0);
   constexpr bool CHECKED = Key<T>::is_float;
   if (LEAF == M_LINEAR || LEAF == M_LOGLINEAR) {
     // linear.rs:79-83 / :61-72,169-173 — drained stream: vector + repeat of the final item
     LeafWelford<CHECKED> w;
     w.init(rcp);
     ItemTracker<T> it;
-    it.init(r.vs, F0);
-    stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64 idx) {
-      double yy = it.next(k, idx);
+    it.init(kfirst, vsd, f0d);
+    stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) {
+      double yy = it.next(k);
       if (LEAF == M_LOGLINEAR) { yy = log(yy); if (!isfinite(yy)) return; }
       w.push(Key<T>::as_float(k), yy);
     });
@@ -295,34 +338,31 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, T* wbuf, co
       if (LEAF == M_LOGLINEAR) yy = log(yy);
       if (LEAF == M_LINEAR || isfinite(yy)) w.push(Key<T>::as_float(it.pk), yy);
     }
-    if (!w.finish(f[0], f[1])) set_status(aux, ST_NEG_VARIANCE);
+    if (!w.finish(f[0], f[1])) bad |= ST_NEG_VARIANCE;
   } else if (LEAF == M_ROBUST_LINEAR) {
     // linear.rs:239-260 — skip(bnd).take(len - 2*bnd): never drains the iterator
-    u64 bnd = f64_to_u64_sat(__dmul_rn(__ull2double_rn(L), 0.0001));
+    u64 bnd = f64_to_u64_sat(__dmul_rn(__ull2double_rn((u64)L), 0.0001));
     if (bnd < 1) bnd = 1;
-    bool ok = L == 0 || (bnd * 2 + 1 < L);
-    if (!ok) set_status(aux, ST_ROBUST_TOO_SMALL);
+    bool ok = L == 0 || (bnd * 2 + 1 < (u64)L);
+    if (!ok) bad |= ST_ROBUST_TOO_SMALL;
     LeafWelford<CHECKED> w;
     w.init(rcp);
     ItemTracker<T> it;
-    it.init(r.vs, F0);
+    it.init(kfirst, vsd, f0d);
     u64 pos = 0;
-    stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64 idx) {
-      double yy = it.next(k, idx);
-      if (ok && pos >= bnd && pos < L - bnd) w.push(Key<T>::as_float(k), yy);
+    stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) {
+      double yy = it.next(k);
+      if (ok && pos >= bnd && pos < (u64)L - bnd) w.push(Key<T>::as_float(k), yy);
       ++pos;
     });
     if (L == 0 || !ok) { f[0] = 0.0; f[1] = 0.0; }
-    else if (!w.finish(f[0], f[1])) set_status(aux, ST_NEG_VARIANCE);
+    else if (!w.finish(f[0], f[1])) bad |= ST_NEG_VARIANCE;
   } else if (LEAF == M_LINEAR_SPLINE || LEAF == M_CUBIC) {
     // linear_spline.rs:13-35 on the raw first / last items of the vector
     double la, lb;
-    T k0 = T(), k1 = T();
-    double y0 = 0.0, y1 = 0.0;
-    if (L > 0) {
-      k0 = keys[r.vs]; y0 = __ull2double_rn(F0);
-      k1 = keys[r.ve - 1]; y1 = __ull2double_rn(run_start(keys, r.ve - 1));
-    }
+    T k0 = kfirst, k1 = T();
+    double y0 = f0d, y1 = 0.0;
+    if (L > 0) { k1 = keys[r.ve - 1]; y1 = __ull2double_rn(run_start(keys, (u64)r.ve - 1)); }
     if (L == 0) { la = 0.0; lb = 0.0; }
     else if (L == 1 || k0 == k1) { la = y0; lb = 0.0; }
     else {
@@ -338,9 +378,9 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, T* wbuf, co
     double sxn = 0.0, syn = 0.0;
     {
       ItemTracker<T> it;
-      it.init(r.vs, F0);
-      stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64 idx) {
-        double yy = it.next(k, idx);
+      it.init(kfirst, vsd, f0d);
+      stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) {
+        double yy = it.next(k);
         if (k != k0) uniq = true;
         if (!found1) {
           double sx = scale3(Key<T>::as_float(k), xmin, xmax);
@@ -354,11 +394,11 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, T* wbuf, co
     else {
       bool found2 = false;
       double sxp = 0.0, syp = 0.0;
-      for (u64 p = r.ve; p-- > r.vs;) {   // from the back; almost always the second-to-last item
+      for (u64 p = (u64)r.ve; p-- > (u64)r.vs;) {   // from the back; almost always the second-to-last item
         double sx = scale3(Key<T>::as_float(keys[p]), xmin, xmax);
         if (sx < 1.0) { found2 = true; sxp = sx; syp = scale3(__ull2double_rn(run_start(keys, p)), ymin, ymax); break; }
       }
-      if (!found1 || !found2) { set_status(aux, ST_CUBIC_UNWRAP); a = b = c = d = 0.0; }
+      if (!found1 || !found2) { bad |= ST_CUBIC_UNWRAP; a = b = c = d = 0.0; }
       else {
         double m1 = __ddiv_rn(syn, sxn);
         double m2 = __ddiv_rn(__dadd_rn(1.0, -syp), __dadd_rn(1.0, -sxp));
@@ -390,33 +430,33 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, T* wbuf, co
     double our_error = 0.0, lin_error = 0.0;
     {
       ItemTracker<T> it;
-      it.init(r.vs, F0);
+      it.init(kfirst, vsd, f0d);
       auto acc = [&](double x, double yy) {
         our_error = __dadd_rn(our_error, fabs(__dadd_rn(predict_float<M_CUBIC>(cf, x), -yy)));
         lin_error = __dadd_rn(lin_error, fabs(__dadd_rn(predict_float<M_LINEAR>(lf, x), -yy)));
       };
-      stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64 idx) { acc(Key<T>::as_float(k), it.next(k, idx)); });
+      stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) { acc(Key<T>::as_float(k), it.next(k)); });
       if (L > 0) acc(Key<T>::as_float(it.pk), it.pyd);
     }
     if (lin_error < our_error) { f[0] = 0.0; f[1] = 0.0; f[2] = lb; f[3] = la; }
     else { f[0] = a; f[1] = b; f[2] = c; f[3] = d; }
   } else {  // M_NORMAL / M_LOGNORMAL — normal.rs:28-76
     double scale = -INFINITY, mean = 0.0, stdev = 0.0;
-    const double nf = __ull2double_rn(L);
+    const double nf = __ull2double_rn((u64)L);
     auto tx = [&](T k) {
       double x = Key<T>::as_float(k);
       if (LEAF == M_LOGNORMAL) { double l = log(x); x = isfinite(l) ? l : 0.0; }
       return x;
     };
     ItemTracker<T> it;
-    it.init(r.vs, F0);
-    stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64 idx) {
-      double yy = it.next(k, idx);
+    it.init(kfirst, vsd, f0d);
+    stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) {
+      double yy = it.next(k);
       mean = __dadd_rn(mean, __ddiv_rn(tx(k), nf));
       scale = rust_fmax(scale, yy);
     });
     if (L > 0) { mean = __dadd_rn(mean, __ddiv_rn(tx(it.pk), nf)); scale = rust_fmax(scale, it.pyd); }
-    stream_pass(keys, wbuf, r.vs, r.ve, [&](T k, u64) {
+    stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) {
       double dlt = __dadd_rn(tx(k), -mean);
       stdev = __dadd_rn(stdev, __dmul_rn(dlt, dlt));
     });
@@ -437,48 +477,63 @@ template <int LEAF> __device__ __forceinline__ bool set_constant(double* f, u64 
   return false;
 }
 
-// Model::predict_to_int (models/mod.rs:735-737) = max(0, floor(p)) as u64.  The conversion
-// instruction with round-toward-minus-infinity saturates exactly like Rust's cast (negative
-// -> 0, too large -> u64::MAX), so floor + clamp + cast is one instruction plus a NaN select.
-template <int LEAF> __device__ __forceinline__ u64 leaf_predict(const double* f, double x) {
+// Model::predict_to_int (models/mod.rs:735-737) = max(0, floor(p)) as u64, then clamped to n
+// by error_between.  The float->int conversion with round-toward-minus-infinity saturates
+// like Rust's cast (negative -> 0, too large -> MAX); NaN must be mapped to 0 by hand.  With
+// 32-bit indices (n < 2^32 - 1) the conversion saturates at 2^32 - 1 >= n, which the clamp to n
+// makes equivalent.
+template <int LEAF> __device__ __forceinline__ u64 leaf_predict64(const double* f, double x) {
   double p = predict_float<LEAF>(f, x);
   u64 v = (u64)__double2ull_rd(p);
-  return p != p ? 0ull : v;   // the conversion maps NaN to 2^63; Rust's cast maps it to 0
+  return p != p ? 0ull : v;
+}
+// NANCHECK: leaf parameters (hence predictions) can only be NaN for float keys or for the
+// normal / lognormal / loglinear leaves; integer keys with linear / spline / cubic leaves
+// always give finite parameters, so the select is compiled out there.
+template <int LEAF, class I, bool NANCHECK>
+__device__ __forceinline__ I leaf_predict_clamped(const double* f, double x, I n) {
+  double p = predict_float<LEAF>(f, x);
+  I v;
+  if (sizeof(I) == 4) v = (I)__double2uint_rd(p); else v = (I)__double2ull_rd(p);
+  if (NANCHECK) v = p != p ? (I)0 : v;
+  return v < n ? v : n;
 }
 
-constexpr size_t leaf_smem_bytes(size_t key_size) {
-  return (size_t)RCP_TABLE * sizeof(double) + (size_t)(LEAF_THREADS / 32) * SSTAGES * 32 * SROW * key_size;
+constexpr size_t leaf_smem_bytes() {
+  return (size_t)RCP_TABLE * sizeof(double) + (size_t)(LEAF_THREADS / 32) * WARP_STREAM_BYTES;
 }
 
-template <class T, int LEAF>
+template <class T, class I, int LEAF>
 __global__ void __launch_bounds__(LEAF_THREADS)
 k_leaf(const T* __restrict__ keys, u64 n, u64 N, const u64* __restrict__ S, BuildAux* aux,
        double* __restrict__ params, u64* __restrict__ errors, u64* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_rcp = reinterpret_cast<double*>(smem_raw);
-  T* wbuf = reinterpret_cast<T*>(smem_raw + (size_t)RCP_TABLE * sizeof(double)) +
-            (size_t)(threadIdx.x >> 5) * SSTAGES * 32 * SROW;
+  unsigned char* wsm = smem_raw + (size_t)RCP_TABLE * sizeof(double) + (size_t)(threadIdx.x >> 5) * WARP_STREAM_BYTES;
   for (int c = threadIdx.x; c < RCP_TABLE; c += blockDim.x) s_rcp[c] = c ? __drcp_rn((double)c) : 0.0;
   __syncthreads();
   const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = j < N;
   constexpr int PPM = leaf_params_per_model(LEAF);
+  constexpr bool NANCHECK = Key<T>::is_float || LEAF == M_LOGLINEAR || LEAF == M_NORMAL || LEAF == M_LOGNORMAL;
+  const I nI = (I)n;
 
-  LeafRange<T> r;
-  r.lo = live ? S[j] : 0;
-  r.hi = live ? S[j + 1] : 0;
+  LeafRange<I> r;
+  r.lo = live ? (I)S[j] : (I)0;
+  r.hi = live ? (I)S[j + 1] : (I)0;
   unsigned bad = 0;
   if (r.hi < r.lo) { bad |= ST_NOT_SORTED; r.hi = r.lo; }   // cannot happen on sorted keys
   // which half does leaf j belong to (two_layer.rs:147-175)
-  u64 half_lo, half_hi, first_leaf;
+  I half_lo, half_hi;
+  u64 first_leaf;
   if (aux->has_split) {
     u64 split = aux->split_idx, st = aux->split_target;
-    if (j < st) { half_lo = 0; half_hi = split; first_leaf = 0; }
-    else { half_lo = split + 1; half_hi = n; first_leaf = st; }
-  } else { half_lo = 0; half_hi = n; first_leaf = 0; }
+    if (j < st) { half_lo = 0; half_hi = (I)split; first_leaf = 0; }
+    else { half_lo = (I)(split + 1); half_hi = nI; first_leaf = st; }
+  } else { half_lo = 0; half_hi = nI; first_leaf = 0; }
   {
-    u64 own_lo = r.lo > half_lo ? r.lo : half_lo;
-    u64 own_hi = r.hi < half_hi ? r.hi : half_hi;
+    I own_lo = r.lo > half_lo ? r.lo : half_lo;
+    I own_hi = r.hi < half_hi ? r.hi : half_hi;
     if (live && own_hi > own_lo) {
       r.vs = own_lo > half_lo ? own_lo - 1 : own_lo;     // + last key of the previous leaf
       r.ve = own_hi < half_hi ? own_hi + 1 : own_hi;     // + first key of the next leaf
@@ -490,50 +545,50 @@ k_leaf(const T* __restrict__ keys, u64 n, u64 N, const u64* __restrict__ S, Buil
   }
 
   double f[4] = {0.0, 0.0, 0.0, 0.0};
-  fit_leaf<T, LEAF>(keys, wbuf, r, s_rcp, f, aux);
+  fit_leaf<T, I, LEAF>(keys, n, wsm, r, s_rcp, f, bad);
 
   // two_layer.rs:186-197: empty leaves (lower-bound-correction sense) except the last
-  const u64 next_idx = live ? S[j + 1] : 0;                        // lb.next_index(j)
+  const u64 next_idx = (u64)r.hi;                                   // lb.next_index(j) = S[j+1]
   if (live && j + 1 < N && r.lo == r.hi) {
     if (!set_constant<LEAF>(f, next_idx)) atomicAdd(&aux->could_not_replace, 1ull);
   }
 
   // two_layer.rs:207-217 forward pass over the leaf's own keys + longest run
   // (lower_bound_correction.rs:101-119: a run is recorded when the NEXT run starts, so the
-  // data set's final run never is)
+  // data set's final run never is).  Seeding the tracker with the key before the leaf (or the
+  // leaf's own first key at index 0) makes the first item an ordinary one and checks the
+  // ordering across the leaf boundary too.
   const T prev_key = (live && r.lo > 0) ? keys[r.lo - 1] : Key<T>::zero_value();
-  u64 max_err = 0, run_max = 0;
+  I max_err = 0, run_max = 0;
   {
-    T pk = prev_key;
-    bool have_pk = live && r.lo > 0;
-    u64 F = r.lo, run = 0;
-    stream_pass(keys, wbuf, r.lo, r.hi, [&](T k, u64 i) {
-      if (have_pk && k < pk) bad |= ST_NOT_SORTED;
-      if (i == r.lo || k != pk) { if (run > run_max) run_max = run; run = 1; F = i; }
-      else run += 1;
-      pk = k; have_pk = true;
-      u64 pred = leaf_predict<LEAF>(f, Key<T>::as_float(k));
-      u64 e = error_between(pred, F, n);
-      if (e > max_err) max_err = e;
+    T pk = (live && r.lo == 0 && r.hi > 0) ? keys[0] : prev_key;
+    I F = r.lo, run = 0;
+    stream_pass<T, I>(keys, n, wsm, r.lo, r.hi, [&](T k, I i) {
+      if (k != pk) { run_max = run > run_max ? run : run_max; run = 0; F = i; }
+      run += 1;
+      pk = k;
+      I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
+      I e = pred > F ? pred - F : F - pred;
+      max_err = e > max_err ? e : max_err;
     });
-    if (r.hi < n && run > run_max) run_max = run;
+    if (r.hi < nI && run > run_max) run_max = run;
   }
   if (bad) set_status(aux, bad);
   if (!live) return;
-  u64 cnt = r.hi - r.lo;
-  if (r.hi == n && r.lo < r.hi) cnt += 1;   // the drained iterator's repeated final item
+  u64 cnt = (u64)(r.hi - r.lo);
+  if (r.hi == nI && r.lo < r.hi) cnt += 1;   // the drained iterator's repeated final item
 
   // two_layer.rs:226-259 widening
   T next_key = next_idx < n ? keys[next_idx] : Key<T>::max_value();
-  u64 first_idx = j == 0 ? S[1] : r.lo;                            // lb.next_index(max(j-1, 0))
-  u64 up = leaf_predict<LEAF>(f, Key<T>::as_float(Key<T>::minus_epsilon(next_key)));
+  u64 first_idx = j == 0 ? S[1] : (u64)r.lo;                       // lb.next_index(max(j-1, 0))
+  u64 up = leaf_predict64<LEAF>(f, Key<T>::as_float(Key<T>::minus_epsilon(next_key)));
   u64 upper_error = error_between(up, next_idx + 1, n);
-  u64 lp = leaf_predict<LEAF>(f, Key<T>::as_float(Key<T>::plus_epsilon(prev_key)));
+  u64 lp = leaf_predict64<LEAF>(f, Key<T>::as_float(Key<T>::plus_epsilon(prev_key)));
   u64 lower_error = error_between(lp, first_idx, n);
-  u64 new_err = max_err;
+  u64 new_err = (u64)max_err;
   if (upper_error > new_err) new_err = upper_error;
   if (lower_error > new_err) new_err = lower_error;
-  new_err += run_max;
+  new_err += (u64)run_max;
 
 #pragma unroll
   for (int q = 0; q < PPM; ++q) params[j * PPM + q] = f[q];
@@ -663,9 +718,14 @@ template <class T, int LEAF>
 void launch_leaf(const Launch& L, const T* keys, u64 n, u64 N, const u64* d_S, BuildAux* d_aux, double* d_params,
                  u64* d_errors, u64* d_counts) {
   u64 blocks = (N + LEAF_THREADS - 1) / LEAF_THREADS;
-  constexpr size_t smem = leaf_smem_bytes(sizeof(T));
-  cudaFuncSetAttribute(k_leaf<T, LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_leaf<T, LEAF><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, n, N, d_S, d_aux, d_params, d_errors, d_counts);
+  constexpr size_t smem = leaf_smem_bytes();
+  if (n < 0xfffffff0ull) {   // 32-bit indices
+    cudaFuncSetAttribute(k_leaf<T, u32, LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_leaf<T, u32, LEAF><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, n, N, d_S, d_aux, d_params, d_errors, d_counts);
+  } else {
+    cudaFuncSetAttribute(k_leaf<T, u64, LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_leaf<T, u64, LEAF><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, n, N, d_S, d_aux, d_params, d_errors, d_counts);
+  }
   count_launch();
 }
 
@@ -704,6 +764,30 @@ void fit_leaves(const Launch& L, const T* keys, u64 n, int leaf_kind, u64 N, con
     default: break;
   }
 }
+
+// One pass over the keys at dataset-creation time: flag[0] |= 1 if keys[i] < keys[i-1] anywhere.
+template <class T>
+__global__ void __launch_bounds__(BOUNDS_THREADS)
+k_check_sorted(const T* __restrict__ keys, u64 n, unsigned* __restrict__ flag) {
+  const bool aligned = is_aligned16(keys);
+  u64 stride = (u64)gridDim.x * blockDim.x * 4;
+  bool bad = false;
+  for (u64 base = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < n; base += stride) {
+    T k[4];
+    int c = load_keys4(keys, base, n, aligned, k);
+    if (base > 0) bad |= k[0] < keys[base - 1];
+#pragma unroll
+    for (int e = 1; e < 4; ++e) if (e < c) bad |= k[e] < k[e - 1];
+  }
+  if (bad) atomicOr(flag, 1u);
+}
+template <class T> void check_sorted(const Launch& L, const T* keys, u64 n, unsigned* d_flag) {
+  k_check_sorted<T><<<grid_cap((n + 3) / 4, BOUNDS_THREADS, L.num_sms * 8), BOUNDS_THREADS, 0, L.stream>>>(keys, n, d_flag);
+  count_launch();
+}
+template void check_sorted<u64>(const Launch&, const u64*, u64, unsigned*);
+template void check_sorted<u32>(const Launch&, const u32*, u64, unsigned*);
+template void check_sorted<double>(const Launch&, const double*, u64, unsigned*);
 
 size_t stats_scratch_bytes(u64) { return sizeof(StatsPartial) * STATS_MAX_BLOCKS; }
 
