@@ -19,7 +19,8 @@ HEADERS = ["rust_math.cuh", "models.cuh", "device_util.cuh", "kernels.h",
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: the reference fuses a multiply-add only where it writes mul_add; everything
 # else must round twice (see csrc/rust_math.cuh).
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+EXTRA_DEFS = os.environ.get("RMI_NVCC_DEFS", "").split()
+NVCC_FLAGS = EXTRA_DEFS + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
 

@@ -145,7 +145,13 @@ __global__ void k_split(const T* __restrict__ keys, u64 n, const TopModel* __res
 // ------------------------------------------------------------------------------------------
 constexpr int ROW_BYTES = 144;   // 128 B of keys + 16 B pad: rows stay 16-byte aligned and the 8 lanes of
                                  // a 128-bit shared-load phase hit 8 distinct bank quads
-constexpr int SSTAGES = 3;
+#ifndef RMI_SSTAGES
+#define RMI_SSTAGES 3
+#endif
+#ifndef RMI_PARTIAL_MODE
+#define RMI_PARTIAL_MODE 0   // 0: per-lane fast/slow split, 1: warp-uniform predicated walk, 2: one variable-bound loop
+#endif
+constexpr int SSTAGES = RMI_SSTAGES;
 constexpr int WARP_STREAM_BYTES = SSTAGES * 32 * ROW_BYTES + 32 * 4 + 32 * 4;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
@@ -206,24 +212,29 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
       if (c < np[q]) {
         const u32 g = g0[q] + 8u * c;
         const int bytes = g < g_full ? 16 : tail_bytes;
+        u64 src;
+        asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(src) : "r"(g), "l"(kb));
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)),
-                     "l"(kb + (u64)g * 16u), "r"(bytes) : "memory");
+                     "l"(src), "r"(bytes) : "memory");
       }
     }
     cp_async_commit();
   };
-  issue(0);
-  if (nchunks > 1) issue(1); else cp_async_commit();
+  // prologue: chunks 0 .. SSTAGES-2 in flight; every iteration commits exactly one group (an
+  // empty one past the end) so that wait_group<SSTAGES-1> always means "chunk c has landed"
+#pragma unroll
+  for (u32 c = 0; c + 1 < (u32)SSTAGES; ++c) { if (c < nchunks) issue(c); else cp_async_commit(); }
   for (u32 c = 0; c < nchunks; ++c) {
-    if (c + 2 < nchunks) issue(c + 2); else cp_async_commit();   // empty groups keep the count uniform
-    cp_async_wait<2>();
+    if (c + (SSTAGES - 1) < nchunks) issue(c + (SSTAGES - 1)); else cp_async_commit();
+    cp_async_wait<SSTAGES - 1>();
     __syncwarp();
     const unsigned char* row = wsm + (int)(c % SSTAGES) * (32 * ROW_BYTES) + lane * ROW_BYTES;
     const I cbase = (I)c * (I)SW;
     const I lo_k = skip > cbase ? skip : cbase;
     const I hi_k = rlen < cbase + (I)SW ? rlen : cbase + (I)SW;
-    if (lo_k == cbase && hi_k == cbase + (I)SW) {
-      // full chunk: 8 x 128-bit shared loads, no position tests
+    const bool full = lo_k == cbase && hi_k == cbase + (I)SW;
+#if RMI_PARTIAL_MODE == 0
+    if (full) {
       I idx = a + cbase;
 #pragma unroll 4
       for (int pp = 0; pp < 8; ++pp) {
@@ -238,6 +249,60 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
       const int p0 = (int)(lo_k - cbase), p1 = (int)(hi_k - cbase);
       for (int pos = p0; pos < p1; ++pos) fn(*reinterpret_cast<const T*>(row + pos * (int)sizeof(T)), (I)(a + cbase + (I)pos));
     }
+#elif RMI_PARTIAL_MODE == 2
+    if (__all_sync(FULL, full)) {
+      I idx = a + cbase;
+#pragma unroll 4
+      for (int pp = 0; pp < 8; ++pp) {
+        uint4 v = *reinterpret_cast<const uint4*>(row + pp * 16);
+        T kk[KPP];
+        memcpy(kk, &v, 16);
+#pragma unroll
+        for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(idx + (I)t));
+        idx += (I)KPP;
+      }
+    } else {
+      // some lane starts or ends inside this chunk: every lane walks its own [p0, p1) in ONE
+      // loop (full lanes: all SW keys), so the warp pays max(p1 - p0) iterations once instead
+      // of a full-chunk path plus a partial-chunk path
+      const int p0 = lo_k < hi_k ? (int)(lo_k - cbase) : 0, p1 = lo_k < hi_k ? (int)(hi_k - cbase) : 0;
+#pragma unroll 2
+      for (int pos = p0; pos < p1; ++pos)
+        fn(*reinterpret_cast<const T*>(row + pos * (int)sizeof(T)), (I)(a + cbase + (I)pos));
+    }
+#else
+    if (__all_sync(FULL, full)) {
+      // every lane has a full chunk: 8 x 128-bit shared loads, no position tests
+      I idx = a + cbase;
+#pragma unroll 4
+      for (int pp = 0; pp < 8; ++pp) {
+        uint4 v = *reinterpret_cast<const uint4*>(row + pp * 16);
+        T kk[KPP];
+        memcpy(kk, &v, 16);
+#pragma unroll
+        for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(idx + (I)t));
+        idx += (I)KPP;
+      }
+    } else {
+      // some lane starts or ends inside this chunk: ONE predicated walk for the whole warp
+      // (a two-path split would make the warp execute both paths for most chunks, because
+      // 32 leaves begin and end at 32 different phases)
+      const int p0 = lo_k < hi_k ? (int)(lo_k - cbase) : SW, p1 = lo_k < hi_k ? (int)(hi_k - cbase) : 0;
+      I idx = a + cbase;
+#pragma unroll 2
+      for (int pp = 0; pp < 8; ++pp) {
+        uint4 v = *reinterpret_cast<const uint4*>(row + pp * 16);
+        T kk[KPP];
+        memcpy(kk, &v, 16);
+#pragma unroll
+        for (int t = 0; t < KPP; ++t) {
+          const int pos = pp * KPP + t;
+          if (pos >= p0 && pos < p1) fn(kk[t], (I)(idx + (I)t));
+        }
+        idx += (I)KPP;
+      }
+    }
+#endif
     __syncwarp();
   }
 }
@@ -256,11 +321,16 @@ template <class I> struct LeafRange {
 // div_by_count (rust_math.cuh): bit-identical to IEEE division, 3 FP64 ops instead of ~20.
 // CHECKED = false skips div_by_count's range test (integer keys cannot produce operands
 // outside [2^-900, 2^900], and a zero operand is handled exactly by the fast sequence).
+__device__ __noinline__ double rcp_beyond_table(double nf) { return __drcp_rn(nf); }
+
 template <bool CHECKED> struct LeafWelford {
   double mean_x, mean_y, c, m2, nf;
-  unsigned ni;
-  const double* rcp;
-  __device__ __forceinline__ void init(const double* table) { mean_x = mean_y = c = m2 = nf = 0.0; ni = 0; rcp = table; }
+  unsigned ra, ra_end;   // shared-memory address of 1/ni in the reciprocal table, and of its last entry
+  __device__ __forceinline__ void init(const double* table) {
+    mean_x = mean_y = c = m2 = nf = 0.0;
+    ra = (unsigned)__cvta_generic_to_shared(table);
+    ra_end = ra + (unsigned)((RCP_TABLE - 1) * sizeof(double));
+  }
   __device__ __forceinline__ double dv(double a, double rc) const {
     if (CHECKED) return div_by_count(a, nf, rc);
     double q0 = __dmul_rn(a, rc);
@@ -269,9 +339,13 @@ template <bool CHECKED> struct LeafWelford {
   }
   __device__ __forceinline__ void push(double x, double y) {
     nf = __dadd_rn(nf, 1.0);
-    ni += 1u;
-    double rc = rcp[ni < (unsigned)RCP_TABLE ? ni : 0u];
-    if (ni >= (unsigned)RCP_TABLE) rc = __drcp_rn(nf);   // leaves longer than the table: rare
+    double rc;
+    if (ra < ra_end) {   // 1/nf from the shared table (entry ni = table[ni])
+      ra += (unsigned)sizeof(double);
+      asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
+    } else {
+      rc = rcp_beyond_table(nf);   // leaves longer than the table: a real call, so it is not if-converted
+    }
     double dx = __dadd_rn(x, -mean_x);
     mean_x = __dadd_rn(mean_x, dv(dx, rc));
     mean_y = __dadd_rn(mean_y, dv(__dadd_rn(y, -mean_y), rc));

@@ -14,6 +14,8 @@ ds = rmi_b200.RMITrainingData.from_device(k.data_ptr(), n, rmi_b200.KEY_U64, 0, 
 configs = [("linear,linear", 1 << 20, 0), ("radix,linear", 1 << 19, 0), ("cubic,linear", 1 << 18, 0),
            ("linear,linear", 1 << 20, rmi_b200.FLAG_STATS_ONLY), ("linear_spline,cubic", 1 << 18, 0),
            ("radix18,linear", 1 << 16, 0), ("bradix,linear", 1 << 18, 0), ("histogram,linear", 1 << 16, 0)]
+if "--quick" in sys.argv:
+    configs = configs[:3]
 if "--exact" in sys.argv:
     configs.append(("linear,linear", 1 << 20, rmi_b200.FLAG_TOP_FIT_EXACT))
 for spec, bf, flags in configs:
