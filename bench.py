@@ -210,9 +210,21 @@ def main():
     k = torch.randint(0, width, (n,), dtype=torch.int64, device=dev, generator=g) + rank * width
     k, _ = torch.sort(k)
     torch.cuda.synchronize()
-    ds = rmi_b200.RMITrainingData.from_device(k.data_ptr(), n, rmi_b200.KEY_U64, local_rank, keep_alive=k)
     ppm = 2
     key_bytes = 8
+    if world == 1:
+        ds = rmi_b200.RMITrainingData.from_device(k.data_ptr(), n, rmi_b200.KEY_U64, local_rank, keep_alive=k)
+
+        def build():
+            return rmi_b200.train(ds, args.spec, N, flags)
+    else:
+        # range-partitioned build: ONE global RMI with N leaves over all ranks' keys
+        # (rank r holds the r-th slab of the globally sorted array); weak scaling in keys.
+        from rmi_b200 import sharded
+        sdata = sharded.ShardedTrainingData(k, n, rmi_b200.KEY_U64, halo_capacity=1 << 20)
+
+        def build():
+            return sharded.train_sharded(sdata, args.spec, N, flags)
 
     def barrier():
         if dist is not None:
@@ -223,7 +235,7 @@ def main():
     # ---- warm-up --------------------------------------------------------------------------
     res = None
     for _ in range(max(args.warmup, 3)):
-        res = rmi_b200.train(ds, args.spec, N, flags)
+        res = build()
     if rank == 0:
         clocks.start()
     # ---- timed region: K resident builds ---------------------------------------------------
@@ -236,7 +248,7 @@ def main():
     e0.record()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = rmi_b200.train(ds, args.spec, N, flags)      # synchronous: returns with results on the host
+        res = build()      # synchronous: returns with results on the host
         phase += np.array(res.phase_device_ns, dtype=np.float64)
         dev_ns += res.device_time_ns
     e1.record()
@@ -256,18 +268,26 @@ def main():
     host.copy_(k)
     torch.cuda.synchronize()
     host_np = host.numpy().view(np.uint64)
-    for _ in range(1):
-        d2 = rmi_b200.RMITrainingData(host_np, device=local_rank)
-        rmi_b200.train(d2, args.spec, N, flags)
-        d2.close()
+    def e2e_step():
+        if world == 1:
+            d2 = rmi_b200.RMITrainingData(host_np, device=local_rank)   # cudaMemcpy H2D from pinned memory
+            r2 = rmi_b200.train(d2, args.spec, N, flags)
+            d2.close()
+        else:
+            from rmi_b200 import sharded
+            kd = torch.empty(n + (1 << 20), dtype=torch.int64, device=dev)
+            kd[:n].copy_(host, non_blocking=False)                       # H2D from pinned memory
+            sd = sharded.ShardedTrainingData(kd, n, rmi_b200.KEY_U64, halo_capacity=1 << 20)
+            r2 = sharded.train_sharded(sd, args.spec, N, flags)
+        return r2
+
+    e2e_step()
     barrier()
     e2 = torch.cuda.Event(enable_timing=True)
     e3 = torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(args.e2e_steps):
-        d2 = rmi_b200.RMITrainingData(host_np, device=local_rank)   # cudaMemcpy H2D from pinned memory
-        r2 = rmi_b200.train(d2, args.spec, N, flags)
-        d2.close()
+        e2e_step()
     e3.record()
     barrier()
     t_e2e = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
@@ -321,7 +341,10 @@ def main():
                       "top_fit": "exact-serial" if args.exact_top else "parallel (coefficients within 1e-9 of the reference)",
                       "keys_per_gpu": n, "leaves": N, "key_type": "uint64",
                       "l2": "inputs (1.6 GB) larger than L2, no flush needed",
-                      "parallelism": "1 GPU" if world == 1 else f"{world} independent range partitions (interim)",
+                      "parallelism": "1 GPU" if world == 1 else
+                      f"range-partitioned over {world} GPUs: one global RMI with {N} leaves over {n * world} keys; "
+                      "all-reduce of top-model sums (64 B), leaf boundaries ((N+1)*8 B) and leaf records (N*32 B), "
+                      "halo send/recv between neighbours",
                       "timing": "CUDA events around K synchronous builds, max over ranks",
                       "wall_ms_per_step": 1e3 * wall / args.steps},
            "clocks": clk,

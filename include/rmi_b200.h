@@ -135,6 +135,61 @@ int rmi_train_with_top(const rmi_dataset* ds, const char* model_spec, uint64_t b
                        const double* l0_fparams, uint32_t n_fparams, rmi_result** out);
 void rmi_result_free(rmi_result* r);
 
+/* ---- Range-partitioned (multi-GPU) build ----------------------------------------------------
+ * One process per GPU; rank r holds the r-th contiguous slab of the globally sorted key array
+ * in an rmi_dataset.  The leaf fits are independent once the top model and the leaf boundaries
+ * are global, so a build is a sequence of local phases separated by three small collectives
+ * that the HOST issues on the buffers below (rmi_b200/sharded.py does it with
+ * torch.distributed over NCCL):
+ *     RMI_PHASE_TOP_LOCAL   -> all-reduce SUM  of buffers.sums   (8 doubles)
+ *     RMI_PHASE_TOP_FINISH, RMI_PHASE_BOUNDS
+ *                           -> all-reduce MIN  of buffers.S      ((N+1) u64)
+ *     RMI_PHASE_SPLIT       -> halo: copy the keys of this rank's last leaf that live on the
+ *                              following rank(s) behind the local keys, rmi_shard_set_halo()
+ *     RMI_PHASE_LEAF        -> all-reduce SUM  of params / errors / counts (zero where not owned,
+ *                              summed as 64-bit integers), all-reduce MAX of buffers.status
+ *     RMI_PHASE_STATS, rmi_shard_finish()
+ * All phases are enqueued on the caller's CUDA stream and do not synchronise.  The result is
+ * identical on every rank and equal to a single-GPU build of the concatenated array (same
+ * tolerance rules).  Offered for the top models linear, robust_linear, linear_spline, radix. */
+typedef struct {          /* what a rank publishes about its slab (host struct) */
+  uint64_t first_key_bits, last_key_bits;  /* raw key bits (u32 zero-extended, f64 bit pattern) */
+  uint64_t last_run_start;                 /* local index of the first key equal to the last key */
+  uint64_t n_local;
+} rmi_shard_ends;
+int rmi_shard_ends_get(const rmi_dataset* ds, rmi_shard_ends* out);
+
+typedef struct {
+  uint64_t base, n_global;                 /* global index of local key 0, total keys */
+  int32_t has_prev, is_last;
+  uint64_t prev_key_bits, prev_F;          /* last key before this slab and its duplicate-fixed offset */
+  uint64_t first_key_bits, last_key_bits, last_F;   /* global first / last key, offset of the last */
+  uint64_t halo_capacity;                  /* keys of room behind the local keys in the device array */
+  double pivot_x, pivot_y;                 /* common pivot of the top-level sums (any value, same on all ranks) */
+} rmi_shard_info;
+
+typedef struct {          /* device buffers owned by the caller (the collectives run on them) */
+  void* sums;             /* 8 x f64 */
+  void* S;                /* (N+1) x u64 */
+  void* params;           /* N x params_per_model x f64 */
+  void* errors;           /* N x u64 */
+  void* counts;           /* N x u64 */
+  void* status;           /* 1 x u32 */
+} rmi_shard_buffers;
+
+enum { RMI_PHASE_TOP_LOCAL = 0, RMI_PHASE_TOP_FINISH = 1, RMI_PHASE_BOUNDS = 2, RMI_PHASE_SPLIT = 3,
+       RMI_PHASE_LEAF = 4, RMI_PHASE_STATS = 5 };
+
+typedef struct rmi_shard_build rmi_shard_build;
+int rmi_shard_build_create(const rmi_dataset* local, const rmi_shard_info* info, const char* model_spec,
+                           uint64_t branch_factor, const rmi_shard_buffers* buffers, void* cuda_stream,
+                           rmi_shard_build** out);
+int rmi_shard_phase(rmi_shard_build* b, int phase);
+int rmi_shard_set_halo(rmi_shard_build* b, uint64_t halo_keys);
+int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out);
+void rmi_shard_build_destroy(rmi_shard_build* b);
+uint32_t rmi_params_per_model(const char* leaf_model_name);
+
 /* Message of the last failure on the calling thread ("" if none). */
 const char* rmi_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */

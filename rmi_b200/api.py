@@ -225,6 +225,11 @@ def train(data: RMITrainingData, model_spec: str, branch_factor: int, flags: int
         rc = L.rmi_train_with_top(data._h, model_spec.encode(), int(branch_factor), int(flags),
                                   p.ctypes.data_as(C.c_void_p), p.size, C.byref(res))
     _check(rc)
+    return result_from_pointer(res, model_spec)
+
+
+def result_from_pointer(res, model_spec: str) -> TrainedRMI:
+    """Wrap a struct rmi_result* returned by the library (zero-copy views, freed with the last view)."""
     if True:
         r = res.contents
         owner = _ResultOwner(res)

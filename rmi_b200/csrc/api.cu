@@ -399,7 +399,7 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
         // injected top parameters are not known to be monotone: take the streaming pass, which checks
         compute_leaf_bounds<T>(L, keys, n, top.kind, d_top, N, d_S, d_aux, /*allow_search=*/l0_over == nullptr);
         cudaEventRecord(evp[1], st);
-        fit_leaves<T>(L, keys, n, leaf.kind, N, d_S, d_aux, d_params, d_errors, d_counts);
+        fit_leaves<T>(L, keys, whole_array<T>(n), leaf.kind, N, d_S, d_aux, d_params, d_errors, d_counts);
         cudaEventRecord(evp[2], st);
         leaf_statistics(L, n, N, d_errors, d_counts, d_aux, d_stats);
       } else {
@@ -550,6 +550,282 @@ int rmi_train_with_top(const rmi_dataset* ds, const char* model_spec, uint64_t b
                        const double* l0_fparams, uint32_t n_fparams, rmi_result** out) {
   if (!l0_fparams) return fail(RMI_ERR_INVALID, "rmi_train_with_top: null parameters");
   return train_entry(ds, model_spec, branch_factor, flags, l0_fparams, n_fparams, out);
+}
+
+}  // extern "C"
+
+// ===========================================================================================
+// Range-partitioned build (include/rmi_b200.h, "Range-partitioned (multi-GPU) build")
+// ===========================================================================================
+struct rmi_shard_build {
+  const rmi_dataset* ds = nullptr;
+  rmi_shard_info info{};
+  rmi_shard_buffers buf{};
+  const ModelName* top = nullptr;
+  const ModelName* leaf = nullptr;
+  uint64_t N = 0;
+  uint64_t halo = 0;
+  cudaStream_t st = nullptr;
+  int num_sms = 0;
+  TopModel* d_top = nullptr;
+  BuildAux* d_aux = nullptr;
+  void* d_scratch = nullptr;
+  void* d_stats = nullptr;
+  unsigned host_status = 0;
+  std::chrono::steady_clock::time_point t_start;
+  cudaEvent_t ev_begin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_end[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ran[6] = {false, false, false, false, false, false};
+};
+
+namespace {
+
+template <class T> T key_from_bits(uint64_t bits) {
+  T k;
+  if (sizeof(T) == 4) { uint32_t v = (uint32_t)bits; memcpy(&k, &v, 4); }
+  else memcpy(&k, &bits, 8);
+  return k;
+}
+template <class T> uint64_t bits_from_key(T k) {
+  uint64_t bits = 0;
+  if (sizeof(T) == 4) { uint32_t v; memcpy(&v, &k, 4); bits = v; }
+  else memcpy(&bits, &k, 8);
+  return bits;
+}
+
+template <class T> Shard<T> make_shard(const rmi_shard_build* b) {
+  Shard<T> s;
+  s.base = b->info.base;
+  s.n_global = b->info.n_global;
+  s.n_local = b->ds->n;
+  s.n_avail = b->ds->n + b->halo;
+  s.has_prev = b->info.has_prev;
+  s.is_last = b->info.is_last;
+  s.prev_key = key_from_bits<T>(b->info.prev_key_bits);
+  s.prev_F = b->info.prev_F;
+  return s;
+}
+
+template <class T> int shard_ends_typed(const rmi_dataset* ds, rmi_shard_ends* out) {
+  out->n_local = ds->n;
+  out->first_key_bits = out->last_key_bits = out->last_run_start = 0;
+  if (ds->n == 0) return RMI_OK;
+  const T* keys = (const T*)ds->d_keys;
+  T first, last;
+  CUDA_TRY(cudaMemcpy(&first, keys, sizeof(T), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&last, keys + (ds->n - 1), sizeof(T), cudaMemcpyDeviceToHost));
+  out->first_key_bits = bits_from_key<T>(first);
+  out->last_key_bits = bits_from_key<T>(last);
+  // first index whose key equals the last key: host-driven binary search (a handful of 8-byte reads)
+  uint64_t lo = 0, hi = ds->n - 1;
+  while (lo < hi) {
+    uint64_t mid = lo + (hi - lo) / 2;
+    T v;
+    CUDA_TRY(cudaMemcpy(&v, keys + mid, sizeof(T), cudaMemcpyDeviceToHost));
+    if (v == last) hi = mid; else lo = mid + 1;
+  }
+  out->last_run_start = lo;
+  return RMI_OK;
+}
+
+template <class T> int shard_phase_typed(rmi_shard_build* b, int phase) {
+  const T* keys = (const T*)b->ds->d_keys;
+  Shard<T> sh = make_shard<T>(b);
+  Launch L{b->st, b->num_sms};
+  const int ppm = leaf_params_per_model(b->leaf->kind);
+  if (phase >= 0 && phase < 6) { cudaEventRecord(b->ev_begin[phase], b->st); b->ran[phase] = true; }
+  if (phase == RMI_PHASE_TOP_LOCAL) {   // a build object may be reused for many builds
+    b->t_start = std::chrono::steady_clock::now();
+    b->host_status = 0;
+    for (int q = 1; q < 6; ++q) b->ran[q] = false;
+  }
+  switch (phase) {
+    case RMI_PHASE_TOP_LOCAL:
+      cudaMemsetAsync(b->d_aux, 0, sizeof(BuildAux), b->st);
+      {
+        TopModel h;
+        memset(&h, 0, sizeof(h));
+        h.kind = b->top->kind; h.high = 1;
+        cudaMemcpyAsync(b->d_top, &h, sizeof(h), cudaMemcpyHostToDevice, b->st);
+      }
+      b->host_status |= shard_top_local<T>(L, keys, sh, b->top->kind, b->N, b->info.pivot_x, b->info.pivot_y, b->d_scratch,
+                                           (double*)b->buf.sums);
+      break;
+    case RMI_PHASE_TOP_FINISH:
+      shard_top_finish<T>(L, sh, b->top->kind, b->N, b->info.pivot_x, b->info.pivot_y, (const double*)b->buf.sums,
+                          key_from_bits<T>(b->info.first_key_bits), key_from_bits<T>(b->info.last_key_bits),
+                          b->info.last_F, b->d_top, b->d_aux);
+      break;
+    case RMI_PHASE_BOUNDS:
+      shard_bounds<T>(L, keys, sh, b->top->kind, b->d_top, b->N, (u64*)b->buf.S);
+      break;
+    case RMI_PHASE_SPLIT:
+      shard_split<T>(L, keys, sh, b->top->kind, b->d_top, b->N, (const u64*)b->buf.S, b->d_aux);
+      break;
+    case RMI_PHASE_LEAF:
+      cudaMemsetAsync(b->buf.params, 0, sizeof(double) * b->N * ppm, b->st);
+      cudaMemsetAsync(b->buf.errors, 0, sizeof(u64) * b->N, b->st);
+      cudaMemsetAsync(b->buf.counts, 0, sizeof(u64) * b->N, b->st);
+      fit_leaves<T>(L, keys, sh, b->leaf->kind, b->N, (const u64*)b->buf.S, b->d_aux, (double*)b->buf.params,
+                    (u64*)b->buf.errors, (u64*)b->buf.counts);
+      shard_copy_status(L, b->d_aux, (unsigned*)b->buf.status);
+      break;
+    case RMI_PHASE_STATS:
+      leaf_statistics(L, b->info.n_global, b->N, (const u64*)b->buf.errors, (const u64*)b->buf.counts, b->d_aux, b->d_stats);
+      break;
+    default:
+      return fail(RMI_ERR_INVALID, "rmi_shard_phase: unknown phase");
+  }
+  if (phase >= 0 && phase < 6) cudaEventRecord(b->ev_end[phase], b->st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(RMI_ERR_CUDA, std::string("rmi_shard_phase: ") + cudaGetErrorString(e));
+  return RMI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t rmi_params_per_model(const char* leaf_model_name) {
+  const ModelName* m = leaf_model_name ? find_model(leaf_model_name) : nullptr;
+  return m ? (uint32_t)leaf_params_per_model(m->kind) : 0;
+}
+
+int rmi_shard_ends_get(const rmi_dataset* ds, rmi_shard_ends* out) {
+  if (!ds || !out) return fail(RMI_ERR_INVALID, "rmi_shard_ends_get: null argument");
+  CUDA_TRY(cudaSetDevice(ds->device));
+  switch (ds->key_type) {
+    case RMI_KEY_U64: return shard_ends_typed<u64>(ds, out);
+    case RMI_KEY_U32: return shard_ends_typed<u32>(ds, out);
+    default: return shard_ends_typed<double>(ds, out);
+  }
+}
+
+int rmi_shard_build_create(const rmi_dataset* local, const rmi_shard_info* info, const char* model_spec,
+                           uint64_t branch_factor, const rmi_shard_buffers* buffers, void* cuda_stream,
+                           rmi_shard_build** out) {
+  g_last_error.clear();
+  if (!local || !info || !model_spec || !buffers || !out) return fail(RMI_ERR_INVALID, "rmi_shard_build_create: null argument");
+  std::string s(model_spec);
+  size_t c = s.find(',');
+  if (c == std::string::npos || s.find(',', c + 1) != std::string::npos)
+    return fail(RMI_ERR_PANIC, "only two-layer RMIs can be trained (the reference panics on other depths)");
+  const ModelName* top = find_model(s.substr(0, c));
+  const ModelName* leaf = find_model(s.substr(c + 1));
+  if (!top) return fail(RMI_ERR_PANIC, "Unknown model type: " + s.substr(0, c));
+  if (!leaf) return fail(RMI_ERR_PANIC, "Unknown model type: " + s.substr(c + 1));
+  if (leaf->kind == M_RADIX || leaf->kind == M_BRADIX || leaf->kind == M_HISTOGRAM)
+    return fail(RMI_ERR_PANIC, "if used, model type " + s.substr(c + 1) + " must be the root model");
+  if (!(top->kind == M_LINEAR || top->kind == M_ROBUST_LINEAR || top->kind == M_LINEAR_SPLINE || top->kind == M_RADIX))
+    return fail(RMI_ERR_UNSUPPORTED, "range-partitioned builds offer the top models linear, robust_linear, linear_spline, radix");
+  if (leaf->kind == M_RADIX_TABLE) return fail(RMI_ERR_UNSUPPORTED, "radix tables are only offered as the top model");
+  if (branch_factor < 1) return fail(RMI_ERR_PANIC, "branching factor must be at least 1");
+  if (info->n_global == 0) return fail(RMI_ERR_PANIC, "start index was 0 but end index was 0");
+  if (!local->sorted) return fail(RMI_ERR_PANIC, "keys are not sorted in ascending order");
+  CUDA_TRY(cudaSetDevice(local->device));
+  DeviceInfo di;
+  if (int rc = device_info(local->device, &di)) return rc;
+  auto* b = new rmi_shard_build();
+  b->ds = local; b->info = *info; b->buf = *buffers; b->top = top; b->leaf = leaf; b->N = branch_factor;
+  b->st = (cudaStream_t)cuda_stream; b->num_sms = di.num_sms; b->halo = 0;
+  b->t_start = std::chrono::steady_clock::now();
+  bool ok = cudaMalloc(&b->d_top, sizeof(TopModel)) == cudaSuccess && cudaMalloc(&b->d_aux, sizeof(BuildAux)) == cudaSuccess &&
+            cudaMalloc(&b->d_scratch, shard_scratch_bytes()) == cudaSuccess &&
+            cudaMalloc(&b->d_stats, stats_scratch_bytes(branch_factor)) == cudaSuccess;
+  for (int q = 0; q < 6; ++q) ok = ok && cudaEventCreate(&b->ev_begin[q]) == cudaSuccess && cudaEventCreate(&b->ev_end[q]) == cudaSuccess;
+  if (!ok) { rmi_shard_build_destroy(b); return fail(RMI_ERR_CUDA, "rmi_shard_build_create: device allocation failed"); }
+  *out = b;
+  return RMI_OK;
+}
+
+int rmi_shard_phase(rmi_shard_build* b, int phase) {
+  if (!b) return fail(RMI_ERR_INVALID, "rmi_shard_phase: null build");
+  CUDA_TRY(cudaSetDevice(b->ds->device));
+  switch (b->ds->key_type) {
+    case RMI_KEY_U64: return shard_phase_typed<u64>(b, phase);
+    case RMI_KEY_U32: return shard_phase_typed<u32>(b, phase);
+    default: return shard_phase_typed<double>(b, phase);
+  }
+}
+
+int rmi_shard_set_halo(rmi_shard_build* b, uint64_t halo_keys) {
+  if (!b) return fail(RMI_ERR_INVALID, "rmi_shard_set_halo: null build");
+  if (halo_keys > b->info.halo_capacity) return fail(RMI_ERR_INVALID, "rmi_shard_set_halo: halo exceeds the capacity behind the local keys");
+  b->halo = halo_keys;
+  return RMI_OK;
+}
+
+int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
+  if (!b || !out) return fail(RMI_ERR_INVALID, "rmi_shard_finish: null argument");
+  CUDA_TRY(cudaSetDevice(b->ds->device));
+  const uint64_t N = b->N, n = b->info.n_global;
+  const int ppm = leaf_params_per_model(b->leaf->kind);
+  const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0;
+  auto box = new ResultBox();
+  bool host_ok = box->scalars.resize(sizeof(BuildAux) + sizeof(TopModel));
+  if (!stats_only) host_ok = host_ok && box->l1_params.resize((size_t)N * ppm) && box->l1_errors.resize(N) && box->l1_counts.resize(N);
+  if (!host_ok) { delete box; return fail(RMI_ERR_CUDA, "pinned host allocation for the results failed"); }
+  BuildAux& h_aux = *reinterpret_cast<BuildAux*>(box->scalars.data());
+  TopModel& h_top = *reinterpret_cast<TopModel*>(box->scalars.data() + sizeof(BuildAux));
+  unsigned h_status = 0;
+  cudaMemcpyAsync(&h_aux, b->d_aux, sizeof(BuildAux), cudaMemcpyDeviceToHost, b->st);
+  cudaMemcpyAsync(&h_top, b->d_top, sizeof(TopModel), cudaMemcpyDeviceToHost, b->st);
+  if (!stats_only) {
+    cudaMemcpyAsync(box->l1_params.data(), b->buf.params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, b->st);
+    cudaMemcpyAsync(box->l1_errors.data(), b->buf.errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, b->st);
+    cudaMemcpyAsync(box->l1_counts.data(), b->buf.counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, b->st);
+  }
+  cudaError_t e = cudaStreamSynchronize(b->st);
+  if (e == cudaSuccess) e = cudaMemcpy(&h_status, b->buf.status, sizeof(unsigned), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { delete box; return fail(RMI_ERR_CUDA, std::string("rmi_shard_finish: ") + cudaGetErrorString(e)); }
+  unsigned st_all = b->host_status | h_aux.status | h_status;   // buffers.status holds the MAX over ranks
+  if (st_all) {
+    delete box;
+    std::string msg = status_text(b->host_status | h_aux.status);
+    if (msg.empty()) msg = "another rank reported a failure";
+    if (st_all & ST_HALO_TOO_SMALL) msg += (msg.empty() ? "" : "; ") + std::string("a leaf reaches past the halo copied from the next rank");
+    return fail(RMI_ERR_PANIC, msg);
+  }
+  rmi_result& R = box->pub;
+  memset(&R, 0, sizeof(R));
+  R.num_rmi_rows = n; R.num_data_rows = n; R.branching_factor = N;
+  R.model_max_error = h_aux.max_error;
+  R.model_max_error_idx = h_aux.max_error_idx;
+  R.model_avg_error = (double)h_aux.sum_n_err / (double)n;
+  R.model_avg_l2_error = h_aux.sum_l2;
+  R.model_avg_log2_error = h_aux.sum_log2 / (double)n;
+  R.model_max_log2_error = std::log2((double)h_aux.max_error);
+  R.l0_model_id = b->top->kind;
+  R.l0_bradix_high = 1;
+  if (b->top->kind == M_RADIX) R.l0_num_iparams = 2; else R.l0_num_fparams = 2;
+  for (int q = 0; q < 4; ++q) { R.l0_fparams[q] = h_top.f[q]; R.l0_iparams[q] = h_top.ip[q]; }
+  R.l1_model_id = b->leaf->kind;
+  R.l1_params_per_model = ppm;
+  R.l1_params = stats_only ? nullptr : box->l1_params.data();
+  R.l1_errors = stats_only ? nullptr : box->l1_errors.data();
+  R.l1_counts = stats_only ? nullptr : box->l1_counts.data();
+  {   // device time of this rank's phases (collectives between them are not included)
+    const int map[6] = {0, 0, 1, 1, 2, 3};
+    for (int q = 0; q < 6; ++q) {
+      if (!b->ran[q]) continue;
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, b->ev_begin[q], b->ev_end[q]) == cudaSuccess) {
+        R.phase_device_ns[map[q]] += (uint64_t)((double)ms * 1e6);
+        R.device_time_ns += (uint64_t)((double)ms * 1e6);
+      }
+    }
+  }
+  R.could_not_replace = 0;   // per-rank counters are not reduced; the warning condition is local
+  R.build_time_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - b->t_start).count();
+  *out = &box->pub;
+  return RMI_OK;
+}
+
+void rmi_shard_build_destroy(rmi_shard_build* b) {
+  if (!b) return;
+  cudaFree(b->d_top); cudaFree(b->d_aux); cudaFree(b->d_scratch); cudaFree(b->d_stats);
+  for (int q = 0; q < 6; ++q) { if (b->ev_begin[q]) cudaEventDestroy(b->ev_begin[q]); if (b->ev_end[q]) cudaEventDestroy(b->ev_end[q]); }
+  delete b;
 }
 
 }  // extern "C"

@@ -25,6 +25,16 @@ template <class T> __device__ __forceinline__ u64 run_start(const T* __restrict_
   return lo;
 }
 
+// Duplicate-fixed GLOBAL offset of local item i on a rank's slab: the run may start on an
+// earlier rank, whose last key and offset travel in (has_prev, prev_key, prev_F).
+template <class T>
+__device__ __forceinline__ u64 global_run_start(const T* __restrict__ keys, u64 i, u64 base, int has_prev, T prev_key,
+                                                u64 prev_F) {
+  u64 ls = run_start(keys, i);
+  if (ls == 0 && has_prev && keys[0] == prev_key) return prev_F;
+  return base + ls;
+}
+
 // Four consecutive keys starting at `base` (base % 4 == 0): two 128-bit loads for 8-byte
 // keys, one for 4-byte keys, when the array is 16-byte aligned and all four are in range;
 // scalar loads otherwise (entries past the end repeat the last key).  Returns how many are valid.

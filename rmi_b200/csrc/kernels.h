@@ -22,7 +22,8 @@ enum StatusBit : unsigned {
   ST_HIST_BINS = 1u << 8,         // histogram.rs:25-27 division by zero / items_per_bin >= 1
   ST_NEG_VARIANCE = 1u << 9,      // linear.rs:48     assert!(var >= 0.0)
   ST_BRADIX_OOB = 1u << 10,       // balanced_radix.rs:28 counts[] index out of bounds
-  ST_RADIX_TABLE_OOB = 1u << 11   // radix.rs:103     assert!(current_radix < hint_table.len())
+  ST_RADIX_TABLE_OOB = 1u << 11,  // radix.rs:103     assert!(current_radix < hint_table.len())
+  ST_HALO_TOO_SMALL = 1u << 12    // sharded build: a leaf reaches past the keys copied from the next rank
 };
 
 // Small device-resident scalars shared between kernels of one build.
@@ -40,6 +41,25 @@ struct BuildAux {
   int best_valid, _pad;
   u64 could_not_replace;
 };
+
+// Position of a rank's slab inside the global sorted key array (single-GPU: base 0, the whole
+// array, no neighbours).  Kernels index the LOCAL slab; every offset that enters a fit or an
+// error bound is global (base + local).
+template <class T> struct Shard {
+  u64 base;       // global index of local key 0
+  u64 n_global;   // keys in the whole data set
+  u64 n_local;    // keys this rank owns
+  u64 n_avail;    // n_local + halo keys (copied from the following ranks) readable after them
+  int has_prev;   // some earlier rank holds keys; prev_key / prev_F describe the last of them
+  int is_last;    // this rank holds the data set's last key
+  T prev_key;
+  u64 prev_F;     // duplicate-fixed global offset of prev_key
+};
+template <class T> inline Shard<T> whole_array(u64 n) {
+  Shard<T> s;
+  s.base = 0; s.n_global = n; s.n_local = n; s.n_avail = n; s.has_prev = 0; s.is_last = 1; s.prev_key = T(); s.prev_F = 0;
+  return s;
+}
 
 struct Launch {
   cudaStream_t stream;
@@ -72,11 +92,26 @@ void compute_leaf_bounds(const Launch& L, const T* keys, u64 n, int top_kind, co
 // pass / max error, lower-bound widening (two_layer.rs:20-99, :186-259,
 // lower_bound_correction.rs:91-137).  Writes N x ppm params, N errors, N counts.
 template <class T>
-void fit_leaves(const Launch& L, const T* keys, u64 n, int leaf_kind, u64 num_leaves, const u64* d_S,
+void fit_leaves(const Launch& L, const T* keys, const Shard<T>& shard, int leaf_kind, u64 num_leaves, const u64* d_S,
                 BuildAux* d_aux, double* d_params, u64* d_errors, u64* d_counts);
 // Summary statistics over the N leaves (two_layer.rs:267-284) into d_aux.
 void leaf_statistics(const Launch& L, u64 n, u64 num_leaves, const u64* d_errors, const u64* d_counts,
                      BuildAux* d_aux, void* scratch);
 size_t stats_scratch_bytes(u64 num_leaves);
+
+// ---- range-partitioned build phases (kernels_shard.cu) ---------------------------------------
+size_t shard_scratch_bytes();
+template <class T>
+unsigned shard_top_local(const Launch& L, const T* keys, const Shard<T>& sh, int kind, u64 N, double px, double py,
+                         void* scratch, double* d_sums);
+template <class T>
+void shard_top_finish(const Launch& L, const Shard<T>& sh, int kind, u64 N, double px, double py, const double* d_sums,
+                      T first_key, T last_key, u64 last_F, TopModel* d_top, BuildAux* d_aux);
+template <class T>
+void shard_bounds(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N, u64* d_S);
+template <class T>
+void shard_split(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N,
+                 const u64* d_S, BuildAux* d_aux);
+void shard_copy_status(const Launch& L, const BuildAux* d_aux, unsigned* d_out);
 
 }  // namespace rmi

@@ -312,9 +312,14 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
 // array — [last key of the previous leaf] + own keys + [first key of the next leaf], neither
 // across the half boundary — whose item offsets are the duplicate-fixed global offsets F.
 // ------------------------------------------------------------------------------------------
-template <class I> struct LeafRange {
-  I lo, hi;      // all keys of the leaf: [S[j], S[j+1])
-  I vs, ve;      // training vector
+template <class T, class I> struct LeafRange {
+  I lo, hi;        // all keys of the leaf, LOCAL indices: [S[j], S[j+1]) - base
+  I vs, ve;        // training vector, LOCAL indices (without a remote first item)
+  bool p_remote;   // the vector's first item is the previous rank's last key (pkey, pF)
+  T pkey;
+  u64 pF;
+  u64 F0;          // duplicate-fixed global offset of the vector's first item
+  u64 vs_global;   // global index of the vector's first item
 };
 
 // The reference's Welford step (linear.rs:24-34) with the two count divisions done by
@@ -389,12 +394,18 @@ template <class T> struct ItemTracker {
 // f receives Model::params().  Every lane of the warp must call this (with vs == ve if it has
 // no leaf or an empty vector).
 template <class T, class I, int LEAF>
-__device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, u64 n_keys, unsigned char* wsm,
-                                         const LeafRange<I>& r, const double* rcp, double* f, unsigned& bad) {
-  const I L = r.ve - r.vs;
-  const u64 F0 = L ? run_start(keys, (u64)r.vs) : 0;
-  const T kfirst = L ? keys[r.vs] : T();
-  const double vsd = __ull2double_rn((u64)r.vs), f0d = __ull2double_rn(F0);
+__device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard<T>& sh, unsigned char* wsm,
+                                         const LeafRange<T, I>& r, const double* rcp, double* f, unsigned& bad) {
+  const u64 n_keys = sh.n_avail;
+  const I L = (I)(r.ve - r.vs) + (r.p_remote ? (I)1 : (I)0);
+  const T kfirst = r.p_remote ? r.pkey : (L ? keys[r.vs] : T());
+  const double vsd = __ull2double_rn(r.vs_global), f0d = __ull2double_rn(r.F0);
+  // one pass over the vector: the remote first item (if any), then the local stream
+  auto vector_pass = [&](auto&& fn) {
+    if (r.p_remote) fn(r.pkey, (I)0);
+    stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, fn);
+  };
+  auto gF = [&](u64 local_i) { return global_run_start(keys, local_i, sh.base, sh.has_prev, sh.prev_key, sh.prev_F); };
   constexpr bool CHECKED = Key<T>::is_float;
   if (LEAF == M_LINEAR || LEAF == M_LOGLINEAR) {
     // linear.rs:79-83 / :61-72,169-173 — drained stream: vector + repeat of the final item
@@ -402,7 +413,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, u64 n_keys,
     w.init(rcp);
     ItemTracker<T> it;
     it.init(kfirst, vsd, f0d);
-    stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) {
+    vector_pass([&](T k, I) {
       double yy = it.next(k);
       if (LEAF == M_LOGLINEAR) { yy = log(yy); if (!isfinite(yy)) return; }
       w.push(Key<T>::as_float(k), yy);
@@ -424,7 +435,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, u64 n_keys,
     ItemTracker<T> it;
     it.init(kfirst, vsd, f0d);
     u64 pos = 0;
-    stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) {
+    vector_pass([&](T k, I) {
       double yy = it.next(k);
       if (ok && pos >= bnd && pos < (u64)L - bnd) w.push(Key<T>::as_float(k), yy);
       ++pos;
@@ -436,7 +447,10 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, u64 n_keys,
     double la, lb;
     T k0 = kfirst, k1 = T();
     double y0 = f0d, y1 = 0.0;
-    if (L > 0) { k1 = keys[r.ve - 1]; y1 = __ull2double_rn(run_start(keys, (u64)r.ve - 1)); }
+    if (L > 0) {
+      if (r.ve > r.vs) { k1 = keys[r.ve - 1]; y1 = __ull2double_rn(gF((u64)r.ve - 1)); }
+      else { k1 = r.pkey; y1 = __ull2double_rn(r.pF); }
+    }
     if (L == 0) { la = 0.0; lb = 0.0; }
     else if (L == 1 || k0 == k1) { la = y0; lb = 0.0; }
     else {
@@ -453,7 +467,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, u64 n_keys,
     {
       ItemTracker<T> it;
       it.init(kfirst, vsd, f0d);
-      stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) {
+      vector_pass([&](T k, I) {
         double yy = it.next(k);
         if (k != k0) uniq = true;
         if (!found1) {
@@ -470,7 +484,11 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, u64 n_keys,
       double sxp = 0.0, syp = 0.0;
       for (u64 p = (u64)r.ve; p-- > (u64)r.vs;) {   // from the back; almost always the second-to-last item
         double sx = scale3(Key<T>::as_float(keys[p]), xmin, xmax);
-        if (sx < 1.0) { found2 = true; sxp = sx; syp = scale3(__ull2double_rn(run_start(keys, p)), ymin, ymax); break; }
+        if (sx < 1.0) { found2 = true; sxp = sx; syp = scale3(__ull2double_rn(gF(p)), ymin, ymax); break; }
+      }
+      if (!found2 && r.p_remote) {
+        double sx = scale3(Key<T>::as_float(r.pkey), xmin, xmax);
+        if (sx < 1.0) { found2 = true; sxp = sx; syp = scale3(__ull2double_rn(r.pF), ymin, ymax); }
       }
       if (!found1 || !found2) { bad |= ST_CUBIC_UNWRAP; a = b = c = d = 0.0; }
       else {
@@ -509,7 +527,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, u64 n_keys,
         our_error = __dadd_rn(our_error, fabs(__dadd_rn(predict_float<M_CUBIC>(cf, x), -yy)));
         lin_error = __dadd_rn(lin_error, fabs(__dadd_rn(predict_float<M_LINEAR>(lf, x), -yy)));
       };
-      stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) { acc(Key<T>::as_float(k), it.next(k)); });
+      vector_pass([&](T k, I) { acc(Key<T>::as_float(k), it.next(k)); });
       if (L > 0) acc(Key<T>::as_float(it.pk), it.pyd);
     }
     if (lin_error < our_error) { f[0] = 0.0; f[1] = 0.0; f[2] = lb; f[3] = la; }
@@ -524,13 +542,13 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, u64 n_keys,
     };
     ItemTracker<T> it;
     it.init(kfirst, vsd, f0d);
-    stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) {
+    vector_pass([&](T k, I) {
       double yy = it.next(k);
       mean = __dadd_rn(mean, __ddiv_rn(tx(k), nf));
       scale = rust_fmax(scale, yy);
     });
     if (L > 0) { mean = __dadd_rn(mean, __ddiv_rn(tx(it.pk), nf)); scale = rust_fmax(scale, it.pyd); }
-    stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, [&](T k, I) {
+    vector_pass([&](T k, I) {
       double dlt = __dadd_rn(tx(k), -mean);
       stdev = __dadd_rn(stdev, __dmul_rn(dlt, dlt));
     });
@@ -579,7 +597,7 @@ constexpr size_t leaf_smem_bytes() {
 
 template <class T, class I, int LEAF>
 __global__ void __launch_bounds__(LEAF_THREADS)
-k_leaf(const T* __restrict__ keys, u64 n, u64 N, const u64* __restrict__ S, BuildAux* aux,
+k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restrict__ S, BuildAux* aux,
        double* __restrict__ params, u64* __restrict__ errors, u64* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_rcp = reinterpret_cast<double*>(smem_raw);
@@ -587,74 +605,108 @@ k_leaf(const T* __restrict__ keys, u64 n, u64 N, const u64* __restrict__ S, Buil
   for (int c = threadIdx.x; c < RCP_TABLE; c += blockDim.x) s_rcp[c] = c ? __drcp_rn((double)c) : 0.0;
   __syncthreads();
   const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = j < N;
   constexpr int PPM = leaf_params_per_model(LEAF);
   constexpr bool NANCHECK = Key<T>::is_float || LEAF == M_LOGLINEAR || LEAF == M_NORMAL || LEAF == M_LOGNORMAL;
+  const u64 n = sh.n_global;
   const I nI = (I)n;
+  const I baseI = (I)sh.base;
 
-  LeafRange<I> r;
-  r.lo = live ? (I)S[j] : (I)0;
-  r.hi = live ? (I)S[j + 1] : (I)0;
+  // global leaf range; a rank builds the leaves whose FIRST index lies in its slab
+  u64 g_lo = j < N ? S[j] : 0, g_hi = j < N ? S[j + 1] : 0;
   unsigned bad = 0;
-  if (r.hi < r.lo) { bad |= ST_NOT_SORTED; r.hi = r.lo; }   // cannot happen on sorted keys
-  // which half does leaf j belong to (two_layer.rs:147-175)
-  I half_lo, half_hi;
-  u64 first_leaf;
+  if (g_hi < g_lo) { bad |= ST_NOT_SORTED; g_hi = g_lo; }   // cannot happen on sorted keys
+  // owner of leaf j: the rank whose slab holds index S[j]; S[j] == n (trailing empty leaves)
+  // belongs to the last rank
+  const bool live = j < N && ((g_lo >= sh.base && g_lo < sh.base + sh.n_local) || (g_lo >= n && sh.is_last));
+
+  // which half does leaf j belong to (two_layer.rs:147-175), in global indices
+  u64 half_lo, half_hi, first_leaf;
   if (aux->has_split) {
     u64 split = aux->split_idx, st = aux->split_target;
-    if (j < st) { half_lo = 0; half_hi = (I)split; first_leaf = 0; }
-    else { half_lo = (I)(split + 1); half_hi = nI; first_leaf = st; }
-  } else { half_lo = 0; half_hi = nI; first_leaf = 0; }
+    if (j < st) { half_lo = 0; half_hi = split; first_leaf = 0; }
+    else { half_lo = split + 1; half_hi = n; first_leaf = st; }
+  } else { half_lo = 0; half_hi = n; first_leaf = 0; }
+
+  LeafRange<T, I> r;
+  r.lo = live ? (I)(g_lo - sh.base) : (I)0;
+  r.hi = live ? (I)(g_hi - sh.base) : (I)0;
+  r.p_remote = false; r.pkey = T(); r.pF = 0; r.F0 = 0; r.vs_global = 0;
+  r.vs = r.ve = 0;
   {
-    I own_lo = r.lo > half_lo ? r.lo : half_lo;
-    I own_hi = r.hi < half_hi ? r.hi : half_hi;
+    u64 own_lo = g_lo > half_lo ? g_lo : half_lo;
+    u64 own_hi = g_hi < half_hi ? g_hi : half_hi;
+    u64 vs_g = 0, ve_g = 0;
     if (live && own_hi > own_lo) {
-      r.vs = own_lo > half_lo ? own_lo - 1 : own_lo;     // + last key of the previous leaf
-      r.ve = own_hi < half_hi ? own_hi + 1 : own_hi;     // + first key of the next leaf
+      vs_g = own_lo > half_lo ? own_lo - 1 : own_lo;     // + last key of the previous leaf
+      ve_g = own_hi < half_hi ? own_hi + 1 : own_hi;     // + first key of the next leaf
     } else if (live && j == first_leaf && half_lo < half_hi) {
       // the half's first leaf, if it owns no key, is trained on the half's first item alone
       // (two_layer.rs:52-62 with an empty second_layer_data); other empty leaves on empty data
-      r.vs = half_lo; r.ve = half_lo + 1;
-    } else { r.vs = r.ve = 0; }
+      vs_g = half_lo; ve_g = half_lo + 1;
+    }
+    if (ve_g > vs_g) {
+      if (ve_g > sh.base + sh.n_avail) { bad |= ST_HALO_TOO_SMALL; ve_g = vs_g; }
+      else {
+        r.vs_global = vs_g;
+        if (vs_g < sh.base) {       // only possible as base - 1: the previous rank's last key
+          r.p_remote = true; r.pkey = sh.prev_key; r.pF = sh.prev_F; r.F0 = sh.prev_F;
+          r.vs = 0;
+        } else {
+          r.vs = (I)(vs_g - sh.base);
+          r.F0 = global_run_start(keys, (u64)r.vs, sh.base, sh.has_prev, sh.prev_key, sh.prev_F);
+        }
+        r.ve = (I)(ve_g - sh.base);
+      }
+    }
   }
+  if (live && g_hi > sh.base + sh.n_avail) { bad |= ST_HALO_TOO_SMALL; r.hi = r.lo; }
 
   double f[4] = {0.0, 0.0, 0.0, 0.0};
-  fit_leaf<T, I, LEAF>(keys, n, wsm, r, s_rcp, f, bad);
+  fit_leaf<T, I, LEAF>(keys, sh, wsm, r, s_rcp, f, bad);
 
   // two_layer.rs:186-197: empty leaves (lower-bound-correction sense) except the last
-  const u64 next_idx = (u64)r.hi;                                   // lb.next_index(j) = S[j+1]
-  if (live && j + 1 < N && r.lo == r.hi) {
+  const u64 next_idx = g_hi;                                        // lb.next_index(j) = S[j+1]
+  if (live && j + 1 < N && g_lo == g_hi) {
     if (!set_constant<LEAF>(f, next_idx)) atomicAdd(&aux->could_not_replace, 1ull);
   }
 
   // two_layer.rs:207-217 forward pass over the leaf's own keys + longest run
   // (lower_bound_correction.rs:101-119: a run is recorded when the NEXT run starts, so the
   // data set's final run never is).  Seeding the tracker with the key before the leaf (or the
-  // leaf's own first key at index 0) makes the first item an ordinary one and checks the
-  // ordering across the leaf boundary too.
-  const T prev_key = (live && r.lo > 0) ? keys[r.lo - 1] : Key<T>::zero_value();
+  // leaf's own first key at global index 0) makes the first item an ordinary one.
+  T prev_key = Key<T>::zero_value();
+  bool have_prev = false;
+  if (live && g_lo > 0 && g_lo < n) {
+    if (r.lo > 0) { prev_key = keys[r.lo - 1]; have_prev = true; }
+    else if (sh.has_prev) { prev_key = sh.prev_key; have_prev = true; }
+  } else if (live && g_lo >= n && n > 0) {
+    // trailing empty leaf: the key before it is the data set's last key
+    if (sh.n_local > 0) { prev_key = keys[sh.n_local - 1]; have_prev = true; }
+    else if (sh.has_prev) { prev_key = sh.prev_key; have_prev = true; }
+  }
   I max_err = 0, run_max = 0;
   {
-    T pk = (live && r.lo == 0 && r.hi > 0) ? keys[0] : prev_key;
-    I F = r.lo, run = 0;
-    stream_pass<T, I>(keys, n, wsm, r.lo, r.hi, [&](T k, I i) {
-      if (k != pk) { run_max = run > run_max ? run : run_max; run = 0; F = i; }
+    T pk = (live && g_lo == 0 && g_hi > 0) ? keys[0] : prev_key;
+    I F = (I)g_lo, run = 0;
+    stream_pass<T, I>(keys, sh.n_avail, wsm, r.lo, r.hi, [&](T k, I i) {
+      if (k != pk) { run_max = run > run_max ? run : run_max; run = 0; F = (I)(i + baseI); }
       run += 1;
       pk = k;
       I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
       I e = pred > F ? pred - F : F - pred;
       max_err = e > max_err ? e : max_err;
     });
-    if (r.hi < nI && run > run_max) run_max = run;
+    if (g_hi < n && run > run_max) run_max = run;
   }
   if (bad) set_status(aux, bad);
   if (!live) return;
-  u64 cnt = (u64)(r.hi - r.lo);
-  if (r.hi == nI && r.lo < r.hi) cnt += 1;   // the drained iterator's repeated final item
+  u64 cnt = g_hi - g_lo;
+  if (g_hi == n && g_lo < g_hi) cnt += 1;   // the drained iterator's repeated final item
 
   // two_layer.rs:226-259 widening
-  T next_key = next_idx < n ? keys[next_idx] : Key<T>::max_value();
-  u64 first_idx = j == 0 ? S[1] : (u64)r.lo;                       // lb.next_index(max(j-1, 0))
+  T next_key = next_idx < n ? keys[next_idx - sh.base] : Key<T>::max_value();
+  if (!have_prev) prev_key = Key<T>::zero_value();
+  u64 first_idx = j == 0 ? S[1] : g_lo;                            // lb.next_index(max(j-1, 0))
   u64 up = leaf_predict64<LEAF>(f, Key<T>::as_float(Key<T>::minus_epsilon(next_key)));
   u64 upper_error = error_between(up, next_idx + 1, n);
   u64 lp = leaf_predict64<LEAF>(f, Key<T>::as_float(Key<T>::plus_epsilon(prev_key)));
@@ -789,16 +841,16 @@ void launch_bounds_impl(const Launch& L, const T* keys, u64 n, const TopModel* d
 }
 
 template <class T, int LEAF>
-void launch_leaf(const Launch& L, const T* keys, u64 n, u64 N, const u64* d_S, BuildAux* d_aux, double* d_params,
-                 u64* d_errors, u64* d_counts) {
+void launch_leaf(const Launch& L, const T* keys, const Shard<T>& sh, u64 N, const u64* d_S, BuildAux* d_aux,
+                 double* d_params, u64* d_errors, u64* d_counts) {
   u64 blocks = (N + LEAF_THREADS - 1) / LEAF_THREADS;
   constexpr size_t smem = leaf_smem_bytes();
-  if (n < 0xfffffff0ull) {   // 32-bit indices
+  if (sh.n_global < 0xfffffff0ull) {   // 32-bit indices
     cudaFuncSetAttribute(k_leaf<T, u32, LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_leaf<T, u32, LEAF><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, n, N, d_S, d_aux, d_params, d_errors, d_counts);
+    k_leaf<T, u32, LEAF><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts);
   } else {
     cudaFuncSetAttribute(k_leaf<T, u64, LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_leaf<T, u64, LEAF><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, n, N, d_S, d_aux, d_params, d_errors, d_counts);
+    k_leaf<T, u64, LEAF><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts);
   }
   count_launch();
 }
@@ -825,16 +877,16 @@ void compute_leaf_bounds(const Launch& L, const T* keys, u64 n, int top_kind, co
 }
 
 template <class T>
-void fit_leaves(const Launch& L, const T* keys, u64 n, int leaf_kind, u64 N, const u64* d_S, BuildAux* d_aux,
+void fit_leaves(const Launch& L, const T* keys, const Shard<T>& sh, int leaf_kind, u64 N, const u64* d_S, BuildAux* d_aux,
                 double* d_params, u64* d_errors, u64* d_counts) {
   switch (leaf_kind) {
-    case M_LINEAR: launch_leaf<T, M_LINEAR>(L, keys, n, N, d_S, d_aux, d_params, d_errors, d_counts); break;
-    case M_ROBUST_LINEAR: launch_leaf<T, M_ROBUST_LINEAR>(L, keys, n, N, d_S, d_aux, d_params, d_errors, d_counts); break;
-    case M_LINEAR_SPLINE: launch_leaf<T, M_LINEAR_SPLINE>(L, keys, n, N, d_S, d_aux, d_params, d_errors, d_counts); break;
-    case M_CUBIC: launch_leaf<T, M_CUBIC>(L, keys, n, N, d_S, d_aux, d_params, d_errors, d_counts); break;
-    case M_LOGLINEAR: launch_leaf<T, M_LOGLINEAR>(L, keys, n, N, d_S, d_aux, d_params, d_errors, d_counts); break;
-    case M_NORMAL: launch_leaf<T, M_NORMAL>(L, keys, n, N, d_S, d_aux, d_params, d_errors, d_counts); break;
-    case M_LOGNORMAL: launch_leaf<T, M_LOGNORMAL>(L, keys, n, N, d_S, d_aux, d_params, d_errors, d_counts); break;
+    case M_LINEAR: launch_leaf<T, M_LINEAR>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts); break;
+    case M_ROBUST_LINEAR: launch_leaf<T, M_ROBUST_LINEAR>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts); break;
+    case M_LINEAR_SPLINE: launch_leaf<T, M_LINEAR_SPLINE>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts); break;
+    case M_CUBIC: launch_leaf<T, M_CUBIC>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts); break;
+    case M_LOGLINEAR: launch_leaf<T, M_LOGLINEAR>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts); break;
+    case M_NORMAL: launch_leaf<T, M_NORMAL>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts); break;
+    case M_LOGNORMAL: launch_leaf<T, M_LOGNORMAL>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts); break;
     default: break;
   }
 }
@@ -876,7 +928,7 @@ void leaf_statistics(const Launch& L, u64 n, u64 N, const u64* d_errors, const u
 
 #define INST(T)                                                                                                  \
   template void compute_leaf_bounds<T>(const Launch&, const T*, u64, int, const TopModel*, u64, u64*, BuildAux*, bool); \
-  template void fit_leaves<T>(const Launch&, const T*, u64, int, u64, const u64*, BuildAux*, double*, u64*, u64*);
+  template void fit_leaves<T>(const Launch&, const T*, const Shard<T>&, int, u64, const u64*, BuildAux*, double*, u64*, u64*);
 INST(u64)
 INST(u32)
 INST(double)

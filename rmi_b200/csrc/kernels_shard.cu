@@ -1,0 +1,292 @@
+// kernels_shard.cu — the pieces of a range-partitioned (multi-GPU) build that differ from the
+// single-GPU path.  Every rank holds a contiguous slab of the globally sorted key array
+// (Shard<T>, kernels.h); the top model and the leaf boundaries S are made global by small
+// collectives issued by the host between these phases (rmi_b200/sharded.py):
+//
+//   phase TOP_LOCAL   k_shard_slr_partial / k_shard_slr_reduce   -> 5 partial sums per rank
+//        [all-reduce SUM of 5 doubles]                             (linear, robust_linear)
+//   phase TOP_FINISH  k_shard_slr_solve  or  k_shard_top_from_ends (linear_spline, radix: O(1)
+//                     functions of the global first / last key)
+//   phase BOUNDS      k_shard_bounds_search -> S_local (global indices, n_global where none)
+//        [all-reduce MIN of (N+1) u64]
+//   phase SPLIT       k_split_from_S
+//        [halo: each rank receives the keys of its last leaf that live on the next rank(s)]
+//   phase LEAF        k_leaf (kernels_leaf.cu) on the leaves whose first key is local
+//        [all-reduce SUM of the zero-initialised parameter / error / count arrays]
+//   phase STATS       leaf_statistics
+//
+// The fits themselves are the same code as on one GPU; only offsets become global
+// (base + local) and the item before local index 0 comes from the previous rank.
+#include "device_util.cuh"
+#include "kernels.h"
+
+namespace rmi {
+
+namespace {
+
+constexpr int SH_THREADS = 256;
+constexpr int SH_MAX_BLOCKS = 148 * 8;
+
+__device__ __forceinline__ void set_status(BuildAux* aux, unsigned bit) { atomicOr(&aux->status, bit); }
+
+// Partial sums of the top-level simple linear regression over the global item range
+// [g0, g1) restricted to this rank's slab, about the common pivot (px, py).
+template <class T>
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_slr_partial(const T* __restrict__ keys, const Shard<T> sh, u64 g0, u64 g1, double sf, int use_sf, double px,
+                    double py, double* __restrict__ partials) {
+  __shared__ double sm[32];
+  // local range
+  u64 lo = g0 > sh.base ? g0 - sh.base : 0;
+  u64 hi = g1 > sh.base ? g1 - sh.base : 0;
+  if (hi > sh.n_local) hi = sh.n_local;
+  double sx = 0, sy = 0, sxx = 0, sxy = 0;
+  unsigned icnt = 0;
+  const bool aligned = is_aligned16(keys);
+  u64 stride = (u64)gridDim.x * blockDim.x * 4;
+  for (u64 b = (lo & ~3ull) + ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; b < hi; b += stride) {
+    T k[4];
+    int c = load_keys4(keys, b, sh.n_local, aligned, k);
+    u64 F = global_run_start(keys, b, sh.base, sh.has_prev, sh.prev_key, sh.prev_F);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e >= c) break;
+      u64 i = b + e;
+      if (e > 0 && k[e] != k[e - 1]) F = sh.base + i;
+      if (i < lo || i >= hi) continue;
+      double x = Key<T>::as_float(k[e]);
+      double y = __ull2double_rn(scale_offset(F, sf, use_sf));
+      double dx = x - px, dy = y - py;
+      sx += dx; sy += dy; sxx = fma(dx, dx, sxx); sxy = fma(dx, dy, sxy);
+      icnt += 1;
+    }
+  }
+  double r0 = block_sum(sx, sm), r1 = block_sum(sy, sm), r2 = block_sum(sxx, sm), r3 = block_sum(sxy, sm),
+         r4 = block_sum((double)icnt, sm);
+  if (threadIdx.x == 0) {
+    double* p = partials + (size_t)blockIdx.x * 5;
+    p[0] = r0; p[1] = r1; p[2] = r2; p[3] = r3; p[4] = r4;
+  }
+}
+
+// Block partials -> sums[0..5); the rank holding the global last key adds the drained
+// iterator's repeated final item (models/mod.rs:180) when the fit drains the iterator.
+template <class T>
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_slr_reduce(const T* __restrict__ keys, const Shard<T> sh, int repeat, double sf, int use_sf, double px, double py,
+                   const double* __restrict__ partials, int nblocks, double* __restrict__ sums) {
+  __shared__ double sm[32];
+  double s[5] = {0, 0, 0, 0, 0};
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+    for (int q = 0; q < 5; ++q) s[q] += partials[(size_t)b * 5 + q];
+  double r[5];
+  for (int q = 0; q < 5; ++q) r[q] = block_sum(s[q], sm);
+  if (threadIdx.x != 0) return;
+  if (repeat && sh.is_last && sh.n_local > 0) {
+    u64 i = sh.n_local - 1;
+    double x = Key<T>::as_float(keys[i]);
+    u64 F = global_run_start(keys, i, sh.base, sh.has_prev, sh.prev_key, sh.prev_F);
+    double y = __ull2double_rn(scale_offset(F, sf, use_sf));
+    double dx = x - px, dy = y - py;
+    r[0] += dx; r[1] += dy; r[2] += dx * dx; r[3] += dx * dy; r[4] += 1.0;
+  }
+  for (int q = 0; q < 5; ++q) sums[q] = r[q];
+}
+
+// slr()'s closing formulas (linear.rs:36-58) on the globally reduced sums.
+__global__ void k_shard_slr_solve(const double* __restrict__ sums, double px, double py, TopModel* top, BuildAux* aux) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double sx = sums[0], sy = sums[1], sxx = sums[2], sxy = sums[3], cnt = sums[4];
+  double alpha, beta;
+  if (cnt == 0.0) { alpha = 0.0; beta = 0.0; }
+  else {
+    double mx = sx / cnt, my = sy / cnt;
+    double mean_x = px + mx, mean_y = py + my;
+    if (cnt == 1.0) { alpha = mean_y; beta = 0.0; }
+    else {
+      double m2 = sxx - sx * mx, c = sxy - sx * my;
+      double cov = c / (cnt - 1.0), var = m2 / (cnt - 1.0);
+      if (!(var >= 0.0)) {
+        if (var > -1e-9 * fabs(sxx / cnt)) var = 0.0;
+        else set_status(aux, ST_NEG_VARIANCE);
+      }
+      if (var == 0.0) { alpha = mean_y; beta = 0.0; }
+      else { beta = cov / var; alpha = mean_y - beta * mean_x; }
+    }
+  }
+  top->f[0] = alpha;
+  top->f[1] = beta;
+}
+
+// Top models that are O(1) functions of the global first / last item:
+// linear_spline (linear_spline.rs:13-35) and radix (radix.rs:18-40, utils.rs:13-36).
+template <class T>
+__global__ void k_shard_top_from_ends(int kind, T first_key, T last_key, u64 last_F, u64 n, double sf, int use_sf,
+                                      TopModel* top, BuildAux* aux) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (kind == M_LINEAR_SPLINE) {
+    double alpha, beta;
+    double y0 = __ull2double_rn(scale_offset(0, sf, use_sf));
+    if (n == 0) { alpha = 0.0; beta = 0.0; }
+    else if (n == 1 || first_key == last_key) { alpha = y0; beta = 0.0; }
+    else {
+      double y1 = __ull2double_rn(scale_offset(n - 1, sf, use_sf));
+      double x0 = Key<T>::as_float(first_key), x1 = Key<T>::as_float(last_key);
+      double slope = __ddiv_rn(__dadd_rn(y0, -y1), __dadd_rn(x0, -x1));
+      alpha = __dadd_rn(y0, -__dmul_rn(slope, x0));
+      beta = slope;
+    }
+    top->f[0] = alpha; top->f[1] = beta;
+  } else if (kind == M_RADIX) {
+    int prefix = common_prefix_sorted(Key<T>::as_int(first_key), Key<T>::as_int(last_key));
+    u64 largest = scale_offset(last_F, sf, use_sf);
+    aux->max_scaled_y = largest;
+    int bits = num_bits_of(largest);
+    if (bits < 1) set_status(aux, ST_NUM_BITS);
+    top->ip[0] = (u64)prefix; top->ip[1] = (u64)bits;
+  }
+}
+
+// S_local[j] = global index of the first LOCAL key whose prediction reaches j, n_global if
+// none (the all-reduce MIN over ranks then yields the global S).
+template <class T, int TOP>
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_bounds_search(const T* __restrict__ keys, const Shard<T> sh, const TopModel* __restrict__ top_ptr, u64 N,
+                      u64* __restrict__ S) {
+  TopModel m = *top_ptr;
+  u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > N) return;
+  u64 v;
+  if (j == N) v = sh.n_global;
+  else if (j == 0) v = 0;
+  else {
+    u64 lo = 0, hi = sh.n_local;
+    while (lo < hi) {
+      u64 mid = lo + ((hi - lo) >> 1);
+      if (top_predict<TOP>(m, keys[mid]) >= j) hi = mid; else lo = mid + 1;
+    }
+    v = lo < sh.n_local ? sh.base + lo : sh.n_global;
+  }
+  S[j] = v;
+}
+
+// two_layer.rs:131-159 from the global S alone: split = S[N/2]; the split key's leaf is the
+// last j with S[j] == split (leaves N/2 .. that one - 1 are empty).
+template <class T, int TOP>
+__global__ void k_split_from_S(const T* __restrict__ keys, const Shard<T> sh, const TopModel* __restrict__ top_ptr,
+                               u64 N, const u64* __restrict__ S, BuildAux* aux) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  TopModel m = *top_ptr;
+  u64 n = sh.n_global;
+  if (TOP == M_LINEAR && !(m.f[1] >= 0.0)) set_status(aux, ST_NON_MONOTONE);
+  if (sh.is_last && sh.n_local > 0) {
+    bool nbc = !(TOP == M_CUBIC || TOP == M_RADIX || TOP == M_RADIX_TABLE || TOP == M_BRADIX || TOP == M_HISTOGRAM);
+    if (!nbc && top_predict<TOP>(m, keys[sh.n_local - 1]) >= N) set_status(aux, ST_TOP_OUT_OF_BOUNDS);
+  }
+  u64 split = S[N / 2];
+  aux->split_idx = split;
+  if (split >= n) { aux->has_split = 0; aux->split_target = 0; return; }
+  aux->has_split = 1;
+  if (split == 0) set_status(aux, ST_SPLIT_AT_ZERO);
+  if (split + 1 >= n) set_status(aux, ST_SPLIT_AT_END);
+  u64 lo = N / 2, hi = N;   // last j in [N/2, N) with S[j] == split  (S is non-decreasing)
+  while (lo + 1 < hi) {
+    u64 mid = lo + ((hi - lo) >> 1);
+    if (S[mid] <= split) lo = mid; else hi = mid;
+  }
+  aux->split_target = lo;
+}
+
+__global__ void k_copy_status(const BuildAux* __restrict__ aux, unsigned* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = aux->status;
+}
+
+int sh_grid(u64 n, int num_sms) {
+  u64 blocks = (n + SH_THREADS - 1) / SH_THREADS;
+  u64 cap = (u64)num_sms * 8;
+  if (cap > (u64)SH_MAX_BLOCKS) cap = SH_MAX_BLOCKS;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+size_t shard_scratch_bytes() { return (size_t)SH_MAX_BLOCKS * 5 * sizeof(double); }
+
+template <class T>
+unsigned shard_top_local(const Launch& L, const T* keys, const Shard<T>& sh, int kind, u64 N, double px, double py,
+                         void* scratch, double* d_sums) {
+  double sf = (double)N / (double)sh.n_global;
+  int use_sf = std::fabs(sf - 1.0) > DBL_EPSILON ? 1 : 0;
+  double* partials = (double*)scratch;
+  if (kind == M_LINEAR || kind == M_ROBUST_LINEAR) {
+    u64 g0 = 0, g1 = sh.n_global;
+    int repeat = 1;
+    if (kind == M_ROBUST_LINEAR) {
+      u64 n = sh.n_global;
+      if (n == 0) { g0 = g1 = 0; repeat = 0; }
+      else {
+        u64 bnd = (u64)((double)n * 0.0001);
+        if (bnd < 1) bnd = 1;
+        if (!(bnd * 2 + 1 < n)) return ST_ROBUST_TOO_SMALL;
+        g0 = bnd; g1 = n - bnd; repeat = 0;
+      }
+    }
+    int g = sh_grid((sh.n_local + 3) / 4 + 1, L.num_sms);
+    k_shard_slr_partial<T><<<g, SH_THREADS, 0, L.stream>>>(keys, sh, g0, g1, sf, use_sf, px, py, partials);
+    count_launch();
+    k_shard_slr_reduce<T><<<1, SH_THREADS, 0, L.stream>>>(keys, sh, repeat, sf, use_sf, px, py, partials, g, d_sums);
+    count_launch();
+  } else {
+    cudaMemsetAsync(d_sums, 0, 8 * sizeof(double), L.stream);
+  }
+  return 0;
+}
+
+template <class T>
+void shard_top_finish(const Launch& L, const Shard<T>& sh, int kind, u64 N, double px, double py, const double* d_sums,
+                      T first_key, T last_key, u64 last_F, TopModel* d_top, BuildAux* d_aux) {
+  double sf = (double)N / (double)sh.n_global;
+  int use_sf = std::fabs(sf - 1.0) > DBL_EPSILON ? 1 : 0;
+  if (kind == M_LINEAR || kind == M_ROBUST_LINEAR) {
+    k_shard_slr_solve<<<1, 32, 0, L.stream>>>(d_sums, px, py, d_top, d_aux);
+  } else {
+    k_shard_top_from_ends<T><<<1, 32, 0, L.stream>>>(kind, first_key, last_key, last_F, sh.n_global, sf, use_sf, d_top, d_aux);
+  }
+  count_launch();
+}
+
+template <class T>
+void shard_bounds(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N, u64* d_S) {
+  unsigned blocks = (unsigned)((N + 1 + SH_THREADS - 1) / SH_THREADS);
+  if (kind == M_RADIX) k_shard_bounds_search<T, M_RADIX><<<blocks, SH_THREADS, 0, L.stream>>>(keys, sh, d_top, N, d_S);
+  else k_shard_bounds_search<T, M_LINEAR><<<blocks, SH_THREADS, 0, L.stream>>>(keys, sh, d_top, N, d_S);
+  count_launch();
+}
+
+template <class T>
+void shard_split(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N,
+                 const u64* d_S, BuildAux* d_aux) {
+  if (kind == M_RADIX) k_split_from_S<T, M_RADIX><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux);
+  else k_split_from_S<T, M_LINEAR><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux);
+  count_launch();
+}
+
+void shard_copy_status(const Launch& L, const BuildAux* d_aux, unsigned* d_out) {
+  k_copy_status<<<1, 32, 0, L.stream>>>(d_aux, d_out);
+  count_launch();
+}
+
+#define INST(T)                                                                                                     \
+  template unsigned shard_top_local<T>(const Launch&, const T*, const Shard<T>&, int, u64, double, double, void*, double*); \
+  template void shard_top_finish<T>(const Launch&, const Shard<T>&, int, u64, double, double, const double*, T, T, u64,   \
+                                    TopModel*, BuildAux*);                                                          \
+  template void shard_bounds<T>(const Launch&, const T*, const Shard<T>&, int, const TopModel*, u64, u64*);          \
+  template void shard_split<T>(const Launch&, const T*, const Shard<T>&, int, const TopModel*, u64, const u64*, BuildAux*);
+INST(u64)
+INST(u32)
+INST(double)
+#undef INST
+
+}  // namespace rmi

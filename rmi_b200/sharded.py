@@ -1,0 +1,312 @@
+"""Range-partitioned (multi-GPU) two-layer RMI build: one process per GPU, torch.distributed
+for the three small collectives, the C ABI's rmi_shard_* phases for all arithmetic.
+
+The result is the same TrainedRMI on every rank and equals a single-GPU build of the
+concatenated key array (reference semantics: rmi_lib::train on the whole data set).
+
+    data = ShardedTrainingData(local_sorted_keys_tensor, n_local)     # rank r holds the r-th slab
+    rmi  = train_sharded(data, "linear,linear", 1 << 20)
+
+Data path per build:
+    all-reduce SUM   8 doubles          top-model sums (linear / robust_linear)
+    all-reduce MIN   (N+1) x u64        leaf boundaries S
+    send/recv        halo keys          the tail of a rank's last leaf that lives on the next rank(s)
+    all-reduce SUM   N x (ppm+2) x 8 B  leaf parameters, error bounds, key counts (zero where not owned)
+The orchestration below is engine-agnostic: `CudaShardEngine` drives librmi_b200.so; the
+CPU tests (gloo, world_size 2) plug in a numpy engine to exercise exactly this host logic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import api
+
+PHASE_TOP_LOCAL, PHASE_TOP_FINISH, PHASE_BOUNDS, PHASE_SPLIT, PHASE_LEAF, PHASE_STATS = range(6)
+SHARDED_TOPS = ("linear", "robust_linear", "linear_spline", "radix")
+_PPM = {"linear": 2, "robust_linear": 2, "linear_spline": 2, "loglinear": 2, "cubic": 4, "normal": 3, "lognormal": 3}
+_TORCH_OF_KEY = {api.KEY_U64: torch.int64, api.KEY_U32: torch.int32, api.KEY_F64: torch.float64}
+
+
+class _Ends(C.Structure):
+    _fields_ = [("first_key_bits", C.c_uint64), ("last_key_bits", C.c_uint64), ("last_run_start", C.c_uint64),
+                ("n_local", C.c_uint64)]
+
+
+class _Info(C.Structure):
+    _fields_ = [("base", C.c_uint64), ("n_global", C.c_uint64), ("has_prev", C.c_int32), ("is_last", C.c_int32),
+                ("prev_key_bits", C.c_uint64), ("prev_F", C.c_uint64), ("first_key_bits", C.c_uint64),
+                ("last_key_bits", C.c_uint64), ("last_F", C.c_uint64), ("halo_capacity", C.c_uint64),
+                ("pivot_x", C.c_double), ("pivot_y", C.c_double)]
+
+
+class _Buffers(C.Structure):
+    _fields_ = [("sums", C.c_void_p), ("S", C.c_void_p), ("params", C.c_void_p), ("errors", C.c_void_p),
+                ("counts", C.c_void_p), ("status", C.c_void_p)]
+
+
+def key_bits_to_float(bits: int, key_type: int) -> float:
+    """key.as_float() of a raw key (only used to place the common pivot of the sums)."""
+    if key_type == api.KEY_F64:
+        return struct.unpack("<d", struct.pack("<Q", bits))[0]
+    return float(bits)
+
+
+def plan_global_layout(ends_all: np.ndarray, key_type: int, num_leaves: int) -> list[dict]:
+    """From every rank's (first_key_bits, last_key_bits, last_run_start, n_local) derive, for every
+    rank, its shard description.  Pure function of the gathered table: every rank computes the same.
+
+    prev_key / prev_F: last key before the slab and the first global index of its run of equal keys
+    (the offset FixDupsIter would report, reference models/mod.rs:154-185), which may lie several
+    ranks back when whole slabs consist of one repeated key."""
+    world = ends_all.shape[0]
+    n_local = [int(x) for x in ends_all[:, 3]]
+    bases = [0]
+    for g in range(world):
+        bases.append(bases[-1] + n_local[g])
+    n_global = bases[-1]
+    nonempty = [g for g in range(world) if n_local[g] > 0]
+    last_F = {}
+    prev = None
+    for g in nonempty:
+        first_b, last_b, lrs = int(ends_all[g, 0]), int(ends_all[g, 1]), int(ends_all[g, 2])
+        if lrs == 0 and prev is not None and int(ends_all[prev, 1]) == first_b:
+            last_F[g] = last_F[prev]           # the whole slab is one run that began on an earlier rank
+        else:
+            last_F[g] = bases[g] + lrs
+        prev = g
+    first_bits = int(ends_all[nonempty[0], 0]) if nonempty else 0
+    last_bits = int(ends_all[nonempty[-1], 1]) if nonempty else 0
+    gl_last_F = last_F[nonempty[-1]] if nonempty else 0
+    px = 0.5 * key_bits_to_float(first_bits, key_type) + 0.5 * key_bits_to_float(last_bits, key_type)
+    py = 0.5 * float(num_leaves)
+    out = []
+    for g in range(world):
+        before = [r for r in nonempty if r < g]
+        p = before[-1] if before else None
+        out.append(dict(base=bases[g], n_global=n_global, has_prev=int(p is not None),
+                        is_last=int(bool(nonempty) and g == nonempty[-1]),
+                        prev_key_bits=int(ends_all[p, 1]) if p is not None else 0,
+                        prev_F=last_F[p] if p is not None else 0,
+                        first_key_bits=first_bits, last_key_bits=last_bits, last_F=gl_last_F,
+                        pivot_x=px, pivot_y=py, bases=bases))
+    return out
+
+
+def plan_halo(bases: list[int], v: list[int], n_global: int) -> list[tuple[int, int, int, int]]:
+    """v[g] = first leaf boundary S[j] >= bases[g+1] (the end of rank g's last owned leaf).
+    Rank g needs global keys [bases[g+1], min(v[g] + 1, n_global)); returns the transfers
+    (dst_rank, src_rank, src_local_offset, count) that deliver them."""
+    world = len(bases) - 1
+    moves = []
+    for g in range(world - 1):
+        lo, hi = bases[g + 1], min(v[g] + 1, n_global)
+        for r in range(g + 1, world):
+            a, b = max(lo, bases[r]), min(hi, bases[r + 1])
+            if b > a:
+                moves.append((g, r, a - bases[r], b - a))
+    return moves
+
+
+class ShardedTrainingData:
+    """This rank's slab of a globally sorted key array, in device memory with room behind it
+    for halo keys.  `keys` must be a 1-D torch tensor on the rank's device (int64 storage for
+    uint64 keys, int32 for uint32, float64)."""
+
+    def __init__(self, keys: torch.Tensor, n_local: int | None = None, key_type: int = api.KEY_U64,
+                 halo_capacity: int = 1 << 20, group=None):
+        self.group = group
+        self.key_type = key_type
+        n_local = keys.numel() if n_local is None else n_local
+        cap = n_local + halo_capacity
+        if keys.numel() >= cap:
+            self.buf = keys
+        else:
+            self.buf = torch.empty(cap, dtype=keys.dtype, device=keys.device)
+            self.buf[:n_local].copy_(keys[:n_local])
+        self.n_local = n_local
+        self.halo_capacity = self.buf.numel() - n_local
+        self.engine = CudaShardEngine(self)
+
+
+class CudaShardEngine:
+    """Phases of a range-partitioned build on librmi_b200.so (include/rmi_b200.h rmi_shard_*)."""
+
+    def __init__(self, data: ShardedTrainingData):
+        self.data = data
+        self.lib = api.load_library()
+        L = self.lib
+        L.rmi_shard_ends_get.argtypes = [C.c_void_p, C.POINTER(_Ends)]
+        L.rmi_shard_build_create.argtypes = [C.c_void_p, C.POINTER(_Info), C.c_char_p, C.c_uint64, C.POINTER(_Buffers),
+                                             C.c_void_p, C.POINTER(C.c_void_p)]
+        L.rmi_shard_phase.argtypes = [C.c_void_p, C.c_int]
+        L.rmi_shard_set_halo.argtypes = [C.c_void_p, C.c_uint64]
+        L.rmi_shard_finish.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(api._Result))]
+        L.rmi_shard_build_destroy.argtypes = [C.c_void_p]
+        self.device = data.buf.device
+        self.ds = api.RMITrainingData.from_device(data.buf.data_ptr(), data.n_local, data.key_type,
+                                                  self.device.index or 0, keep_alive=data.buf)
+        self._build = None
+
+    def ends(self):
+        e = _Ends()
+        api._check(self.lib.rmi_shard_ends_get(self.ds._h, C.byref(e)))
+        return int(e.first_key_bits), int(e.last_key_bits), int(e.last_run_start), int(e.n_local)
+
+    def begin(self, info: dict, spec: str, num_leaves: int, bufs: dict):
+        key = (spec, num_leaves, tuple(bufs[k].data_ptr() for k in sorted(bufs)))
+        if self._build is not None and getattr(self, "_build_key", None) == key:
+            return      # same spec / buffers: the build object (scratch, events) is reused
+        self.end()
+        self._build_key = key
+        ci = _Info(base=info["base"], n_global=info["n_global"], has_prev=info["has_prev"], is_last=info["is_last"],
+                   prev_key_bits=info["prev_key_bits"], prev_F=info["prev_F"], first_key_bits=info["first_key_bits"],
+                   last_key_bits=info["last_key_bits"], last_F=info["last_F"], halo_capacity=self.data.halo_capacity,
+                   pivot_x=info["pivot_x"], pivot_y=info["pivot_y"])
+        cb = _Buffers(*(bufs[k].data_ptr() for k in ("sums", "S", "params", "errors", "counts", "status")))
+        h = C.c_void_p()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        api._check(self.lib.rmi_shard_build_create(self.ds._h, C.byref(ci), spec.encode(), num_leaves, C.byref(cb),
+                                                   C.c_void_p(stream), C.byref(h)))
+        self._build = h
+        self._spec = spec
+
+    def phase(self, k: int):
+        api._check(self.lib.rmi_shard_phase(self._build, k))
+
+    def set_halo(self, count: int):
+        api._check(self.lib.rmi_shard_set_halo(self._build, count))
+
+    def halo_view(self, offset: int, count: int) -> torch.Tensor:
+        n = self.data.n_local
+        return self.data.buf[n + offset: n + offset + count]
+
+    def local_view(self, offset: int, count: int) -> torch.Tensor:
+        return self.data.buf[offset: offset + count]
+
+    def finish(self, flags: int = 0):
+        res = C.POINTER(api._Result)()
+        api._check(self.lib.rmi_shard_finish(self._build, flags, C.byref(res)))
+        return api.result_from_pointer(res, self._spec)
+
+    def end(self):
+        if self._build is not None:
+            self.lib.rmi_shard_build_destroy(self._build)
+            self._build = None
+
+    def __del__(self):
+        try:
+            self.end()
+        except Exception:
+            pass
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=None, engine=None):
+    """rmi_lib::train on a range-partitioned key array; returns the full TrainedRMI on every rank."""
+    eng = engine if engine is not None else data.engine
+    group = group if group is not None else getattr(data, "group", None)
+    rank, world = _world(group)
+    dev = eng.device
+    parts = model_spec.split(",")
+    if len(parts) != 2:
+        raise api.RMIPanic("only two-layer RMIs can be trained (the reference panics on other depths)")
+    if parts[0] not in SHARDED_TOPS:
+        raise api.RMIError(f"range-partitioned builds offer the top models {SHARDED_TOPS}")
+    ppm = _PPM.get(parts[1])
+    if ppm is None:
+        raise api.RMIPanic(f"unsupported or unknown leaf model {parts[1]}")
+    N = int(num_leaves)
+
+    # 1. what every rank's slab looks like at its ends (cached on the data object: the data is immutable)
+    layout = getattr(data, "_layout", None)
+    if layout is None or layout[0] != N:
+        e = torch.tensor(np.array(eng.ends(), dtype=np.uint64).view(np.int64), dtype=torch.int64, device=dev)
+        gathered = [torch.empty_like(e) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(gathered, e, group=group)
+        else:
+            gathered = [e]
+        ends_all = torch.stack(gathered).cpu().numpy().view(np.uint64)
+        layout = (N, plan_global_layout(ends_all, data.key_type, N))
+        data._layout = layout
+    info = layout[1][rank]
+    bases, n_global = info["bases"], info["n_global"]
+
+    bufs = getattr(data, "_bufs", None)
+    if bufs is None or bufs["S"].numel() != N + 1 or bufs["params"].numel() != N * ppm:
+        bufs = dict(sums=torch.zeros(8, dtype=torch.float64, device=dev),
+                    S=torch.empty(N + 1, dtype=torch.int64, device=dev),
+                    params=torch.empty(N * ppm, dtype=torch.float64, device=dev),
+                    errors=torch.empty(N, dtype=torch.int64, device=dev),
+                    counts=torch.empty(N, dtype=torch.int64, device=dev),
+                    status=torch.zeros(1, dtype=torch.int32, device=dev))
+        data._bufs = bufs
+    eng.begin(info, model_spec, N, bufs)
+
+    # 2. top model: local sums -> all-reduce -> closed form (identical on every rank)
+    eng.phase(PHASE_TOP_LOCAL)
+    if world > 1:
+        dist.all_reduce(bufs["sums"], op=dist.ReduceOp.SUM, group=group)
+    eng.phase(PHASE_TOP_FINISH)
+    # 3. leaf boundaries: local lower bounds -> all-reduce MIN
+    eng.phase(PHASE_BOUNDS)
+    if world > 1:
+        dist.all_reduce(bufs["S"], op=dist.ReduceOp.MIN, group=group)
+    eng.phase(PHASE_SPLIT)
+    # 4. halo: the keys of a rank's last leaf that live on the following rank(s)
+    halo = 0
+    if world > 1:
+        S = bufs["S"]
+        cuts = torch.tensor(bases[1:], dtype=torch.int64, device=dev)
+        pos = torch.searchsorted(S, cuts).clamp_(max=N)
+        v = S[pos].cpu().tolist()
+        moves = plan_halo(bases, v, n_global)
+        need = {}
+        for (dst, src, off, cnt) in moves:
+            need[dst] = need.get(dst, 0) + cnt
+        too_big = max(need.values(), default=0) > _min_halo_capacity(data, group, world, dev)
+        if too_big:
+            raise api.RMIError("a leaf reaches further into the next rank than the halo capacity "
+                               f"({max(need.values())} keys needed)")
+        ops, recv_off = [], 0
+        for (dst, src, off, cnt) in moves:
+            if dst == rank:
+                ops.append(dist.P2POp(dist.irecv, eng.halo_view(recv_off, cnt), src, group=group))
+                recv_off += cnt
+            elif src == rank:
+                ops.append(dist.P2POp(dist.isend, eng.local_view(off, cnt), dst, group=group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        halo = need.get(rank, 0)
+    eng.set_halo(halo)
+    # 5. leaves owned by this rank, then everyone gets everything
+    eng.phase(PHASE_LEAF)
+    if world > 1:
+        dist.all_reduce(bufs["params"].view(torch.int64), op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(bufs["errors"], op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(bufs["counts"], op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(bufs["status"], op=dist.ReduceOp.MAX, group=group)
+    eng.phase(PHASE_STATS)
+    return eng.finish(flags)
+
+
+def _min_halo_capacity(data, group, world, dev):
+    cap = getattr(data, "_min_cap", None)
+    if cap is None:
+        t = torch.tensor([data.halo_capacity], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        cap = int(t.item())
+        data._min_cap = cap
+    return cap

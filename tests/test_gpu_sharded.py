@@ -1,0 +1,115 @@
+"""The CUDA range-partitioned build (rmi_shard_* phases through rmi_b200/sharded.py) against the
+oracle's single-process build.  With >= 2 GPUs the ranks use NCCL, one GPU each; on a one-GPU
+box two processes share cuda:0 and the collectives go through gloo (same code path on the
+library side: slabs, halos, ownership, global offsets)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from tests import datasets, parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _keys(kind, n):
+    if kind == "uniform":
+        return datasets.uniform_u64(n, seed=31)
+    if kind == "dups":
+        k = datasets.with_duplicates(datasets.uniform_u64(n, seed=32), frac=0.1)
+        k[n // 2 - 300: n // 2 + 300] = k[n // 2 - 300]
+        k.sort()
+        return k
+    return datasets.lognormal_u64(n, seed=33)
+
+
+def _worker(rank, world, port, kind, n, spec, N, backend, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = torch.device("cuda", rank if backend == "nccl" else 0)
+    torch.cuda.set_device(dev)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    try:
+        import oracle
+        import rmi_b200
+        from rmi_b200 import sharded
+        keys = _keys(kind, n)
+        cuts = [0] + [int(n * (0.31 + 0.38 * r) / 1.0) if world == 2 else n * (r + 1) // world for r in range(world - 1)] + [n]
+        cuts = sorted(set(cuts))
+        while len(cuts) < world + 1:
+            cuts.insert(-1, cuts[-2] + 1)
+        local = torch.from_numpy(keys[cuts[rank]:cuts[rank + 1]].view(np.int64).copy()).to(dev)
+        data = sharded.ShardedTrainingData(local, key_type=rmi_b200.KEY_U64, halo_capacity=1 << 16)
+        g = sharded.train_sharded(data, spec, N)
+        top = spec.split(",")[0]
+        if top in ("linear", "robust_linear"):
+            o_ref = oracle.train(keys, spec, N)
+            parity.assert_top_equal(g, o_ref, exact=False, N=N)
+            o = oracle.train(keys, spec, N, l0_override=g.l0_fparams)
+        else:
+            o = oracle.train(keys, spec, N)
+            if g.l0_model == "linear_spline" or o.l0.kind == "linear_spline":
+                g.l0_model = o.l0.kind
+        parity.assert_same_rmi(g, o)
+        # a second build on the same data object (cached layout / buffers) must agree too
+        g2 = sharded.train_sharded(data, spec, N)
+        assert np.array_equal(parity.bits(g2.l1_params), parity.bits(g.l1_params))
+        assert np.array_equal(g2.last_layer_max_l1s, g.last_layer_max_l1s)
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL: " + "".join(traceback.format_exception(e))[-2000:]))
+    finally:
+        dist.destroy_process_group()
+
+
+CASES = [("uniform", "linear,linear", 1024), ("uniform", "radix,linear", 4096), ("dups", "linear_spline,linear", 512),
+         ("lognormal", "radix,linear_spline", 1000), ("dups", "robust_linear,cubic", 256), ("uniform", "linear,cubic", 333)]
+
+
+@pytest.mark.parametrize("kind,spec,N", CASES, ids=[f"{c[0]}-{c[1]}-{c[2]}" for c in CASES])
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_cuda_build_equals_oracle(oracle, world, kind, spec, N):
+    import torch.multiprocessing as mp
+    n = 150_000
+    try:
+        oracle.train(_keys(kind, n), spec, N)
+    except oracle.OraclePanic as e:
+        pytest.skip(f"reference panics on this configuration: {e}")
+    backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, n, spec, N, backend, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    bad = [r for r in results if r[1] != "ok"]
+    assert not bad, bad
+
+
+def test_sharded_single_rank_equals_plain_train(oracle):
+    """world_size 1 (no process group): the phase API with base 0 must equal rmi_train."""
+    import rmi_b200
+    from rmi_b200 import sharded
+    keys = datasets.uniform_u64(300_000, seed=34)
+    dev = torch.device("cuda", 0)
+    local = torch.from_numpy(keys.view(np.int64).copy()).to(dev)
+    data = sharded.ShardedTrainingData(local, key_type=rmi_b200.KEY_U64, halo_capacity=16)
+    for spec, N in [("radix,linear", 2048), ("linear_spline,cubic", 512)]:
+        g = sharded.train_sharded(data, spec, N)
+        o = oracle.train(keys, spec, N)
+        parity.assert_same_rmi(g, o)
