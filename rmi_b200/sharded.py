@@ -132,6 +132,19 @@ class ShardedTrainingData:
         self.halo_capacity = self.buf.numel() - n_local
         self.engine = CudaShardEngine(self)
 
+    def grow_halo(self, capacity: int):
+        """Re-home the slab in a buffer with room for `capacity` halo keys (a leaf reached further
+        into the following ranks than expected — heavy skew)."""
+        old = self.buf
+        self.buf = torch.empty(self.n_local + capacity, dtype=old.dtype, device=old.device)
+        self.buf[: self.n_local].copy_(old[: self.n_local])
+        self.halo_capacity = capacity
+        self.engine.end()
+        self.engine = CudaShardEngine(self)
+        for attr in ("_min_cap",):
+            if hasattr(self, attr):
+                delattr(self, attr)
+
 
 class CudaShardEngine:
     """Phases of a range-partitioned build on librmi_b200.so (include/rmi_b200.h rmi_shard_*)."""
@@ -274,20 +287,33 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
         need = {}
         for (dst, src, off, cnt) in moves:
             need[dst] = need.get(dst, 0) + cnt
-        too_big = max(need.values(), default=0) > _min_halo_capacity(data, group, world, dev)
-        if too_big:
+        most = max(need.values(), default=0)
+        if most > _min_halo_capacity(data, group, world, dev):
+            # every rank computes the same `most`, so they all take this branch together
+            if engine is None and hasattr(data, "grow_halo"):
+                data.grow_halo(int(most * 1.25) + 1024)
+                return train_sharded(data, model_spec, num_leaves, flags, group)
             raise api.RMIError("a leaf reaches further into the next rank than the halo capacity "
-                               f"({max(need.values())} keys needed)")
-        ops, recv_off = [], 0
+                               f"({most} keys needed)")
+        # gloo cannot send/recv device memory (one-GPU test boxes): stage through the host there
+        stage = dev.type == "cuda" and dist.get_backend(group) == "gloo"
+        ops, recv_off, landed = [], 0, []
         for (dst, src, off, cnt) in moves:
             if dst == rank:
-                ops.append(dist.P2POp(dist.irecv, eng.halo_view(recv_off, cnt), src, group=group))
+                view = eng.halo_view(recv_off, cnt)
+                t = torch.empty(cnt, dtype=view.dtype) if stage else view
+                if stage:
+                    landed.append((view, t))
+                ops.append(dist.P2POp(dist.irecv, t, src, group=group))
                 recv_off += cnt
             elif src == rank:
-                ops.append(dist.P2POp(dist.isend, eng.local_view(off, cnt), dst, group=group))
+                view = eng.local_view(off, cnt)
+                ops.append(dist.P2POp(dist.isend, view.cpu() if stage else view, dst, group=group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+        for view, t in landed:
+            view.copy_(t)
         halo = need.get(rank, 0)
     eng.set_halo(halo)
     # 5. leaves owned by this rank, then everyone gets everything
