@@ -166,9 +166,14 @@ template <int N_> __device__ __forceinline__ void cp_async_wait() {
 // Calls fn(key, index) for index = b .. e-1 of THIS lane's range (I = u32 or u64 index type),
 // all 32 lanes of the warp taking part in the copies.  Must be called by every lane of the
 // warp (empty ranges allowed).  `keys` must be 16-byte aligned.
-template <class T, class I, class Fn>
+// With SOLO = true the pass stops as soon as exactly one lane still has at least SOLO_MIN keys
+// to go and every other lane is done; it then reports that lane and the index it stopped at
+// (*solo_lane = -1 if the pass ran to completion), so that the caller can finish the long
+// leaf with solo_pass(), where the whole warp serves the one remaining chain.
+constexpr int SOLO_MIN = 384;
+template <class T, class I, class Fn, bool SOLO = false>
 __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_keys, unsigned char* wsm, I b, I e,
-                                            Fn&& fn) {
+                                            Fn&& fn, int* solo_lane = nullptr, I* solo_resume = nullptr) {
   constexpr int KPP = 16 / (int)sizeof(T);   // keys per 16-byte piece
   constexpr int SW = 8 * KPP;                // keys per row per chunk
   const unsigned FULL = 0xffffffffu;
@@ -184,6 +189,7 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
     I t = __shfl_xor_sync(FULL, maxlen, o);
     if (t > maxlen) maxlen = t;
   }
+  if (SOLO) *solo_lane = -1;
   if (maxlen == 0) return;
   // Piece bookkeeping in 16-byte units (32-bit: covers 64 GB of keys).  Rows longer than
   // 2^32 pieces cannot occur below that size either.
@@ -225,6 +231,23 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
 #pragma unroll
   for (u32 c = 0; c + 1 < (u32)SSTAGES; ++c) { if (c < nchunks) issue(c); else cp_async_commit(); }
   for (u32 c = 0; c < nchunks; ++c) {
+    if (SOLO) {
+      const I done_keys = (I)c * (I)SW;
+      const bool active = rlen > done_keys;
+      const unsigned am = __ballot_sync(FULL, active);
+      if (__popc(am) == 1) {
+        const int sl = __ffs(am) - 1;
+        const I left = __shfl_sync(FULL, rlen > done_keys ? (I)(rlen - done_keys) : (I)0, sl);
+        if (left >= (I)SOLO_MIN) {
+          cp_async_wait<0>();
+          __syncwarp();
+          *solo_lane = sl;
+          const I at = a + done_keys;           // next index of this lane's stream
+          *solo_resume = at > b ? at : b;
+          return;
+        }
+      }
+    }
     if (c + (SSTAGES - 1) < nchunks) issue(c + (SSTAGES - 1)); else cp_async_commit();
     cp_async_wait<SSTAGES - 1>();
     __syncwarp();
@@ -307,6 +330,29 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
   }
 }
 
+// One long chain served by the whole warp: 32 keys per coalesced load (the next 32 already in
+// flight), every lane replays the same steps from shuffles, so all lanes hold the same state and
+// the chain runs at FP64 dependency latency instead of at the pace of the row-copy machinery.
+template <class T, class I, class Fn>
+__device__ __forceinline__ void solo_pass(const T* __restrict__ keys, I b, I e, Fn&& fn) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (b >= e) return;
+  T cur = (b + (I)lane) < e ? keys[b + (I)lane] : T();
+  for (I base = b; base < e; base += 32) {
+    const I nb = base + 32;
+    T nxt = (nb + (I)lane) < e ? keys[nb + (I)lane] : T();     // prefetch the next 32 keys
+    const int cnt = (e - base) < (I)32 ? (int)(e - base) : 32;
+    if (cnt == 32) {
+#pragma unroll 8
+      for (int q = 0; q < 32; ++q) fn(__shfl_sync(FULL, cur, q), (I)(base + (I)q));
+    } else {
+      for (int q = 0; q < cnt; ++q) fn(__shfl_sync(FULL, cur, q), (I)(base + (I)q));
+    }
+    cur = nxt;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-leaf training vector (two_layer.rs:52-82): a contiguous index range [vs, ve) of the key
 // array — [last key of the previous leaf] + own keys + [first key of the next leaf], neither
@@ -351,6 +397,16 @@ template <bool CHECKED> struct LeafWelford {
     } else {
       rc = rcp_beyond_table(nf);   // leaves longer than the table: a real call, so it is not if-converted
     }
+    double dx = __dadd_rn(x, -mean_x);
+    mean_x = __dadd_rn(mean_x, dv(dx, rc));
+    mean_y = __dadd_rn(mean_y, dv(__dadd_rn(y, -mean_y), rc));
+    c = __dadd_rn(c, __dmul_rn(dx, __dadd_rn(y, -mean_y)));
+    double dx2 = __dadd_rn(x, -mean_x);
+    m2 = __dadd_rn(m2, __dmul_rn(dx, dx2));
+  }
+  // the same step with the count's reciprocal supplied by the caller (solo mode)
+  __device__ __forceinline__ void push_rc(double x, double y, double rc) {
+    nf = __dadd_rn(nf, 1.0);
     double dx = __dadd_rn(x, -mean_x);
     mean_x = __dadd_rn(mean_x, dv(dx, rc));
     mean_y = __dadd_rn(mean_y, dv(__dadd_rn(y, -mean_y), rc));
@@ -413,17 +469,63 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     w.init(rcp);
     ItemTracker<T> it;
     it.init(kfirst, vsd, f0d);
-    vector_pass([&](T k, I) {
+    auto item = [&](T k, I) {
       double yy = it.next(k);
       if (LEAF == M_LOGLINEAR) { yy = log(yy); if (!isfinite(yy)) return; }
       w.push(Key<T>::as_float(k), yy);
-    });
-    if (L > 0) {
-      double yy = it.pyd;
-      if (LEAF == M_LOGLINEAR) yy = log(yy);
-      if (LEAF == M_LINEAR || isfinite(yy)) w.push(Key<T>::as_float(it.pk), yy);
+    };
+    auto finalize = [&]() {
+      if (L > 0) {   // the drained iterator's repeat of the final item
+        double yy = it.pyd;
+        if (LEAF == M_LOGLINEAR) yy = log(yy);
+        if (LEAF == M_LINEAR || isfinite(yy)) w.push(Key<T>::as_float(it.pk), yy);
+      }
+      if (!w.finish(f[0], f[1])) bad |= ST_NEG_VARIANCE;
+    };
+    if (r.p_remote) item(r.pkey, (I)0);
+    int solo_lane;
+    I solo_at;
+    if (LEAF == M_LINEAR) stream_pass<T, I, decltype(item)&, true>(keys, n_keys, wsm, r.vs, r.ve, item, &solo_lane, &solo_at);
+    else { stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item); solo_lane = -1; solo_at = 0; }
+    if (solo_lane < 0) {
+      finalize();
+    } else {
+      // every other lane's leaf is complete; the whole warp now runs the one long chain
+      const unsigned FULL = 0xffffffffu;
+      const int lane = threadIdx.x & 31;
+      if (lane != solo_lane) finalize();
+      w.mean_x = __shfl_sync(FULL, w.mean_x, solo_lane); w.mean_y = __shfl_sync(FULL, w.mean_y, solo_lane);
+      w.c = __shfl_sync(FULL, w.c, solo_lane); w.m2 = __shfl_sync(FULL, w.m2, solo_lane);
+      w.nf = __shfl_sync(FULL, w.nf, solo_lane); w.ra = __shfl_sync(FULL, w.ra, solo_lane);
+      it.pk = __shfl_sync(FULL, it.pk, solo_lane); it.pyd = __shfl_sync(FULL, it.pyd, solo_lane);
+      it.idxd = __shfl_sync(FULL, it.idxd, solo_lane);
+      const I s_b = __shfl_sync(FULL, solo_at, solo_lane), s_e = __shfl_sync(FULL, r.ve, solo_lane);
+      // 32 keys per coalesced load (next 32 in flight); each lane prepares ITS key's x, duplicate
+      // flag and the reciprocal of ITS step's count, then all lanes replay the 32 steps from
+      // shuffles: the chain runs at FP64 dependency latency
+      T cur = (s_b + (I)lane) < s_e ? keys[s_b + (I)lane] : T();
+      for (I base = s_b; base < s_e; base += 32) {
+        const I nb = base + 32;
+        const T nxt = (nb + (I)lane) < s_e ? keys[nb + (I)lane] : T();
+        const int cnt = (s_e - base) < (I)32 ? (int)(s_e - base) : 32;
+        T kp = __shfl_up_sync(FULL, cur, 1);
+        if (lane == 0) kp = it.pk;
+        const unsigned dmask = __ballot_sync(FULL, cur == kp);
+        const double xl = Key<T>::as_float(cur);
+        const double rcl = __drcp_rn(__dadd_rn(w.nf, (double)(lane + 1)));
+        for (int q = 0; q < cnt; ++q) {
+          const double xq = __shfl_sync(FULL, xl, q), rq = __shfl_sync(FULL, rcl, q);
+          const double yd = ((dmask >> q) & 1u) ? it.pyd : it.idxd;
+          it.pyd = yd;
+          it.idxd = __dadd_rn(it.idxd, 1.0);
+          w.push_rc(xq, yd, rq);
+        }
+        it.pk = __shfl_sync(FULL, cur, cnt - 1);
+        cur = nxt;
+      }
+      w.ra = w.ra_end;   // the table cursor was not advanced in solo mode: later steps compute 1/n directly
+      if (lane == solo_lane) finalize();
     }
-    if (!w.finish(f[0], f[1])) bad |= ST_NEG_VARIANCE;
   } else if (LEAF == M_ROBUST_LINEAR) {
     // linear.rs:239-260 — skip(bnd).take(len - 2*bnd): never drains the iterator
     u64 bnd = f64_to_u64_sat(__dmul_rn(__ull2double_rn((u64)L), 0.0001));
@@ -604,7 +706,11 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   unsigned char* wsm = smem_raw + (size_t)RCP_TABLE * sizeof(double) + (size_t)(threadIdx.x >> 5) * WARP_STREAM_BYTES;
   for (int c = threadIdx.x; c < RCP_TABLE; c += blockDim.x) s_rcp[c] = c ? __drcp_rn((double)c) : 0.0;
   __syncthreads();
-  const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  // Leaf groups are handed out from both ends of the leaf range: with a regression top model
+  // the first and the last leaf collect every key the model places below 0 / above N-1 and are
+  // by far the longest serial chains, so they must start first, not last.
+  const u64 group = (blockIdx.x & 1u) ? (u64)gridDim.x - 1 - (blockIdx.x >> 1) : (u64)(blockIdx.x >> 1);
+  const u64 j = group * blockDim.x + threadIdx.x;
   constexpr int PPM = leaf_params_per_model(LEAF);
   constexpr bool NANCHECK = Key<T>::is_float || LEAF == M_LOGLINEAR || LEAF == M_NORMAL || LEAF == M_LOGNORMAL;
   const u64 n = sh.n_global;
@@ -685,10 +791,17 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
     else if (sh.has_prev) { prev_key = sh.prev_key; have_prev = true; }
   }
   I max_err = 0, run_max = 0;
+  // Leaves longer than LONG_LEAF keys skip the lane-serial walk: their forward pass has no
+  // order dependence, so the whole warp does it afterwards, 32 keys per step, coalesced.
+  constexpr u64 LONG_LEAF = 1024;
+  const bool is_long = live && (g_hi - g_lo) > LONG_LEAF;
+  // worth it only when a few lanes are long (when all 32 are, lane-serial walks are already balanced)
+  const unsigned long_mask = __ballot_sync(0xffffffffu, is_long);   // (all lanes vote: no short-circuit)
+  const bool long_leaf = is_long && __popc(long_mask) <= 4;
   {
     T pk = (live && g_lo == 0 && g_hi > 0) ? keys[0] : prev_key;
     I F = (I)g_lo, run = 0;
-    stream_pass<T, I>(keys, sh.n_avail, wsm, r.lo, r.hi, [&](T k, I i) {
+    stream_pass<T, I>(keys, sh.n_avail, wsm, r.lo, long_leaf ? r.lo : r.hi, [&](T k, I i) {
       if (k != pk) { run_max = run > run_max ? run : run_max; run = 0; F = (I)(i + baseI); }
       run += 1;
       pk = k;
@@ -697,6 +810,66 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
       max_err = e > max_err ? e : max_err;
     });
     if (g_hi < n && run > run_max) run_max = run;
+  }
+  {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(FULL, long_leaf);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      // the owner's leaf, parameters and boundary key, broadcast to the warp
+      const u64 c_lo = __shfl_sync(FULL, (u64)r.lo, src), c_hi = __shfl_sync(FULL, (u64)r.hi, src);
+      const u64 c_ghi = __shfl_sync(FULL, g_hi, src);
+      double cf[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cf[q] = __shfl_sync(FULL, f[q], src);
+      T carry_k = __shfl_sync(FULL, prev_key, src);
+      const bool c_have_prev = __shfl_sync(FULL, (int)have_prev, src) != 0;
+      I carry_F = (I)(c_lo + sh.base);
+      I w_err = 0, w_run = 0;
+      for (u64 b0 = c_lo; b0 < c_hi; b0 += 32) {
+        const u64 i = b0 + lane;
+        const bool valid = i < c_hi;
+        const T k = valid ? keys[i] : T();
+        T kp = __shfl_up_sync(FULL, k, 1);
+        if (lane == 0) kp = carry_k;
+        // a run starts where the key differs from its predecessor (the leaf's first key always
+        // differs from the key before the leaf; at global index 0 there is no predecessor)
+        const bool starts = valid && (k != kp || (i == c_lo && !c_have_prev));
+        I F = starts ? (I)(i + sh.base) : (I)0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          I t = __shfl_up_sync(FULL, F, o);
+          if (lane >= o && t > F) F = t;
+        }
+        if (carry_F > F) F = carry_F;
+        if (valid) {
+          I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, Key<T>::as_float(k), nI);
+          I e = pred > F ? pred - F : F - pred;
+          w_err = e > w_err ? e : w_err;
+        }
+        // a run ends at i when the next key differs or the leaf ends; its length counts unless
+        // it is the data set's final run (lower_bound_correction.rs:108-119)
+        T kn = __shfl_down_sync(FULL, k, 1);
+        if (lane == 31 && i + 1 < c_hi) kn = keys[i + 1];
+        const bool last_of_leaf = valid && i + 1 == c_hi;
+        const bool ends = valid && (last_of_leaf || kn != k);
+        if (ends && !(last_of_leaf && c_ghi >= n)) {
+          I len = (I)(i + sh.base) - F + 1;
+          w_run = len > w_run ? len : w_run;
+        }
+        const int lastv = (c_hi - b0) < 32 ? (int)(c_hi - b0) - 1 : 31;
+        carry_F = __shfl_sync(FULL, F, lastv);
+        carry_k = __shfl_sync(FULL, k, lastv);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        I t = __shfl_xor_sync(FULL, w_err, o); w_err = t > w_err ? t : w_err;
+        t = __shfl_xor_sync(FULL, w_run, o); w_run = t > w_run ? t : w_run;
+      }
+      if (lane == src) { max_err = w_err; run_max = w_run; }
+    }
   }
   if (bad) set_status(aux, bad);
   if (!live) return;

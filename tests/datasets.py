@@ -49,3 +49,15 @@ def lognormal_f64(n: int, seed: int = 11, sigma: float = 2.0) -> np.ndarray:
     k = np.exp(rng.normal(0.0, sigma, size=n))
     k.sort()
     return k
+
+
+def front_heavy_u64(n: int, seed: int = 13) -> np.ndarray:
+    """Three quarters of the keys packed into [0, 2^20), the rest spread over [2^20, 2^63):
+    under a radix / spline top model the first leaf holds a very long run of keys while all its
+    neighbours are short (exercises the long-leaf paths of the fused leaf kernel)."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    a = rng.integers(0, 1 << 20, size=(3 * n) // 4, dtype=np.uint64)
+    b = rng.integers(1 << 20, 1 << 63, size=n - a.size, dtype=np.uint64)
+    k = np.concatenate([a, b])
+    k.sort()
+    return k

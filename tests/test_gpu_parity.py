@@ -23,6 +23,7 @@ DATA = {
     "uniform_u32": lambda: datasets.uniform_u32(N_KEYS),
     "uniform_f64": lambda: datasets.uniform_f64(N_KEYS),
     "lognormal_f64": lambda: datasets.lognormal_f64(N_KEYS),
+    "front_heavy_u64": lambda: datasets.front_heavy_u64(N_KEYS),
 }
 _cache = {}
 

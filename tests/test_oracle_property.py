@@ -26,6 +26,7 @@ DATA = {
     "dups_u64": lambda: datasets.with_duplicates(datasets.uniform_u64(200_000)),
     "uniform_u32": lambda: datasets.uniform_u32(200_000),
     "uniform_f64": lambda: datasets.uniform_f64(200_000),
+    "front_heavy_u64": lambda: datasets.front_heavy_u64(200_000),
 }
 
 

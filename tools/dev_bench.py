@@ -26,7 +26,7 @@ for spec, bf, flags in configs:
             t1 = time.perf_counter()
         print(json.dumps({"spec": spec, "bf": bf, "flags": flags, "wall_ms": (t1 - t0) * 1e3,
                           "lib_wall_ms": r.build_time / 1e6, "device_ms": r.device_time_ns / 1e6,
-                          "phases_ms": [p / 1e6 for p in r.phase_device_ns], "max_err": r.model_max_error,
+                          "phases_ms": [p / 1e6 for p in r.phase_device_ns], "max_err": r.model_max_error, "max_leaf_keys": int(r.l1_counts.max()) if r.l1_counts is not None else None,
                           "avg_log2": r.model_avg_log2_error, "keys_per_s_device": n / (r.device_time_ns / 1e9)}))
     except rmi_b200.RMIError as e:
         print(json.dumps({"spec": spec, "bf": bf, "error": str(e)}))
