@@ -9,10 +9,11 @@ import numpy as np
 #  * coefficients that depend on libm (pow, ln) or on the order of a 200M-term sum
 #    (parallel top fits): 1e-9 relative, measured against the prediction range for
 #    intercept-like terms;
-#  * the two floating-point summary statistics (avg_l2, avg_log2): 1e-12 relative (the
-#    reference sums N terms serially, the GPU in a fixed tree).
+#  * the two floating-point summary statistics (avg_l2, avg_log2): 1e-10 relative (the
+#    reference sums N terms serially — its own rounding error grows to ~4e-12 at N = 2^20 —
+#    the GPU sums in a fixed tree).
 COEF_RTOL = 1e-9
-STAT_RTOL = 1e-12
+STAT_RTOL = 1e-10
 
 
 def bits(a):
