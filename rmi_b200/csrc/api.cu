@@ -105,6 +105,7 @@ struct rmi_dataset {
   int key_type = 0;
   int device = 0;
   bool owned = false;
+  bool pooled = false;  // d_keys came from the stream-ordered pool (cudaMallocAsync)
   bool sorted = true;   // verified once, when the dataset is created (the data is immutable)
 };
 
@@ -123,9 +124,9 @@ int verify_sorted(rmi_dataset* ds) {
   cudaMemset(d_flag, 0, sizeof(unsigned));
   Launch L{nullptr, di.num_sms};
   switch (ds->key_type) {
-    case RMI_KEY_U64: check_sorted<u64>(L, (const u64*)ds->d_keys, ds->n, d_flag); break;
-    case RMI_KEY_U32: check_sorted<u32>(L, (const u32*)ds->d_keys, ds->n, d_flag); break;
-    default: check_sorted<double>(L, (const double*)ds->d_keys, ds->n, d_flag); break;
+    case RMI_KEY_U64: check_sorted<u64>(L, (const u64*)ds->d_keys, ds->n, 0, ds->n, d_flag); break;
+    case RMI_KEY_U32: check_sorted<u32>(L, (const u32*)ds->d_keys, ds->n, 0, ds->n, d_flag); break;
+    default: check_sorted<double>(L, (const double*)ds->d_keys, ds->n, 0, ds->n, d_flag); break;
   }
   unsigned h = 0;
   cudaError_t e = cudaMemcpy(&h, d_flag, sizeof(unsigned), cudaMemcpyDeviceToHost);
@@ -213,16 +214,48 @@ int rmi_dataset_create(const void* host_keys, uint64_t n, rmi_key_type key_type,
   if (!out || (!host_keys && n) || (int)key_type < 0 || (int)key_type > 2)
     return fail(RMI_ERR_INVALID, "rmi_dataset_create: bad argument");
   CUDA_TRY(cudaSetDevice(device));
+  DeviceInfo di;
+  if (int rc = device_info(device, &di)) return rc;   // also pins the pool's release threshold
   auto* ds = new rmi_dataset();
-  ds->n = n; ds->key_type = key_type; ds->device = device; ds->owned = true;
-  size_t bytes = (size_t)n * key_bytes(key_type);
-  if (bytes) {
-    cudaError_t e = cudaMalloc(&ds->d_keys, bytes);
-    if (e != cudaSuccess) { delete ds; return fail(RMI_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
-    e = cudaMemcpy(ds->d_keys, host_keys, bytes, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(ds->d_keys); delete ds; return fail(RMI_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e)); }
+  ds->n = n; ds->key_type = key_type; ds->device = device; ds->owned = true; ds->pooled = true;
+  const size_t kb = key_bytes(key_type), bytes = (size_t)n * kb;
+  if (bytes == 0) { *out = ds; return RMI_OK; }
+  // The key array comes from the stream-ordered pool (a re-created dataset of the same size
+  // costs no driver allocation), the copy runs in 64 MiB pieces and the sortedness check of
+  // piece c runs behind the copy of piece c+1.
+  cudaStream_t st = nullptr;
+  unsigned* d_flag = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMallocAsync(&ds->d_keys, bytes, st);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_flag, sizeof(unsigned), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, sizeof(unsigned), st);
+  unsigned h_flag = 0;
+  if (e == cudaSuccess) {
+    const uint64_t CH = ((uint64_t)64 << 20) / kb;   // keys per piece (multiple of 4)
+    Launch L{st, di.num_sms};
+    for (uint64_t i0 = 0; i0 < n && e == cudaSuccess; i0 += CH) {
+      const uint64_t i1 = std::min<uint64_t>(n, i0 + CH);
+      e = cudaMemcpyAsync((char*)ds->d_keys + i0 * kb, (const char*)host_keys + i0 * kb, (i1 - i0) * kb,
+                          cudaMemcpyHostToDevice, st);
+      switch (key_type) {
+        case RMI_KEY_U64: check_sorted<u64>(L, (const u64*)ds->d_keys, i1, i0, i1, d_flag); break;
+        case RMI_KEY_U32: check_sorted<u32>(L, (const u32*)ds->d_keys, i1, i0, i1, d_flag); break;
+        default: check_sorted<double>(L, (const double*)ds->d_keys, i1, i0, i1, d_flag); break;
+      }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   }
-  if (int rc = verify_sorted(ds)) { cudaFree(ds->d_keys); delete ds; return rc; }
+  if (d_flag) cudaFreeAsync(d_flag, st);
+  if (e != cudaSuccess) {
+    if (ds->d_keys) cudaFreeAsync(ds->d_keys, st);
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    delete ds;
+    return fail(RMI_ERR_CUDA, std::string("rmi_dataset_create: ") + cudaGetErrorString(e));
+  }
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  ds->sorted = h_flag == 0;
   *out = ds;
   return RMI_OK;
 }
@@ -299,7 +332,10 @@ uint64_t rmi_dataset_len(const rmi_dataset* ds) { return ds ? ds->n : 0; }
 int rmi_dataset_key_type(const rmi_dataset* ds) { return ds ? ds->key_type : -1; }
 void rmi_dataset_destroy(rmi_dataset* ds) {
   if (!ds) return;
-  if (ds->owned && ds->d_keys) { cudaSetDevice(ds->device); cudaFree(ds->d_keys); }
+  if (ds->owned && ds->d_keys) {
+    cudaSetDevice(ds->device);
+    if (ds->pooled) cudaFreeAsync(ds->d_keys, nullptr); else cudaFree(ds->d_keys);
+  }
   delete ds;
 }
 

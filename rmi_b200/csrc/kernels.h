@@ -80,7 +80,7 @@ unsigned fit_top_model(const Launch& L, const T* keys, u64 n, int kind, int tabl
                        u64* d_radix_index);
 
 // Sortedness of a key array (verified once per dataset): *d_flag |= 1 if out of order.
-template <class T> void check_sorted(const Launch& L, const T* keys, u64 n, unsigned* d_flag);
+template <class T> void check_sorted(const Launch& L, const T* keys, u64 n, u64 i0, u64 i1, unsigned* d_flag);
 
 // ---- leaf layer (kernels_leaf.cu) ----------------------------------------------------------
 // S[j] = first index whose clamped top prediction is >= j, for j in [0, N]; also verifies

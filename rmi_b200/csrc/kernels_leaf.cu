@@ -1064,29 +1064,32 @@ void fit_leaves(const Launch& L, const T* keys, const Shard<T>& sh, int leaf_kin
   }
 }
 
-// One pass over the keys at dataset-creation time: flag[0] |= 1 if keys[i] < keys[i-1] anywhere.
+// Sortedness of keys[i0, i1) (each key against its predecessor, also across i0): flag[0] |= 1
+// if out of order.  Run once per dataset, chunk by chunk behind the H2D copy.
 template <class T>
 __global__ void __launch_bounds__(BOUNDS_THREADS)
-k_check_sorted(const T* __restrict__ keys, u64 n, unsigned* __restrict__ flag) {
+k_check_sorted(const T* __restrict__ keys, u64 n, u64 i0, u64 i1, unsigned* __restrict__ flag) {
   const bool aligned = is_aligned16(keys);
   u64 stride = (u64)gridDim.x * blockDim.x * 4;
   bool bad = false;
-  for (u64 base = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < n; base += stride) {
+  for (u64 base = (i0 & ~3ull) + ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < i1; base += stride) {
     T k[4];
-    int c = load_keys4(keys, base, n, aligned, k);
-    if (base > 0) bad |= k[0] < keys[base - 1];
+    u64 lim = i1 < n ? i1 : n;
+    int c = load_keys4(keys, base, lim, aligned, k);
+    if (base > 0 && base >= i0) bad |= k[0] < keys[base - 1];
 #pragma unroll
-    for (int e = 1; e < 4; ++e) if (e < c) bad |= k[e] < k[e - 1];
+    for (int e = 1; e < 4; ++e) if (e < c && base + e >= i0) bad |= k[e] < k[e - 1];
   }
   if (bad) atomicOr(flag, 1u);
 }
-template <class T> void check_sorted(const Launch& L, const T* keys, u64 n, unsigned* d_flag) {
-  k_check_sorted<T><<<grid_cap((n + 3) / 4, BOUNDS_THREADS, L.num_sms * 8), BOUNDS_THREADS, 0, L.stream>>>(keys, n, d_flag);
+template <class T> void check_sorted(const Launch& L, const T* keys, u64 n, u64 i0, u64 i1, unsigned* d_flag) {
+  if (i1 <= i0) return;
+  k_check_sorted<T><<<grid_cap((i1 - i0 + 3) / 4 + 1, BOUNDS_THREADS, L.num_sms * 8), BOUNDS_THREADS, 0, L.stream>>>(keys, n, i0, i1, d_flag);
   count_launch();
 }
-template void check_sorted<u64>(const Launch&, const u64*, u64, unsigned*);
-template void check_sorted<u32>(const Launch&, const u32*, u64, unsigned*);
-template void check_sorted<double>(const Launch&, const double*, u64, unsigned*);
+template void check_sorted<u64>(const Launch&, const u64*, u64, u64, u64, unsigned*);
+template void check_sorted<u32>(const Launch&, const u32*, u64, u64, u64, unsigned*);
+template void check_sorted<double>(const Launch&, const double*, u64, u64, u64, unsigned*);
 
 size_t stats_scratch_bytes(u64) { return sizeof(StatsPartial) * STATS_MAX_BLOCKS; }
 
