@@ -1,0 +1,252 @@
+// rmi — command-line front end with the reference's argument surface (src/main.rs:36-102):
+//   rmi <input> [namespace] [models] [branching factor]
+//       [--no-code] [--param-grid <file>] [--data-path|-d <dir>] [--no-errors] [--threads|-t <n>]
+//       [--max-size <bytes>] [--disable-parallel-training] [--zero-build-time] [--optimize <file>]
+// plus  --exact-top-fit (RMI_FLAG_TOP_FIT_EXACT) and --device <n>.
+// The build itself is librmi_b200.so (CUDA); this binary only loads the data set into HBM,
+// calls rmi_train and writes the artefacts (codegen.hpp).  `--bounded` (cache-fix, a serial
+// CPU pre-pass in the reference) is not offered.  There is no CPU training path: without a
+// usable GPU every build fails with the CUDA error text.
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#include "../include/rmi_b200.h"
+#include "codegen.hpp"
+#include "optimizer.hpp"
+
+using namespace rmihost;
+
+namespace {
+
+[[noreturn]] void die(const std::string& msg) {
+  std::fprintf(stderr, "rmi: %s\n", msg.c_str());
+  std::exit(101);   // the exit status of a Rust panic
+}
+
+// ---- a JSON reader just large enough for --param-grid files (objects, arrays, strings, numbers, bools, null)
+struct JVal {
+  enum T { Null, Bool, Num, Str, Arr, Obj } t = Null;
+  bool b = false; double num = 0; std::string s;
+  std::vector<JVal> a;
+  std::vector<std::pair<std::string, JVal>> o;
+  const JVal* get(const std::string& k) const { for (auto& kv : o) if (kv.first == k) return &kv.second; return nullptr; }
+};
+struct JParser {
+  const std::string& src; size_t i = 0;
+  explicit JParser(const std::string& s) : src(s) {}
+  void ws() { while (i < src.size() && std::isspace((unsigned char)src[i])) ++i; }
+  JVal parse() {
+    ws();
+    if (i >= src.size()) die("param grid: unexpected end of JSON");
+    JVal v; char c = src[i];
+    if (c == '{') {
+      v.t = JVal::Obj; ++i; ws();
+      if (src[i] == '}') { ++i; return v; }
+      for (;;) {
+        ws(); JVal k = parse(); if (k.t != JVal::Str) die("param grid: object key must be a string");
+        ws(); if (src[i++] != ':') die("param grid: ':' expected");
+        v.o.push_back({k.s, parse()}); ws();
+        if (src[i] == ',') { ++i; continue; }
+        if (src[i] == '}') { ++i; break; }
+        die("param grid: ',' or '}' expected");
+      }
+    } else if (c == '[') {
+      v.t = JVal::Arr; ++i; ws();
+      if (src[i] == ']') { ++i; return v; }
+      for (;;) {
+        v.a.push_back(parse()); ws();
+        if (src[i] == ',') { ++i; continue; }
+        if (src[i] == ']') { ++i; break; }
+        die("param grid: ',' or ']' expected");
+      }
+    } else if (c == '"') {
+      v.t = JVal::Str; ++i;
+      while (i < src.size() && src[i] != '"') { if (src[i] == '\\' && i + 1 < src.size()) ++i; v.s += src[i++]; }
+      ++i;
+    } else if (!src.compare(i, 4, "true")) { v.t = JVal::Bool; v.b = true; i += 4; }
+    else if (!src.compare(i, 5, "false")) { v.t = JVal::Bool; i += 5; }
+    else if (!src.compare(i, 4, "null")) { i += 4; }
+    else { v.t = JVal::Num; char* e; v.num = std::strtod(src.c_str() + i, &e); i = e - src.c_str(); }
+    return v;
+  }
+};
+
+std::string json_num(double v) {
+  char buf[64];
+  auto r = std::to_chars(buf, buf + sizeof buf, v);
+  return std::string(buf, r.ptr);
+}
+std::string json_str(const std::string& s) {
+  std::string o = "\"";
+  for (char c : s) { if (c == '"' || c == '\\') o += '\\'; o += c; }
+  return o + "\"";
+}
+
+struct Args {
+  std::vector<std::string> pos;
+  std::map<std::string, std::string> opt;
+  bool has(const std::string& k) const { return opt.count(k) != 0; }
+};
+
+Args parse_args(int argc, char** argv) {
+  const std::map<std::string, bool> takes_value = {
+      {"--no-code", false}, {"--dump-ll-model-data", true}, {"--dump-ll-errors", false}, {"--stats-file", true},
+      {"--param-grid", true}, {"--data-path", true}, {"--no-errors", false}, {"--threads", true}, {"--bounded", true},
+      {"--max-size", true}, {"--disable-parallel-training", false}, {"--zero-build-time", false}, {"--optimize", true},
+      {"--exact-top-fit", false}, {"--device", true}, {"--verbose", false}};
+  Args a;
+  for (int i = 1; i < argc; ++i) {
+    std::string s = argv[i];
+    if (s == "-d") s = "--data-path";
+    if (s == "-t") s = "--threads";
+    if (s == "-s") s = "--stats-file";
+    if (s.rfind("--", 0) == 0) {
+      std::string key = s, val;
+      size_t eq = s.find('=');
+      if (eq != std::string::npos) { key = s.substr(0, eq); val = s.substr(eq + 1); }
+      auto it = takes_value.find(key);
+      if (it == takes_value.end()) die("error: Found argument '" + key + "' which wasn't expected");
+      if (it->second && eq == std::string::npos) { if (i + 1 >= argc) die("error: " + key + " requires a value"); val = argv[++i]; }
+      a.opt[key] = val;
+    } else a.pos.push_back(s);
+  }
+  return a;
+}
+
+void print_stats(const rmi_result& r, uint64_t num_rows) {   // main.rs:297-321 (info! lines)
+  std::fprintf(stderr, "Model build time: %llu ms\n", (unsigned long long)(r.build_time_ns / 1000000));
+  std::fprintf(stderr, "Average model error: %g (%g%%)\n", r.model_avg_error, r.model_avg_error / (double)num_rows * 100.0);
+  std::fprintf(stderr, "Average model L2 error: %g\n", r.model_avg_l2_error);
+  std::fprintf(stderr, "Average model log2 error: %g\n", r.model_avg_log2_error);
+  std::fprintf(stderr, "Max model log2 error: %g\n", r.model_max_log2_error);
+  std::fprintf(stderr, "Max model error on model %llu: %llu (%g%%)\n", (unsigned long long)r.model_max_error_idx,
+               (unsigned long long)r.model_max_error, (double)r.model_max_error / (double)num_rows * 100.0);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Args a = parse_args(argc, argv);
+  if (a.pos.empty()) die("error: The following required arguments were not provided:\n    <input>");
+  const std::string fp = a.pos[0];
+  const std::string data_dir = a.has("--data-path") ? a.opt["--data-path"] : "rmi_data";
+  const bool have_ns = a.pos.size() > 1;
+  if (have_ns && a.has("--param-grid")) die("Can only specify one of namespace or param-grid");
+  if (a.has("--bounded")) die("--bounded (cache-fix) is not offered by this build");
+  const int device = a.has("--device") ? std::atoi(a.opt["--device"].c_str()) : 0;
+  const uint32_t flags = a.has("--exact-top-fit") ? RMI_FLAG_TOP_FIT_EXACT : 0;
+  const bool verbose = a.has("--verbose") || std::getenv("RUST_LOG") != nullptr;
+
+  // main.rs:121-132: the key type comes from the file NAME
+  int file_kt;
+  int code_kt = RMI_KEY_U64;   // KeyType handed to codegen: uint32 files keep U64
+  if (fp.find("uint64") != std::string::npos) file_kt = RMI_KEY_U64;
+  else if (fp.find("uint32") != std::string::npos) file_kt = RMI_KEY_U32;
+  else if (fp.find("f64") != std::string::npos) { file_kt = RMI_KEY_F64; code_kt = RMI_KEY_F64; }
+  else die("Data file must contain uint64, uint32, or f64.");
+
+  rmi_dataset* ds = nullptr;
+  if (rmi_dataset_load_file(fp.c_str(), file_kt, device, &ds) != RMI_OK) die(rmi_last_error());
+  const uint64_t num_rows = rmi_dataset_len(ds);
+
+  if (a.has("--optimize")) {   // main.rs:134-161
+    std::vector<RMIStatistics> results;
+    try { results = find_pareto_efficient_configs(ds, 10, flags, verbose); } catch (std::exception& e) { die(e.what()); }
+    display_table(results);
+    std::string prefix;
+    if (have_ns) prefix = a.pos[1];
+    else { size_t sl = fp.find_last_of('/'); prefix = sl == std::string::npos ? fp : fp.substr(sl + 1); }
+    std::ofstream out(a.opt["--optimize"]);
+    if (!out) die("Could not write optimization results file");
+    out << "{\"configs\":[";
+    for (size_t i = 0; i < results.size(); ++i) {
+      auto& v = results[i];
+      if (i) out << ",";
+      out << "{\"layers\":" << json_str(v.models) << ",\"branching factor\":" << v.branching_factor << ",\"namespace\":"
+          << json_str(prefix + "_" + std::to_string(i)) << ",\"size\":" << v.size << ",\"average log2 error\":"
+          << json_num(v.average_log2_error) << ",\"binary\":true}";
+    }
+    out << "]}";
+    rmi_dataset_destroy(ds);
+    return 0;
+  }
+
+  struct stat st;
+  if (stat(data_dir.c_str(), &st) != 0) {   // main.rs:164-169
+    if (mkdir(data_dir.c_str(), 0777) != 0 && errno != EEXIST) die("The RMI data directory did not exist, and it could not be created.");
+  }
+
+  auto train_one = [&](const std::string& models, uint64_t bf, rmi_result** out) {
+    if (rmi_train(ds, models.c_str(), bf, flags, out) != RMI_OK) die(rmi_last_error());
+  };
+
+  if (a.has("--param-grid")) {   // main.rs:171-261
+    std::ifstream in(a.opt["--param-grid"]);
+    if (!in) die("could not read the parameter grid file");
+    std::stringstream ss; ss << in.rdbuf();
+    std::string text = ss.str();
+    JVal root = JParser(text).parse();
+    const JVal* configs = root.get("configs");
+    if (!configs || configs->t != JVal::Arr) die("Configs must have an array as its value");
+    std::ofstream out(a.opt["--param-grid"] + "_results");
+    if (!out) die("Could not write results file");
+    out << "{\"results\":[";
+    bool first = true;
+    for (auto& el : configs->a) {
+      const JVal* l = el.get("layers"); const JVal* b = el.get("branching factor"); const JVal* nsv = el.get("namespace");
+      if (!l || l->t != JVal::Str || !b || b->t != JVal::Num) die("called `Option::unwrap()` on a `None` value (param grid entry)");
+      rmi_result* r = nullptr;
+      train_one(l->s, (uint64_t)b->num, &r);
+      uint64_t size_bs = rmi_size(*r, true);
+      if (!first) out << ",";
+      first = false;
+      // NB "average error %" is computed from the MAX error in the reference (main.rs:211)
+      out << "{\"layers\":" << json_str(l->s) << ",\"branching factor\":" << (uint64_t)b->num << ",\"average error\":"
+          << json_num(r->model_avg_error) << ",\"average error %\":" << json_num((double)r->model_max_error / (double)num_rows * 100.0)
+          << ",\"average l2 error\":" << json_num(r->model_avg_l2_error) << ",\"average log2 error\":" << json_num(r->model_avg_log2_error)
+          << ",\"max error\":" << r->model_max_error << ",\"max error %\":" << json_num((double)r->model_max_error / (double)num_rows * 100.0)
+          << ",\"max log2 error\":" << json_num(r->model_max_log2_error) << ",\"size binary search\":" << size_bs << ",\"namespace\":"
+          << (nsv && nsv->t == JVal::Str ? json_str(nsv->s) : std::string("null")) << "}";
+      if (nsv && nsv->t == JVal::Str) {
+        try { output_rmi(nsv->s, *r, data_dir, code_kt, true, a.has("--zero-build-time") ? 0 : r->build_time_ns); }
+        catch (std::exception& e) { die(e.what()); }
+      }
+      rmi_result_free(r);
+    }
+    out << "]}";
+  } else if (have_ns) {   // main.rs:263-333
+    const std::string ns = a.pos[1];
+    rmi_result* r = nullptr;
+    if (a.has("--max-size")) {   // train_for_size, train/mod.rs:128-154
+      uint64_t max_size = std::strtoull(a.opt["--max-size"].c_str(), nullptr, 10);
+      std::vector<RMIStatistics> pareto;
+      try { pareto = find_pareto_efficient_configs(ds, 1000, flags, verbose); } catch (std::exception& e) { die(e.what()); }
+      const RMIStatistics* pick = nullptr;
+      for (auto& c : pareto) if (c.size < max_size) { pick = &c; break; }
+      if (!pick) die("Could not find any configurations smaller than " + std::to_string(max_size));
+      std::fprintf(stderr, "Found RMI config %s %llu with size %llu and average log2 %g\n", pick->models.c_str(),
+                   (unsigned long long)pick->branching_factor, (unsigned long long)pick->size, pick->average_log2_error);
+      train_one(pick->models, pick->branching_factor, &r);
+    } else {
+      if (a.pos.size() < 4) die("called `Option::unwrap()` on a `None` value (models and branching factor are required)");
+      train_one(a.pos[2], std::strtoull(a.pos[3].c_str(), nullptr, 10), &r);
+    }
+    print_stats(*r, num_rows);
+    if (!a.has("--no-code")) {
+      try { output_rmi(ns, *r, data_dir, code_kt, !a.has("--no-errors"), a.has("--zero-build-time") ? 0 : r->build_time_ns); }
+      catch (std::exception& e) { die(e.what()); }
+    }
+    rmi_result_free(r);
+  }
+  rmi_dataset_destroy(ds);
+  return 0;
+}

@@ -58,5 +58,24 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+CLI_PATH = os.path.join(HERE, "bin", "rmi")
+
+
+def build_cli(force: bool = False) -> str:
+    """The `rmi` command-line front end (host/rmi_main.cpp) linked against librmi_b200.so."""
+    lib = build_library()
+    root = os.path.dirname(HERE)
+    srcs = [os.path.join(root, "host", f) for f in ("rmi_main.cpp", "codegen.hpp", "optimizer.hpp")]
+    os.makedirs(os.path.dirname(CLI_PATH), exist_ok=True)
+    if force or _stale(CLI_PATH, srcs + [lib, os.path.join(root, "include", "rmi_b200.h")]):
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", srcs[0], "-o", CLI_PATH, "-L", LIB_DIR, "-lrmi_b200",
+               "-Wl,-rpath,$ORIGIN/../lib"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return CLI_PATH
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_cli(force="--force" in sys.argv))

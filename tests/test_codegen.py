@@ -1,0 +1,161 @@
+"""The product's code generator (host/codegen.hpp, a restatement of rmi_lib/src/codegen.rs):
+  * the parameter blob <dir>/<ns>_L1_PARAMETERS is byte-identical to the reference layout
+    (N little-endian records {f64 params..., u64 err}; codegen.rs:288-315, models/mod.rs:613-651),
+  * the constants in <ns>_data.h use Rust's f64 Display form (models/mod.rs:565-574),
+  * the generated C++ compiles with the reference's flags and passes the reference's own
+    integration-test property for every key (tests/simple_model_wiki/main.cpp:26-42).
+CPU-only: models come from the oracle; the GPU test at the bottom runs the `rmi` CLI end to end."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import datasets
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODEL_ID = {"linear": 0, "robust_linear": 1, "linear_spline": 2, "cubic": 3, "loglinear": 4, "normal": 5, "lognormal": 6,
+            "radix": 7, "radix_table": 8, "bradix": 9, "histogram": 10}
+TABLE_BITS = {"radix8": 8, "radix18": 18, "radix22": 22}
+
+
+@pytest.fixture(scope="module")
+def tool(tmp_path_factory):
+    d = tmp_path_factory.mktemp("tool")
+    exe = str(d / "codegen_tool")
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cxx", "codegen_tool.cpp"), "-o", exe], check=True)
+    return exe
+
+
+def dump_model(path, o, spec):
+    top = spec.split(",")[0]
+    u = lambda v: struct.pack("<Q", int(v))
+    with open(path, "wb") as f:
+        f.write(u(o.n) + u(o.branching_factor) + u(MODEL_ID[o.l0.kind]) + u(1 if o.l0.high else 0) + u(TABLE_BITS.get(top, 0)))
+        fp = list(o.l0.fp) + [0.0] * (4 - len(o.l0.fp))
+        f.write(u(len(o.l0.fp)) + b"".join(struct.pack("<d", x) for x in fp))
+        ip = [int(x) for x in o.l0.ip] + [0] * (4 - len(o.l0.ip))
+        if o.l0.kind == "histogram":
+            ip = [0, 0, 0, 0]
+        f.write(u(len(o.l0.ip)) + b"".join(u(x) for x in ip))
+        for arr in (o.l0.t32, o.l0.a1, o.l0.a2):
+            f.write(u(len(arr)) + b"".join(u(x) for x in arr))
+        f.write(u(MODEL_ID[o.l1_kind]) + u(o.l1_params.shape[1]))
+        f.write(o.l1_params.astype("<f8").tobytes())
+        f.write(o.l1_errors.astype("<u8").tobytes())
+
+
+def write_keyfile(path, keys):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", keys.size))
+        f.write(keys.tobytes())
+
+
+def rust_display(v: float) -> str:
+    """Rust's Display for f64 (shortest round-trip digits, no exponent) + c_val()'s '.0' rule."""
+    s = np.format_float_positional(v, unique=True, trim="-")
+    return s if "." in s else s + ".0"
+
+
+CASES = [("linear,linear", 512, "uniform_u64"), ("cubic,linear", 1024, "uniform_u64"), ("radix,linear", 1024, "uniform_u64"),
+         ("robust_linear,linear", 256, "lognormal_u64"), ("linear_spline,cubic", 128, "dups_u64"), ("radix18,linear", 2048, "uniform_u64"),
+         ("bradix,linear", 512, "uniform_u64"), ("linear,linear_spline", 64, "uniform_u32"), ("linear,linear", 300, "uniform_f64"),
+         ("normal,linear", 64, "uniform_u64"), ("linear,loglinear", 32, "uniform_u64")]
+DATA = {"uniform_u64": lambda: datasets.uniform_u64(100_000), "lognormal_u64": lambda: datasets.lognormal_u64(100_000),
+        "dups_u64": lambda: datasets.with_duplicates(datasets.uniform_u64(100_000)), "uniform_u32": lambda: datasets.uniform_u32(100_000),
+        "uniform_f64": lambda: datasets.uniform_f64(100_000)}
+
+
+def build_and_check(work, keys, ns="rmi", no_err=False):
+    keyfile = os.path.join(work, "keys.bin")
+    write_keyfile(keyfile, keys)
+    flags = []
+    if keys.dtype == np.uint32:
+        flags += ["-DKEY_T=uint64_t", "-DFILE_T=uint32_t"]
+    elif keys.dtype == np.float64:
+        flags += ["-DKEY_T=double"]
+    if no_err:
+        flags += ["-DNO_ERR"]
+    exe = os.path.join(work, "check")
+    # the reference's test flags (tests/simple_model_wiki/Makefile:12), minus -march=native
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-O3", "-ffast-math", "-I", work, os.path.join(ROOT, "tests", "cxx", "check_main.cpp"),
+                    os.path.join(work, f"{ns}.cpp"), "-o", exe] + flags, check=True, cwd=work)
+    r = subprocess.run([exe, keyfile, os.path.join(work, "rmi_data")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+@pytest.mark.parametrize("spec,bf,dname", CASES, ids=[f"{c[0]}:{c[1]}:{c[2]}" for c in CASES])
+def test_generated_code_holds_the_reference_property(oracle, tool, tmp_path, spec, bf, dname):
+    keys = DATA[dname]()
+    try:
+        o = oracle.train(keys, spec, bf)
+    except oracle.OraclePanic as e:
+        pytest.skip(f"reference panics: {e}")
+    work = str(tmp_path)
+    os.makedirs(os.path.join(work, "rmi_data"))
+    dump = os.path.join(work, "model.bin")
+    dump_model(dump, o, spec)
+    kt = {np.dtype(np.uint64): 0, np.dtype(np.uint32): 1, np.dtype(np.float64): 2}[keys.dtype]
+    subprocess.run([tool, dump, "rmi", os.path.join(work, "rmi_data"), work, "1", str(kt)], check=True)
+    # 1. the leaf blob is byte-identical to the reference layout
+    ppm = o.l1_params.shape[1]
+    rec = np.zeros(o.branching_factor, dtype=[("p", "<f8", (ppm,)), ("e", "<u8")])
+    rec["p"], rec["e"] = o.l1_params, o.l1_errors
+    blob = open(os.path.join(work, "rmi_data", "rmi_L1_PARAMETERS"), "rb").read()
+    assert blob == rec.tobytes()
+    # 2. top-model constants in Rust's text form
+    data_h = open(os.path.join(work, "rmi_data.h")).read()
+    if len(o.l0.fp) and o.l0.kind != "histogram":
+        for i, v in enumerate(o.l0.fp):
+            assert f"const double L0_PARAMETER{i} = {rust_display(float(v))};" in data_h
+    for i, v in enumerate(o.l0.ip if o.l0.kind in ("radix", "bradix") else []):
+        assert f"const uint64_t L0_PARAMETER{i} = {int(v)}UL;" in data_h
+    # 3. header constants
+    hdr = open(os.path.join(work, "rmi.h")).read()
+    top_bytes = 8 * (len(o.l0.fp) + (len(o.l0.ip) if o.l0.kind in ("radix", "bradix") else 0)) + 4 * len(o.l0.t32)
+    assert f"const size_t RMI_SIZE = {top_bytes + o.branching_factor * (8 * ppm + 8)};" in hdr
+    assert "const uint64_t BUILD_TIME_NS = 0;" in hdr and 'const char NAME[] = "rmi";' in hdr
+    # 4. compile and run the reference's validity check over every key
+    out = build_and_check(work, keys)
+    assert out.startswith("ok")
+
+
+def test_no_errors_variant(oracle, tool, tmp_path):
+    keys = DATA["uniform_u64"]()
+    o = oracle.train(keys, "linear,linear", 128)
+    work = str(tmp_path)
+    os.makedirs(os.path.join(work, "rmi_data"))
+    dump_model(os.path.join(work, "m.bin"), o, "linear,linear")
+    subprocess.run([tool, os.path.join(work, "m.bin"), "rmi", os.path.join(work, "rmi_data"), work, "0", "0"], check=True)
+    # --no-errors: the leaf layer is a plain f64 array, below 4 KiB it is a fixed-size array (codegen.rs:124-147)
+    assert "double L1_PARAMETERS[256];" in open(os.path.join(work, "rmi_data.h")).read()
+    assert "uint64_t lookup(uint64_t key);" in open(os.path.join(work, "rmi.h")).read()
+    assert open(os.path.join(work, "rmi_data", "rmi_L1_PARAMETERS"), "rb").read() == o.l1_params.astype("<f8").tobytes()
+    build_and_check(work, keys, no_err=True)
+
+
+def test_rust_float_display():
+    assert rust_display(1.0) == "1.0" and rust_display(0.1) == "0.1" and rust_display(1e21) == "1000000000000000000000.0"
+    assert rust_display(1.5e-7) == "0.00000015" and rust_display(-2.5) == "-2.5"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec,bf,dname,extra", [("linear,linear", 4096, "uniform_u64", []), ("cubic,linear", 2048, "uniform_u64", []),
+                                                 ("radix,linear", 4096, "uniform_u32", []),
+                                                 ("robust_linear,linear", 1024, "uniform_f64", ["--exact-top-fit"])])
+def test_cli_end_to_end_on_gpu(tmp_path, spec, bf, dname, extra):
+    """`rmi <file> rmi <models> <bf> --zero-build-time` -> generated sources -> reference validity check."""
+    from rmi_b200 import build
+    cli = build.build_cli()
+    keys = {"uniform_u64": datasets.uniform_u64, "uniform_u32": datasets.uniform_u32, "uniform_f64": datasets.uniform_f64}[dname](1_000_000)
+    work = str(tmp_path)
+    suffix = {"uniform_u64": "uint64", "uniform_u32": "uint32", "uniform_f64": "f64"}[dname]
+    datafile = os.path.join(work, f"synthetic_1M_{suffix}")
+    write_keyfile(datafile, keys)
+    r = subprocess.run([cli, datafile, "rmi", spec, str(bf), "--zero-build-time"] + extra, cwd=work, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "const uint64_t BUILD_TIME_NS = 0;" in open(os.path.join(work, "rmi.h")).read()
+    out = build_and_check(work, keys)
+    assert out.startswith("ok")
