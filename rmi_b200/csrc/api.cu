@@ -107,6 +107,7 @@ struct rmi_dataset {
   bool owned = false;
   bool pooled = false;  // d_keys came from the stream-ordered pool (cudaMallocAsync)
   bool sorted = true;   // verified once, when the dataset is created (the data is immutable)
+  bool no_dups = false; // found at the same time: no two keys are equal (kernels drop the duplicate tracking)
 };
 
 namespace {
@@ -132,7 +133,8 @@ int verify_sorted(rmi_dataset* ds) {
   cudaError_t e = cudaMemcpy(&h, d_flag, sizeof(unsigned), cudaMemcpyDeviceToHost);
   cudaFree(d_flag);
   if (e != cudaSuccess) return fail(RMI_ERR_CUDA, std::string("sortedness check: ") + cudaGetErrorString(e));
-  ds->sorted = h == 0;
+  ds->sorted = (h & 1u) == 0;
+  ds->no_dups = (h & 2u) == 0;
   return RMI_OK;
 }
 }  // namespace
@@ -255,7 +257,8 @@ int rmi_dataset_create(const void* host_keys, uint64_t n, rmi_key_type key_type,
   }
   cudaStreamSynchronize(st);
   cudaStreamDestroy(st);
-  ds->sorted = h_flag == 0;
+  ds->sorted = (h_flag & 1u) == 0;
+  ds->no_dups = (h_flag & 2u) == 0;
   *out = ds;
   return RMI_OK;
 }
@@ -435,7 +438,11 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
         // injected top parameters are not known to be monotone: take the streaming pass, which checks
         compute_leaf_bounds<T>(L, keys, n, top.kind, d_top, N, d_S, d_aux, /*allow_search=*/l0_over == nullptr);
         cudaEventRecord(evp[1], st);
-        fit_leaves<T>(L, keys, whole_array<T>(n), leaf.kind, N, d_S, d_aux, d_params, d_errors, d_counts);
+        {
+          Shard<T> whole = whole_array<T>(n);
+          whole.no_dups = ds->no_dups ? 1 : 0;
+          fit_leaves<T>(L, keys, whole, leaf.kind, N, d_S, d_aux, d_params, d_errors, d_counts);
+        }
         cudaEventRecord(evp[2], st);
         leaf_statistics(L, n, N, d_errors, d_counts, d_aux, d_stats);
       } else {
@@ -639,6 +646,7 @@ template <class T> Shard<T> make_shard(const rmi_shard_build* b) {
   s.is_last = b->info.is_last;
   s.prev_key = key_from_bits<T>(b->info.prev_key_bits);
   s.prev_F = b->info.prev_F;
+  s.no_dups = 0;   // runs of equal keys may cross slab boundaries: keep the general kernels
   return s;
 }
 

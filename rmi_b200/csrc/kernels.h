@@ -54,10 +54,11 @@ template <class T> struct Shard {
   int is_last;    // this rank holds the data set's last key
   T prev_key;
   u64 prev_F;     // duplicate-fixed global offset of prev_key
+  int no_dups;    // the whole data set is known to contain no two equal keys
 };
 template <class T> inline Shard<T> whole_array(u64 n) {
   Shard<T> s;
-  s.base = 0; s.n_global = n; s.n_local = n; s.n_avail = n; s.has_prev = 0; s.is_last = 1; s.prev_key = T(); s.prev_F = 0;
+  s.base = 0; s.n_global = n; s.n_local = n; s.n_avail = n; s.has_prev = 0; s.is_last = 1; s.prev_key = T(); s.prev_F = 0; s.no_dups = 0;
   return s;
 }
 

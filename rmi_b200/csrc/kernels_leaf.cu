@@ -217,11 +217,14 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
     for (int q = 0; q < 8; ++q) {
       if (c < np[q]) {
         const u32 g = g0[q] + 8u * c;
-        const int bytes = g < g_full ? 16 : tail_bytes;
         u64 src;
         asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(src) : "r"(g), "l"(kb));
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)),
-                     "l"(src), "r"(bytes) : "memory");
+        if (g < g_full) {   // the only partial piece is the one that straddles the end of the key array
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)), "l"(src) : "memory");
+        } else {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)),
+                       "l"(src), "r"(tail_bytes) : "memory");
+        }
       }
     }
     cp_async_commit();
@@ -389,20 +392,22 @@ template <bool CHECKED> struct LeafWelford {
     return __fma_rn(rem, rc, q0);
   }
   __device__ __forceinline__ void push(double x, double y) {
-    nf = __dadd_rn(nf, 1.0);
     double rc;
-    if (ra < ra_end) {   // 1/nf from the shared table (entry ni = table[ni])
+    if (ra < ra_end) {   // 1/n from the shared table
       ra += (unsigned)sizeof(double);
       asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
     } else {
-      rc = rcp_beyond_table(nf);   // leaves longer than the table: a real call, so it is not if-converted
+      rc = rcp_beyond_table(__dadd_rn(nf, 1.0));   // longer than the table: a real call, so it is not if-converted
     }
-    double dx = __dadd_rn(x, -mean_x);
-    mean_x = __dadd_rn(mean_x, dv(dx, rc));
-    mean_y = __dadd_rn(mean_y, dv(__dadd_rn(y, -mean_y), rc));
-    c = __dadd_rn(c, __dmul_rn(dx, __dadd_rn(y, -mean_y)));
-    double dx2 = __dadd_rn(x, -mean_x);
-    m2 = __dadd_rn(m2, __dmul_rn(dx, dx2));
+    push_rc(x, y, rc);
+  }
+  // the caller guarantees fewer than RCP_TABLE items in total (no lane of the warp has a longer
+  // vector): 1/n always comes from the shared table and the step has no branch
+  __device__ __forceinline__ void push_t(double x, double y) {
+    double rc;
+    ra += (unsigned)sizeof(double);
+    asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
+    push_rc(x, y, rc);
   }
   // the same step with the count's reciprocal supplied by the caller (solo mode)
   __device__ __forceinline__ void push_rc(double x, double y, double rc) {
@@ -434,12 +439,14 @@ __device__ __forceinline__ double scale3(double v, double mn, double mx) {
 // Item tracker for a pass over a training vector: yields y = the duplicate-fixed offset as a
 // double (exact below 2^53) without an int->float conversion per item.  Seeded with the
 // vector's first key and its offset F0, so the first item needs no special case.
-template <class T> struct ItemTracker {
+// DUPS = false (the data set was found free of equal keys when it was created): every item's
+// offset is its own index, no comparison at all.
+template <class T, bool DUPS = true> struct ItemTracker {
   T pk;
   double pyd, idxd;
   __device__ __forceinline__ void init(T first_key, double vs_d, double f0_d) { pk = first_key; pyd = f0_d; idxd = vs_d; }
   __device__ __forceinline__ double next(T k) {
-    double yd = (k == pk) ? pyd : idxd;
+    double yd = (!DUPS || !(k == pk)) ? idxd : pyd;
     pk = k; pyd = yd;
     idxd = __dadd_rn(idxd, 1.0);
     return yd;
@@ -449,7 +456,7 @@ template <class T> struct ItemTracker {
 // train_model(layer2, vector) for every leaf model type, as warp-synchronous stream passes.
 // f receives Model::params().  Every lane of the warp must call this (with vs == ve if it has
 // no leaf or an empty vector).
-template <class T, class I, int LEAF>
+template <class T, class I, int LEAF, bool DUPS>
 __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard<T>& sh, unsigned char* wsm,
                                          const LeafRange<T, I>& r, const double* rcp, double* f, unsigned& bad) {
   const u64 n_keys = sh.n_avail;
@@ -467,7 +474,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     // linear.rs:79-83 / :61-72,169-173 — drained stream: vector + repeat of the final item
     LeafWelford<CHECKED> w;
     w.init(rcp);
-    ItemTracker<T> it;
+    ItemTracker<T, DUPS> it;
     it.init(kfirst, vsd, f0d);
     auto item = [&](T k, I) {
       double yy = it.next(k);
@@ -482,6 +489,16 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
       }
       if (!w.finish(f[0], f[1])) bad |= ST_NEG_VARIANCE;
     };
+    // Warps in which no vector reaches the end of the reciprocal table (almost all of them)
+    // take the branch-free step.
+    const bool all_short = !__any_sync(0xffffffffu, (u64)L + 2 >= (u64)RCP_TABLE);
+    if (LEAF == M_LINEAR && all_short) {
+      auto item_t = [&](T k, I) { w.push_t(Key<T>::as_float(k), it.next(k)); };
+      if (r.p_remote) item_t(r.pkey, (I)0);
+      stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item_t);
+      finalize();
+      return;
+    }
     if (r.p_remote) item(r.pkey, (I)0);
     int solo_lane;
     I solo_at;
@@ -534,7 +551,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     if (!ok) bad |= ST_ROBUST_TOO_SMALL;
     LeafWelford<CHECKED> w;
     w.init(rcp);
-    ItemTracker<T> it;
+    ItemTracker<T, DUPS> it;
     it.init(kfirst, vsd, f0d);
     u64 pos = 0;
     vector_pass([&](T k, I) {
@@ -567,7 +584,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     bool uniq = false, found1 = false;
     double sxn = 0.0, syn = 0.0;
     {
-      ItemTracker<T> it;
+      ItemTracker<T, DUPS> it;
       it.init(kfirst, vsd, f0d);
       vector_pass([&](T k, I) {
         double yy = it.next(k);
@@ -623,7 +640,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     double cf[4] = {a, b, c, d}, lf[2] = {la, lb};
     double our_error = 0.0, lin_error = 0.0;
     {
-      ItemTracker<T> it;
+      ItemTracker<T, DUPS> it;
       it.init(kfirst, vsd, f0d);
       auto acc = [&](double x, double yy) {
         our_error = __dadd_rn(our_error, fabs(__dadd_rn(predict_float<M_CUBIC>(cf, x), -yy)));
@@ -642,7 +659,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
       if (LEAF == M_LOGNORMAL) { double l = log(x); x = isfinite(l) ? l : 0.0; }
       return x;
     };
-    ItemTracker<T> it;
+    ItemTracker<T, DUPS> it;
     it.init(kfirst, vsd, f0d);
     vector_pass([&](T k, I) {
       double yy = it.next(k);
@@ -697,7 +714,7 @@ constexpr size_t leaf_smem_bytes() {
   return (size_t)RCP_TABLE * sizeof(double) + (size_t)(LEAF_THREADS / 32) * WARP_STREAM_BYTES;
 }
 
-template <class T, class I, int LEAF>
+template <class T, class I, int LEAF, bool DUPS>
 __global__ void __launch_bounds__(LEAF_THREADS)
 k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restrict__ S, BuildAux* aux,
        double* __restrict__ params, u64* __restrict__ errors, u64* __restrict__ counts) {
@@ -768,7 +785,7 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   if (live && g_hi > sh.base + sh.n_avail) { bad |= ST_HALO_TOO_SMALL; r.hi = r.lo; }
 
   double f[4] = {0.0, 0.0, 0.0, 0.0};
-  fit_leaf<T, I, LEAF>(keys, sh, wsm, r, s_rcp, f, bad);
+  fit_leaf<T, I, LEAF, DUPS>(keys, sh, wsm, r, s_rcp, f, bad);
 
   // two_layer.rs:186-197: empty leaves (lower-bound-correction sense) except the last
   const u64 next_idx = g_hi;                                        // lb.next_index(j) = S[j+1]
@@ -801,15 +818,29 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   {
     T pk = (live && g_lo == 0 && g_hi > 0) ? keys[0] : prev_key;
     I F = (I)g_lo, run = 0;
-    stream_pass<T, I>(keys, sh.n_avail, wsm, r.lo, long_leaf ? r.lo : r.hi, [&](T k, I i) {
-      if (k != pk) { run_max = run > run_max ? run : run_max; run = 0; F = (I)(i + baseI); }
-      run += 1;
-      pk = k;
-      I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
-      I e = pred > F ? pred - F : F - pred;
-      max_err = e > max_err ? e : max_err;
-    });
-    if (g_hi < n && run > run_max) run_max = run;
+    if (DUPS) {
+      stream_pass<T, I>(keys, sh.n_avail, wsm, r.lo, long_leaf ? r.lo : r.hi, [&](T k, I i) {
+        if (k != pk) { run_max = run > run_max ? run : run_max; run = 0; F = (I)(i + baseI); }
+        run += 1;
+        pk = k;
+        I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
+        I e = pred > F ? pred - F : F - pred;
+        max_err = e > max_err ? e : max_err;
+      });
+      if (g_hi < n && run > run_max) run_max = run;
+    } else {
+      // no two keys of the data set are equal: the offset of a key is its index, every run has
+      // length 1 (and the data set's final run is never recorded)
+      stream_pass<T, I>(keys, sh.n_avail, wsm, r.lo, long_leaf ? r.lo : r.hi, [&](T k, I i) {
+        I Fi = (I)(i + baseI);
+        I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
+        I e = pred > Fi ? pred - Fi : Fi - pred;
+        max_err = e > max_err ? e : max_err;
+      });
+      const u64 recorded = g_hi < n ? (g_hi - g_lo) : (g_hi > g_lo ? g_hi - g_lo - 1 : 0);
+      run_max = recorded > 0 ? (I)1 : (I)0;
+      (void)pk; (void)F; (void)run;
+    }
   }
   {
     const unsigned FULL = 0xffffffffu;
@@ -1013,19 +1044,27 @@ void launch_bounds_impl(const Launch& L, const T* keys, u64 n, const TopModel* d
   count_launch();
 }
 
+template <class T, class I, int LEAF, bool DUPS>
+void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N, const u64* d_S, BuildAux* d_aux,
+                      double* d_params, u64* d_errors, u64* d_counts) {
+  u64 blocks = (N + LEAF_THREADS - 1) / LEAF_THREADS;
+  constexpr size_t smem = leaf_smem_bytes();
+  cudaFuncSetAttribute(k_leaf<T, I, LEAF, DUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_leaf<T, I, LEAF, DUPS><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts);
+  count_launch();
+}
 template <class T, int LEAF>
 void launch_leaf(const Launch& L, const T* keys, const Shard<T>& sh, u64 N, const u64* d_S, BuildAux* d_aux,
                  double* d_params, u64* d_errors, u64* d_counts) {
-  u64 blocks = (N + LEAF_THREADS - 1) / LEAF_THREADS;
-  constexpr size_t smem = leaf_smem_bytes();
+  constexpr bool SPECIALISED = LEAF == M_LINEAR || LEAF == M_LINEAR_SPLINE || LEAF == M_CUBIC;
   if (sh.n_global < 0xfffffff0ull) {   // 32-bit indices
-    cudaFuncSetAttribute(k_leaf<T, u32, LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_leaf<T, u32, LEAF><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts);
+    if (SPECIALISED && sh.no_dups)
+      launch_leaf_inst<T, u32, SPECIALISED ? LEAF : M_LINEAR, false>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts);
+    else
+      launch_leaf_inst<T, u32, LEAF, true>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts);
   } else {
-    cudaFuncSetAttribute(k_leaf<T, u64, LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_leaf<T, u64, LEAF><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts);
+    launch_leaf_inst<T, u64, LEAF, true>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts);
   }
-  count_launch();
 }
 
 }  // namespace
@@ -1065,22 +1104,23 @@ void fit_leaves(const Launch& L, const T* keys, const Shard<T>& sh, int leaf_kin
 }
 
 // Sortedness of keys[i0, i1) (each key against its predecessor, also across i0): flag[0] |= 1
-// if out of order.  Run once per dataset, chunk by chunk behind the H2D copy.
+// if out of order, |= 2 if two neighbours are equal.  Run once per dataset, chunk by chunk behind the H2D copy.
 template <class T>
 __global__ void __launch_bounds__(BOUNDS_THREADS)
 k_check_sorted(const T* __restrict__ keys, u64 n, u64 i0, u64 i1, unsigned* __restrict__ flag) {
   const bool aligned = is_aligned16(keys);
   u64 stride = (u64)gridDim.x * blockDim.x * 4;
-  bool bad = false;
+  bool bad = false, dup = false;
   for (u64 base = (i0 & ~3ull) + ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; base < i1; base += stride) {
     T k[4];
     u64 lim = i1 < n ? i1 : n;
     int c = load_keys4(keys, base, lim, aligned, k);
-    if (base > 0 && base >= i0) bad |= k[0] < keys[base - 1];
+    if (base > 0 && base >= i0) { T p = keys[base - 1]; bad |= k[0] < p; dup |= k[0] == p; }
 #pragma unroll
-    for (int e = 1; e < 4; ++e) if (e < c && base + e >= i0) bad |= k[e] < k[e - 1];
+    for (int e = 1; e < 4; ++e) if (e < c && base + e >= i0) { bad |= k[e] < k[e - 1]; dup |= k[e] == k[e - 1]; }
   }
   if (bad) atomicOr(flag, 1u);
+  if (dup) atomicOr(flag, 2u);   // some key occurs more than once
 }
 template <class T> void check_sorted(const Launch& L, const T* keys, u64 n, u64 i0, u64 i1, unsigned* d_flag) {
   if (i1 <= i0) return;
