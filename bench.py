@@ -216,7 +216,7 @@ def main():
         ds = rmi_b200.RMITrainingData.from_device(k.data_ptr(), n, rmi_b200.KEY_U64, local_rank, keep_alive=k)
 
         def build():
-            return rmi_b200.train(ds, args.spec, N, flags)
+            return rmi_b200.train(ds, args.spec, N, flags, counts=False)
     else:
         # range-partitioned build: ONE global RMI with N leaves over all ranks' keys
         # (rank r holds the r-th slab of the globally sorted array); weak scaling in keys.
@@ -224,7 +224,7 @@ def main():
         sdata = sharded.ShardedTrainingData(k, n, rmi_b200.KEY_U64, halo_capacity=1 << 20)
 
         def build():
-            return sharded.train_sharded(sdata, args.spec, N, flags)
+            return sharded.train_sharded(sdata, args.spec, N, flags, counts=False)
 
     def barrier():
         if dist is not None:
@@ -271,14 +271,14 @@ def main():
     def e2e_step():
         if world == 1:
             d2 = rmi_b200.RMITrainingData(host_np, device=local_rank)   # cudaMemcpy H2D from pinned memory
-            r2 = rmi_b200.train(d2, args.spec, N, flags)
+            r2 = rmi_b200.train(d2, args.spec, N, flags, counts=False)
             d2.close()
         else:
             from rmi_b200 import sharded
             kd = torch.empty(n + (1 << 20), dtype=torch.int64, device=dev)
             kd[:n].copy_(host, non_blocking=False)                       # H2D from pinned memory
             sd = sharded.ShardedTrainingData(kd, n, rmi_b200.KEY_U64, halo_capacity=1 << 20)
-            r2 = sharded.train_sharded(sd, args.spec, N, flags)
+            r2 = sharded.train_sharded(sd, args.spec, N, flags, counts=False)
         return r2
 
     e2e_step()
@@ -307,7 +307,7 @@ def main():
     names = ["top_fit", "leaf_bounds", "leaf_fit_error(k_leaf)", "statistics"]
     dom = int(np.argmax(phase_ms))
     peak, peak_src = measured_hbm_peak()
-    out_bytes = N * (8 * ppm + 16)
+    out_bytes = N * (8 * ppm + 8)     # leaf parameters + error bounds copied to the host every step
     kern_bytes = {0: n * key_bytes, 1: n * key_bytes + (N + 1) * 8, 2: n * key_bytes + (N + 1) * 8 + out_bytes,
                   3: N * 16}[dom]
     achieved = kern_bytes / (phase_ms[dom] / 1e3) / 1e9

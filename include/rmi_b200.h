@@ -59,7 +59,9 @@ enum {
                                    (linear.rs:12-59) on one device thread: bit-identical to the
                                    reference, seconds at 200 M keys.  Default is the parallel fit
                                    (tree reduction, coefficients equal within 1e-9 relative). */
-  RMI_FLAG_NO_ERRORS = 4u       /* reserved for --no-errors (main.rs:84-86); errors are still computed */
+  RMI_FLAG_NO_ERRORS = 4u,      /* reserved for --no-errors (main.rs:84-86); errors are still computed */
+  RMI_FLAG_LEAF_COUNTS = 8u     /* also return l1_counts (keys per leaf as the error pass counts them,
+                                   two_layer.rs:207-217); not part of TrainedRMI, used by parity checks */
 };
 
 /* A device-resident sorted key set.  Replaces src/load.rs:132-157 load_data + the mmap
@@ -120,7 +122,7 @@ typedef struct {
   uint32_t l1_params_per_model;
   const double* l1_params;      /* N x params_per_model, leaf order; NULL with STATS_ONLY */
   const uint64_t* l1_errors;    /* N; NULL with STATS_ONLY */
-  const uint64_t* l1_counts;    /* N keys-per-leaf as counted by two_layer.rs:207-217; NULL with STATS_ONLY */
+  const uint64_t* l1_counts;    /* N keys-per-leaf as counted by two_layer.rs:207-217; only with RMI_FLAG_LEAF_COUNTS */
   uint32_t could_not_replace;   /* two_layer.rs:199-202 warning condition */
   uint32_t top_fit_exact;       /* 1 if the top model came from the serial recurrence */
 } rmi_result;

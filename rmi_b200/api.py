@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "lib", "librmi_b200.so")
 
 KEY_U64, KEY_U32, KEY_F64 = 0, 1, 2
-FLAG_STATS_ONLY, FLAG_TOP_FIT_EXACT = 1, 2
+FLAG_STATS_ONLY, FLAG_TOP_FIT_EXACT, FLAG_LEAF_COUNTS = 1, 2, 8
 _NP_OF_KEY = {KEY_U64: np.uint64, KEY_U32: np.uint32, KEY_F64: np.float64}
 MODEL_NAMES = ["linear", "robust_linear", "linear_spline", "cubic", "loglinear", "normal", "lognormal", "radix",
                "radix_table", "bradix", "histogram"]
@@ -214,9 +214,12 @@ def _arr(ptr, n, ctype, dtype, owner):
 
 
 def train(data: RMITrainingData, model_spec: str, branch_factor: int, flags: int = 0,
-          l0_params=None) -> TrainedRMI:
-    """rmi_lib::train (train/mod.rs:100-126) on the GPU.  Raises RMIPanic where the reference panics."""
+          l0_params=None, counts: bool = True) -> TrainedRMI:
+    """rmi_lib::train (train/mod.rs:100-126) on the GPU.  Raises RMIPanic where the reference panics.
+    counts=True also fetches the per-leaf key counts (RMI_FLAG_LEAF_COUNTS, used by parity checks)."""
     L = load_library()
+    if counts:
+        flags = int(flags) | FLAG_LEAF_COUNTS
     res = C.POINTER(_Result)()
     if l0_params is None:
         rc = L.rmi_train(data._h, model_spec.encode(), int(branch_factor), int(flags), C.byref(res))

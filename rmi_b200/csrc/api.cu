@@ -405,8 +405,9 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
     // pinned host buffers the results are copied into (and that the caller then reads)
     const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0;
     bool host_ok = box->scalars.resize(sizeof(BuildAux) + sizeof(TopModel));
-    if (!stats_only)
-      host_ok = host_ok && box->l1_params.resize((size_t)N * ppm) && box->l1_errors.resize(N) && box->l1_counts.resize(N);
+    const bool want_counts = !stats_only && (flags & RMI_FLAG_LEAF_COUNTS) != 0;
+    if (!stats_only) host_ok = host_ok && box->l1_params.resize((size_t)N * ppm) && box->l1_errors.resize(N);
+    if (want_counts) host_ok = host_ok && box->l1_counts.resize(N);
     if (top.kind == M_RADIX_TABLE) host_ok = host_ok && box->table32.resize((size_t)1 << top.table_bits);
     if (top.kind == M_HISTOGRAM) host_ok = host_ok && box->arr1.resize(((size_t)1 << 20) + 1) && box->arr2.resize(hist_bins);
     if (A.err != cudaSuccess) {
@@ -459,7 +460,7 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
       if (host_status == 0 && !stats_only) {
         cudaMemcpyAsync(box->l1_params.data(), d_params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(box->l1_errors.data(), d_errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(box->l1_counts.data(), d_counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
+        if (want_counts) cudaMemcpyAsync(box->l1_counts.data(), d_counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
       }
       if (host_status == 0 && top.kind == M_RADIX_TABLE) {
         cudaMemcpyAsync(box->table32.data(), d_table, sizeof(u32) * box->table32.size(), cudaMemcpyDeviceToHost, st);
@@ -516,7 +517,7 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
         R.l1_params_per_model = ppm;
         R.l1_params = stats_only ? nullptr : box->l1_params.data();
         R.l1_errors = stats_only ? nullptr : box->l1_errors.data();
-        R.l1_counts = stats_only ? nullptr : box->l1_counts.data();
+        R.l1_counts = want_counts ? box->l1_counts.data() : nullptr;
         R.could_not_replace = h_aux.could_not_replace ? 1 : 0;
         R.top_fit_exact = (exact && !l0_over) ? 1 : 0;
       }
@@ -807,7 +808,9 @@ int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
   const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0;
   auto box = new ResultBox();
   bool host_ok = box->scalars.resize(sizeof(BuildAux) + sizeof(TopModel));
-  if (!stats_only) host_ok = host_ok && box->l1_params.resize((size_t)N * ppm) && box->l1_errors.resize(N) && box->l1_counts.resize(N);
+  const bool want_counts = !stats_only && (flags & RMI_FLAG_LEAF_COUNTS) != 0;
+  if (!stats_only) host_ok = host_ok && box->l1_params.resize((size_t)N * ppm) && box->l1_errors.resize(N);
+  if (want_counts) host_ok = host_ok && box->l1_counts.resize(N);
   if (!host_ok) { delete box; return fail(RMI_ERR_CUDA, "pinned host allocation for the results failed"); }
   BuildAux& h_aux = *reinterpret_cast<BuildAux*>(box->scalars.data());
   TopModel& h_top = *reinterpret_cast<TopModel*>(box->scalars.data() + sizeof(BuildAux));
@@ -817,7 +820,7 @@ int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
   if (!stats_only) {
     cudaMemcpyAsync(box->l1_params.data(), b->buf.params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, b->st);
     cudaMemcpyAsync(box->l1_errors.data(), b->buf.errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, b->st);
-    cudaMemcpyAsync(box->l1_counts.data(), b->buf.counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, b->st);
+    if (want_counts) cudaMemcpyAsync(box->l1_counts.data(), b->buf.counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, b->st);
   }
   cudaError_t e = cudaStreamSynchronize(b->st);
   if (e == cudaSuccess) e = cudaMemcpy(&h_status, b->buf.status, sizeof(unsigned), cudaMemcpyDeviceToHost);
@@ -847,7 +850,7 @@ int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
   R.l1_params_per_model = ppm;
   R.l1_params = stats_only ? nullptr : box->l1_params.data();
   R.l1_errors = stats_only ? nullptr : box->l1_errors.data();
-  R.l1_counts = stats_only ? nullptr : box->l1_counts.data();
+  R.l1_counts = want_counts ? box->l1_counts.data() : nullptr;
   {   // device time of this rank's phases (collectives between them are not included)
     const int map[6] = {0, 0, 1, 1, 2, 3};
     for (int q = 0; q < 6; ++q) {

@@ -146,10 +146,10 @@ __global__ void k_split(const T* __restrict__ keys, u64 n, const TopModel* __res
 constexpr int ROW_BYTES = 144;   // 128 B of keys + 16 B pad: rows stay 16-byte aligned and the 8 lanes of
                                  // a 128-bit shared-load phase hit 8 distinct bank quads
 #ifndef RMI_SSTAGES
-#define RMI_SSTAGES 3
+#define RMI_SSTAGES 2
 #endif
 #ifndef RMI_PARTIAL_MODE
-#define RMI_PARTIAL_MODE 0   // 0: per-lane fast/slow split, 1: warp-uniform predicated walk, 2: one variable-bound loop
+#define RMI_PARTIAL_MODE 2   // 0: per-lane fast/slow split, 1: warp-uniform predicated walk, 2: one variable-bound loop
 #endif
 constexpr int SSTAGES = RMI_SSTAGES;
 constexpr int WARP_STREAM_BYTES = SSTAGES * 32 * ROW_BYTES + 32 * 4 + 32 * 4;

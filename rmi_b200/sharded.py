@@ -203,7 +203,7 @@ class CudaShardEngine:
 
     def finish(self, flags: int = 0):
         res = C.POINTER(api._Result)()
-        api._check(self.lib.rmi_shard_finish(self._build, flags, C.byref(res)))
+        api._check(self.lib.rmi_shard_finish(self._build, int(flags), C.byref(res)))
         return api.result_from_pointer(res, self._spec)
 
     def end(self):
@@ -224,7 +224,7 @@ def _world(group):
     return 0, 1
 
 
-def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=None, engine=None):
+def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=None, engine=None, counts: bool = True):
     """rmi_lib::train on a range-partitioned key array; returns the full TrainedRMI on every rank."""
     eng = engine if engine is not None else data.engine
     group = group if group is not None else getattr(data, "group", None)
@@ -292,7 +292,7 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
             # every rank computes the same `most`, so they all take this branch together
             if engine is None and hasattr(data, "grow_halo"):
                 data.grow_halo(int(most * 1.25) + 1024)
-                return train_sharded(data, model_spec, num_leaves, flags, group)
+                return train_sharded(data, model_spec, num_leaves, flags, group, counts=counts)
             raise api.RMIError("a leaf reaches further into the next rank than the halo capacity "
                                f"({most} keys needed)")
         # gloo cannot send/recv device memory (one-GPU test boxes): stage through the host there
@@ -324,7 +324,7 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
         dist.all_reduce(bufs["counts"], op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(bufs["status"], op=dist.ReduceOp.MAX, group=group)
     eng.phase(PHASE_STATS)
-    return eng.finish(flags)
+    return eng.finish(int(flags) | (api.FLAG_LEAF_COUNTS if counts else 0))
 
 
 def _min_halo_capacity(data, group, world, dev):
