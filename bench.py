@@ -197,6 +197,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout; keep it to ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     n = int(args.keys)

@@ -158,6 +158,7 @@ typedef struct {          /* what a rank publishes about its slab (host struct) 
   uint64_t first_key_bits, last_key_bits;  /* raw key bits (u32 zero-extended, f64 bit pattern) */
   uint64_t last_run_start;                 /* local index of the first key equal to the last key */
   uint64_t n_local;
+  uint64_t no_dups;                        /* 1 if no two LOCAL keys are equal (found when the dataset was created) */
 } rmi_shard_ends;
 int rmi_shard_ends_get(const rmi_dataset* ds, rmi_shard_ends* out);
 
@@ -167,6 +168,7 @@ typedef struct {
   uint64_t prev_key_bits, prev_F;          /* last key before this slab and its duplicate-fixed offset */
   uint64_t first_key_bits, last_key_bits, last_F;   /* global first / last key, offset of the last */
   uint64_t halo_capacity;                  /* keys of room behind the local keys in the device array */
+  uint64_t no_dups;                        /* 1 if no two keys of the WHOLE data set are equal */
   double pivot_x, pivot_y;                 /* common pivot of the top-level sums (any value, same on all ranks) */
 } rmi_shard_info;
 

@@ -647,12 +647,13 @@ template <class T> Shard<T> make_shard(const rmi_shard_build* b) {
   s.is_last = b->info.is_last;
   s.prev_key = key_from_bits<T>(b->info.prev_key_bits);
   s.prev_F = b->info.prev_F;
-  s.no_dups = 0;   // runs of equal keys may cross slab boundaries: keep the general kernels
+  s.no_dups = b->info.no_dups ? 1 : 0;   // global: no rank has equal keys and none straddle a cut
   return s;
 }
 
 template <class T> int shard_ends_typed(const rmi_dataset* ds, rmi_shard_ends* out) {
   out->n_local = ds->n;
+  out->no_dups = ds->no_dups ? 1 : 0;
   out->first_key_bits = out->last_key_bits = out->last_run_start = 0;
   if (ds->n == 0) return RMI_OK;
   const T* keys = (const T*)ds->d_keys;

@@ -47,6 +47,24 @@ k_shard_slr_partial(const T* __restrict__ keys, const Shard<T> sh, u64 g0, u64 g
   for (u64 b = (lo & ~3ull) + ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; b < hi; b += stride) {
     T k[4];
     int c = load_keys4(keys, b, sh.n_local, aligned, k);
+    if (c == 4 && b >= lo && b + 4 <= hi) {
+      const T before = b > 0 ? keys[b - 1] : sh.prev_key;
+      const bool dup = ((b > 0 || sh.has_prev) && before == k[0]) || k[1] == k[0] || k[2] == k[1] || k[3] == k[2];
+      if (!dup) {
+        // every key starts its own run: offset = global index, floor(offset * sf) by the 2^52 trick
+        const double bd = __ull2double_rn(sh.base + b);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          double x = Key<T>::as_float(k[e]);
+          double y = bd + (double)e;
+          if (use_sf) y = __dadd_rn(__dadd_rd(__dmul_rn(y, sf), 4503599627370496.0), -4503599627370496.0);
+          double dx = x - px, dy = y - py;
+          sx += dx; sy += dy; sxx = fma(dx, dx, sxx); sxy = fma(dx, dy, sxy);
+        }
+        icnt += 4;
+        continue;
+      }
+    }
     u64 F = global_run_start(keys, b, sh.base, sh.has_prev, sh.prev_key, sh.prev_F);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {

@@ -34,14 +34,14 @@ _TORCH_OF_KEY = {api.KEY_U64: torch.int64, api.KEY_U32: torch.int32, api.KEY_F64
 
 class _Ends(C.Structure):
     _fields_ = [("first_key_bits", C.c_uint64), ("last_key_bits", C.c_uint64), ("last_run_start", C.c_uint64),
-                ("n_local", C.c_uint64)]
+                ("n_local", C.c_uint64), ("no_dups", C.c_uint64)]
 
 
 class _Info(C.Structure):
     _fields_ = [("base", C.c_uint64), ("n_global", C.c_uint64), ("has_prev", C.c_int32), ("is_last", C.c_int32),
                 ("prev_key_bits", C.c_uint64), ("prev_F", C.c_uint64), ("first_key_bits", C.c_uint64),
                 ("last_key_bits", C.c_uint64), ("last_F", C.c_uint64), ("halo_capacity", C.c_uint64),
-                ("pivot_x", C.c_double), ("pivot_y", C.c_double)]
+                ("no_dups", C.c_uint64), ("pivot_x", C.c_double), ("pivot_y", C.c_double)]
 
 
 class _Buffers(C.Structure):
@@ -79,6 +79,11 @@ def plan_global_layout(ends_all: np.ndarray, key_type: int, num_leaves: int) -> 
         else:
             last_F[g] = bases[g] + lrs
         prev = g
+    # no two equal keys anywhere: every rank is duplicate-free and no cut separates two equal keys
+    no_dups = ends_all.shape[1] > 4 and all(int(ends_all[g, 4]) == 1 for g in nonempty)
+    for a, b in zip(nonempty, nonempty[1:]):
+        if int(ends_all[a, 1]) == int(ends_all[b, 0]):
+            no_dups = False
     first_bits = int(ends_all[nonempty[0], 0]) if nonempty else 0
     last_bits = int(ends_all[nonempty[-1], 1]) if nonempty else 0
     gl_last_F = last_F[nonempty[-1]] if nonempty else 0
@@ -93,7 +98,7 @@ def plan_global_layout(ends_all: np.ndarray, key_type: int, num_leaves: int) -> 
                         prev_key_bits=int(ends_all[p, 1]) if p is not None else 0,
                         prev_F=last_F[p] if p is not None else 0,
                         first_key_bits=first_bits, last_key_bits=last_bits, last_F=gl_last_F,
-                        pivot_x=px, pivot_y=py, bases=bases))
+                        no_dups=int(bool(no_dups)), pivot_x=px, pivot_y=py, bases=bases))
     return out
 
 
@@ -168,7 +173,7 @@ class CudaShardEngine:
     def ends(self):
         e = _Ends()
         api._check(self.lib.rmi_shard_ends_get(self.ds._h, C.byref(e)))
-        return int(e.first_key_bits), int(e.last_key_bits), int(e.last_run_start), int(e.n_local)
+        return int(e.first_key_bits), int(e.last_key_bits), int(e.last_run_start), int(e.n_local), int(e.no_dups)
 
     def begin(self, info: dict, spec: str, num_leaves: int, bufs: dict):
         key = (spec, num_leaves, tuple(bufs[k].data_ptr() for k in sorted(bufs)))
@@ -179,7 +184,7 @@ class CudaShardEngine:
         ci = _Info(base=info["base"], n_global=info["n_global"], has_prev=info["has_prev"], is_last=info["is_last"],
                    prev_key_bits=info["prev_key_bits"], prev_F=info["prev_F"], first_key_bits=info["first_key_bits"],
                    last_key_bits=info["last_key_bits"], last_F=info["last_F"], halo_capacity=self.data.halo_capacity,
-                   pivot_x=info["pivot_x"], pivot_y=info["pivot_y"])
+                   no_dups=info.get("no_dups", 0), pivot_x=info["pivot_x"], pivot_y=info["pivot_y"])
         cb = _Buffers(*(bufs[k].data_ptr() for k in ("sums", "S", "params", "errors", "counts", "status")))
         h = C.c_void_p()
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -257,12 +262,14 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
 
     bufs = getattr(data, "_bufs", None)
     if bufs is None or bufs["S"].numel() != N + 1 or bufs["params"].numel() != N * ppm:
+        # params | errors | counts live in ONE allocation so that a single all-reduce combines them
+        rec = torch.empty(N * (ppm + 2), dtype=torch.int64, device=dev)
         bufs = dict(sums=torch.zeros(8, dtype=torch.float64, device=dev),
                     S=torch.empty(N + 1, dtype=torch.int64, device=dev),
-                    params=torch.empty(N * ppm, dtype=torch.float64, device=dev),
-                    errors=torch.empty(N, dtype=torch.int64, device=dev),
-                    counts=torch.empty(N, dtype=torch.int64, device=dev),
-                    status=torch.zeros(1, dtype=torch.int32, device=dev))
+                    params=rec[: N * ppm].view(torch.float64),
+                    errors=rec[N * ppm: N * (ppm + 1)],
+                    counts=rec[N * (ppm + 1):],
+                    status=torch.zeros(1, dtype=torch.int32, device=dev), records=rec)
         data._bufs = bufs
     eng.begin(info, model_spec, N, bufs)
 
@@ -319,9 +326,8 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
     # 5. leaves owned by this rank, then everyone gets everything
     eng.phase(PHASE_LEAF)
     if world > 1:
-        dist.all_reduce(bufs["params"].view(torch.int64), op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(bufs["errors"], op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(bufs["counts"], op=dist.ReduceOp.SUM, group=group)
+        rec = bufs["records"]
+        dist.all_reduce(rec if counts else rec[: N * (ppm + 1)], op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(bufs["status"], op=dist.ReduceOp.MAX, group=group)
     eng.phase(PHASE_STATS)
     return eng.finish(int(flags) | (api.FLAG_LEAF_COUNTS if counts else 0))

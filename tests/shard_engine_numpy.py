@@ -55,10 +55,10 @@ class NumpyShardEngine:
     def ends(self):
         k = self.keys(self.n_local)
         if self.n_local == 0:
-            return 0, 0, 0, 0
+            return 0, 0, 0, 0, 1
         last = int(k[-1])
         lrs = int(np.searchsorted(k, k[-1], side="left"))
-        return int(k[0]), last, lrs, self.n_local
+        return int(k[0]), last, lrs, self.n_local, int(np.unique(k).size == k.size)
 
     def keys(self, count=None) -> np.ndarray:
         count = self.n_local + self.halo if count is None else count
