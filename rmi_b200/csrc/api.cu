@@ -379,11 +379,23 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
   cudaEventCreate(&ev0);
   cudaEventCreate(&ev1);
   for (auto& e : evp) cudaEventCreate(&e);
+  // fork/join resources of the long-leaf kernel
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  {
+    int lo_prio = 0, hi_prio = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi_prio) != cudaSuccess) side = nullptr;
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+  }
   int rc = RMI_OK;
   auto box = new ResultBox();
   {
     Arena A(st);
     Launch L{st, di.num_sms};
+    L.side = side; L.ev_fork = ev_fork; L.ev_join = ev_join;
+    L.d_long = A.get<u32>(LONG_LEAF_CAP + 1);
     const int ppm = leaf_params_per_model(leaf.kind);
     TopModel* d_top = A.get<TopModel>(1);
     BuildAux* d_aux = A.get<BuildAux>(1);
@@ -527,6 +539,9 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
   for (auto& e : evp) cudaEventDestroy(e);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
+  if (side) cudaStreamDestroy(side);
   cudaStreamDestroy(st);
   if (rc != RMI_OK) { delete box; return rc; }
   box->pub.build_time_ns =
@@ -617,6 +632,9 @@ struct rmi_shard_build {
   void* d_stats = nullptr;
   unsigned host_status = 0;
   std::chrono::steady_clock::time_point t_start;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  u32* d_long = nullptr;
   cudaEvent_t ev_begin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_end[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ran[6] = {false, false, false, false, false, false};
@@ -678,6 +696,7 @@ template <class T> int shard_phase_typed(rmi_shard_build* b, int phase) {
   const T* keys = (const T*)b->ds->d_keys;
   Shard<T> sh = make_shard<T>(b);
   Launch L{b->st, b->num_sms};
+  L.side = b->side; L.ev_fork = b->ev_fork; L.ev_join = b->ev_join; L.d_long = b->d_long;
   const int ppm = leaf_params_per_model(b->leaf->kind);
   if (phase >= 0 && phase < 6) { cudaEventRecord(b->ev_begin[phase], b->st); b->ran[phase] = true; }
   if (phase == RMI_PHASE_TOP_LOCAL) {   // a build object may be reused for many builds
@@ -779,6 +798,14 @@ int rmi_shard_build_create(const rmi_dataset* local, const rmi_shard_info* info,
             cudaMalloc(&b->d_scratch, shard_scratch_bytes()) == cudaSuccess &&
             cudaMalloc(&b->d_stats, stats_scratch_bytes(branch_factor)) == cudaSuccess;
   for (int q = 0; q < 6; ++q) ok = ok && cudaEventCreate(&b->ev_begin[q]) == cudaSuccess && cudaEventCreate(&b->ev_end[q]) == cudaSuccess;
+  {
+    int lo_prio = 0, hi_prio = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+    ok = ok && cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, hi_prio) == cudaSuccess &&
+         cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+         cudaMalloc((void**)&b->d_long, sizeof(u32) * (LONG_LEAF_CAP + 1)) == cudaSuccess;
+  }
   if (!ok) { rmi_shard_build_destroy(b); return fail(RMI_ERR_CUDA, "rmi_shard_build_create: device allocation failed"); }
   *out = b;
   return RMI_OK;
@@ -873,6 +900,10 @@ void rmi_shard_build_destroy(rmi_shard_build* b) {
   if (!b) return;
   cudaFree(b->d_top); cudaFree(b->d_aux); cudaFree(b->d_scratch); cudaFree(b->d_stats);
   for (int q = 0; q < 6; ++q) { if (b->ev_begin[q]) cudaEventDestroy(b->ev_begin[q]); if (b->ev_end[q]) cudaEventDestroy(b->ev_end[q]); }
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_join) cudaEventDestroy(b->ev_join);
+  if (b->side) cudaStreamDestroy(b->side);
+  cudaFree(b->d_long);
   delete b;
 }
 

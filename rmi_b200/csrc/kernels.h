@@ -65,7 +65,12 @@ template <class T> inline Shard<T> whole_array(u64 n) {
 struct Launch {
   cudaStream_t stream;
   int num_sms;
+  // optional fork/join resources for the long-leaf kernel (kernels_leaf.cu); all null = disabled
+  cudaStream_t side = nullptr;       // high-priority stream
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  u32* d_long = nullptr;             // [0] = number of long leaves found, [1 + i] = their indices
 };
+constexpr u32 LONG_LEAF_CAP = 256;   // more long leaves than this: no separate kernel (heavy skew)
 
 void count_launch();   // bumps the process-wide kernel launch counter (api.cu)
 

@@ -453,6 +453,108 @@ template <class T, bool DUPS = true> struct ItemTracker {
   }
 };
 
+// One long Welford chain served by the whole warp (the tail of a leaf that is alone in its warp).
+// A single warp issues in order, so the step's cost is its dependency chain; written naively the
+// x-mean and y-mean chains (5 dependent FP64 ops each, 8 cycles per op) end up back to back and
+// every shuffle / store sits in between (~105 cycles per step measured).  Here
+//   * even lanes run the mean_x chain and odd lanes the mean_y chain in the SAME instructions
+//     (m += RN((v - m) / n)),
+//   * 32 keys are staged per batch in shared memory (x, the duplicate-fixed y, 1/n, n), read two
+//     steps ahead of the chain,
+//   * the only store per step is the new mean; after the batch lane q forms step q's two products
+//     dx*(y - mean_y'), dx*(x - mean_x') from them, and the serial c / m2 accumulations of one
+//     batch ride along the NEXT batch's chain loop (even lanes: c, odd lanes: m2),
+// which measures ~55 cycles per step (tools/micro/fp64_lat.cu).  Values and the order of every
+// rounding are those of LeafWelford::push_rc.
+template <class T, class I, bool CHECKED, bool DUPS>
+__device__ __forceinline__ void solo_chain(const T* __restrict__ keys, I s_b, I s_e, unsigned char* wsm,
+                                           LeafWelford<CHECKED>& w, ItemTracker<T, DUPS>& it) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, h = lane & 1;
+  double2* sV = reinterpret_cast<double2*>(wsm);     // [32][2]: {x | y of the step, pending product}
+  double2* sR = sV + 64;                             // [32]: {1/n, n}
+  double* sM = reinterpret_cast<double*>(sR + 32);   // [32][2]: means after the step
+  double m = h ? w.mean_y : w.mean_x;
+  double acc = h ? w.m2 : w.c;
+  double nf0 = w.nf, idxd0 = it.idxd, pyd = it.pyd;
+  T pk = it.pk;
+  sV[lane * 2].y = 0.0;
+  sV[lane * 2 + 1].y = 0.0;
+  int pending = 0;   // products of the previous batch not yet accumulated
+  T cur = (s_b + (I)lane) < s_e ? keys[s_b + (I)lane] : T();
+  for (I base = s_b; base < s_e; base += 32) {
+    const I nb = base + 32;
+    const T nxt = (nb + (I)lane) < s_e ? keys[nb + (I)lane] : T();   // next batch in flight
+    const int cnt = (s_e - base) < (I)32 ? (int)(s_e - base) : 32;
+    double yl;
+    if (DUPS) {
+      T kp = __shfl_up_sync(FULL, cur, 1);
+      if (lane == 0) kp = pk;
+      const unsigned dmask = __ballot_sync(FULL, cur == kp);
+      const unsigned starts = ~dmask & ((2u << lane) - 1u);   // lanes <= this one that begin a run
+      yl = starts ? __dadd_rn(idxd0, (double)(31 - __clz(starts))) : pyd;
+    } else {
+      yl = __dadd_rn(idxd0, (double)lane);
+    }
+    const double xl = Key<T>::as_float(cur);
+    const double nfl = __dadd_rn(nf0, (double)(lane + 1));
+    const double mx_in = __shfl_sync(FULL, m, 0);
+    sV[lane * 2].x = xl;
+    sV[lane * 2 + 1].x = yl;
+    sR[lane] = make_double2(__drcp_rn(nfl), nfl);
+    __syncwarp();
+    auto step = [&](const double2& vt, const double2& rn, int q) {
+      const double d = __dadd_rn(vt.x, -m);
+      double dq;
+      if (CHECKED) dq = div_by_count(d, rn.y, rn.x);
+      else { const double q0 = __dmul_rn(d, rn.x); dq = __fma_rn(__fma_rn(-rn.y, q0, d), rn.x, q0); }
+      m = __dadd_rn(m, dq);
+      acc = __dadd_rn(acc, vt.y);
+      sM[q * 2 + h] = m;
+    };
+    double2 vt1 = sV[h], rn1 = sR[0], vt2 = sV[2 + h], rn2 = sR[1];
+    if (cnt == 32) {
+#pragma unroll 4
+      for (int q = 0; q < 32; ++q) {
+        const double2 vt = vt1, rn = rn1;
+        vt1 = vt2; rn1 = rn2;
+        vt2 = sV[((q + 2) & 31) * 2 + h]; rn2 = sR[(q + 2) & 31];   // two steps ahead of the store
+        step(vt, rn, q);
+      }
+    } else {
+      for (int q = 0; q < cnt; ++q) step(sV[q * 2 + h], sR[q], q);
+      for (int q = cnt; q < pending; ++q) acc = __dadd_rn(acc, sV[q * 2 + h].y);
+    }
+    __syncwarp();
+    double t1 = 0.0, t2 = 0.0;
+    if (lane < cnt) {
+      const double dx = __dadd_rn(xl, -(lane ? sM[(lane - 1) * 2] : mx_in));
+      t1 = __dmul_rn(dx, __dadd_rn(yl, -sM[lane * 2 + 1]));
+      t2 = __dmul_rn(dx, __dadd_rn(xl, -sM[lane * 2]));
+    }
+    __syncwarp();
+    sV[lane * 2].y = t1;
+    sV[lane * 2 + 1].y = t2;
+    pending = cnt;
+    nf0 = __dadd_rn(nf0, (double)cnt);
+    idxd0 = __dadd_rn(idxd0, (double)cnt);
+    pyd = __shfl_sync(FULL, yl, cnt - 1);
+    pk = __shfl_sync(FULL, cur, cnt - 1);
+    cur = nxt;
+  }
+  __syncwarp();
+  for (int q = 0; q < pending; ++q) acc = __dadd_rn(acc, sV[q * 2 + h].y);
+  w.mean_x = __shfl_sync(FULL, m, 0);
+  w.mean_y = __shfl_sync(FULL, m, 1);
+  w.c = __shfl_sync(FULL, acc, 0);
+  w.m2 = __shfl_sync(FULL, acc, 1);
+  w.nf = nf0;
+  it.idxd = idxd0;
+  it.pyd = pyd;
+  it.pk = pk;
+  __syncwarp();
+}
+
 // train_model(layer2, vector) for every leaf model type, as warp-synchronous stream passes.
 // f receives Model::params().  Every lane of the warp must call this (with vs == ve if it has
 // no leaf or an empty vector).
@@ -517,29 +619,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
       it.pk = __shfl_sync(FULL, it.pk, solo_lane); it.pyd = __shfl_sync(FULL, it.pyd, solo_lane);
       it.idxd = __shfl_sync(FULL, it.idxd, solo_lane);
       const I s_b = __shfl_sync(FULL, solo_at, solo_lane), s_e = __shfl_sync(FULL, r.ve, solo_lane);
-      // 32 keys per coalesced load (next 32 in flight); each lane prepares ITS key's x, duplicate
-      // flag and the reciprocal of ITS step's count, then all lanes replay the 32 steps from
-      // shuffles: the chain runs at FP64 dependency latency
-      T cur = (s_b + (I)lane) < s_e ? keys[s_b + (I)lane] : T();
-      for (I base = s_b; base < s_e; base += 32) {
-        const I nb = base + 32;
-        const T nxt = (nb + (I)lane) < s_e ? keys[nb + (I)lane] : T();
-        const int cnt = (s_e - base) < (I)32 ? (int)(s_e - base) : 32;
-        T kp = __shfl_up_sync(FULL, cur, 1);
-        if (lane == 0) kp = it.pk;
-        const unsigned dmask = __ballot_sync(FULL, cur == kp);
-        const double xl = Key<T>::as_float(cur);
-        const double rcl = __drcp_rn(__dadd_rn(w.nf, (double)(lane + 1)));
-        for (int q = 0; q < cnt; ++q) {
-          const double xq = __shfl_sync(FULL, xl, q), rq = __shfl_sync(FULL, rcl, q);
-          const double yd = ((dmask >> q) & 1u) ? it.pyd : it.idxd;
-          it.pyd = yd;
-          it.idxd = __dadd_rn(it.idxd, 1.0);
-          w.push_rc(xq, yd, rq);
-        }
-        it.pk = __shfl_sync(FULL, cur, cnt - 1);
-        cur = nxt;
-      }
+      solo_chain<T, I, CHECKED, DUPS>(keys, s_b, s_e, wsm, w, it);
       w.ra = w.ra_end;   // the table cursor was not advanced in solo mode: later steps compute 1/n directly
       if (lane == solo_lane) finalize();
     }
@@ -710,6 +790,22 @@ __device__ __forceinline__ I leaf_predict_clamped(const double* f, double x, I n
   return v < n ? v : n;
 }
 
+constexpr u64 LONG_LEAF_KEYS = 2048;   // leaves longer than this go to the long-leaf kernel (linear leaves)
+
+// Owned leaves longer than LONG_LEAF_KEYS -> list (count in list[0], capped at LONG_LEAF_CAP + 1).
+template <class T>
+__global__ void __launch_bounds__(BOUNDS_THREADS)
+k_find_long(const Shard<T> sh, u64 N, const u64* __restrict__ S, u32* __restrict__ list) {
+  u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  u64 lo = S[j], hi = S[j + 1];
+  bool owned = (lo >= sh.base && lo < sh.base + sh.n_local);
+  if (owned && hi > lo && hi - lo > LONG_LEAF_KEYS) {
+    u32 slot = atomicAdd(&list[0], 1u);
+    if (slot < LONG_LEAF_CAP) list[1 + slot] = (u32)j;
+  }
+}
+
 constexpr size_t leaf_smem_bytes() {
   return (size_t)RCP_TABLE * sizeof(double) + (size_t)(LEAF_THREADS / 32) * WARP_STREAM_BYTES;
 }
@@ -717,7 +813,8 @@ constexpr size_t leaf_smem_bytes() {
 template <class T, class I, int LEAF, bool DUPS>
 __global__ void __launch_bounds__(LEAF_THREADS)
 k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restrict__ S, BuildAux* aux,
-       double* __restrict__ params, u64* __restrict__ errors, u64* __restrict__ counts) {
+       double* __restrict__ params, u64* __restrict__ errors, u64* __restrict__ counts,
+       const u32* __restrict__ long_list, int long_mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_rcp = reinterpret_cast<double*>(smem_raw);
   unsigned char* wsm = smem_raw + (size_t)RCP_TABLE * sizeof(double) + (size_t)(threadIdx.x >> 5) * WARP_STREAM_BYTES;
@@ -726,8 +823,15 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   // Leaf groups are handed out from both ends of the leaf range: with a regression top model
   // the first and the last leaf collect every key the model places below 0 / above N-1 and are
   // by far the longest serial chains, so they must start first, not last.
+  // long_mode 1 (one warp per block): block b builds the b-th leaf of the long-leaf list alone —
+  // its lane 0 owns the leaf, the other lanes only help (solo fit, cooperative forward pass).
+  // long_mode 0: the ordinary kernel, which leaves those leaves to the long-leaf kernel.
+  const u32 n_long = long_list ? long_list[0] : 0u;
+  const bool long_active = LEAF == M_LINEAR && long_list != nullptr && n_long > 0 && n_long <= LONG_LEAF_CAP;
+  if (long_mode == 1 && (!long_active || blockIdx.x >= n_long)) return;
   const u64 group = (blockIdx.x & 1u) ? (u64)gridDim.x - 1 - (blockIdx.x >> 1) : (u64)(blockIdx.x >> 1);
-  const u64 j = group * blockDim.x + threadIdx.x;
+  const u64 j = long_mode == 1 ? (threadIdx.x == 0 ? (u64)long_list[1 + blockIdx.x] : N)
+                               : group * blockDim.x + threadIdx.x;
   constexpr int PPM = leaf_params_per_model(LEAF);
   constexpr bool NANCHECK = Key<T>::is_float || LEAF == M_LOGLINEAR || LEAF == M_NORMAL || LEAF == M_LOGNORMAL;
   const u64 n = sh.n_global;
@@ -740,7 +844,8 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   if (g_hi < g_lo) { bad |= ST_NOT_SORTED; g_hi = g_lo; }   // cannot happen on sorted keys
   // owner of leaf j: the rank whose slab holds index S[j]; S[j] == n (trailing empty leaves)
   // belongs to the last rank
-  const bool live = j < N && ((g_lo >= sh.base && g_lo < sh.base + sh.n_local) || (g_lo >= n && sh.is_last));
+  bool live = j < N && ((g_lo >= sh.base && g_lo < sh.base + sh.n_local) || (g_lo >= n && sh.is_last));
+  if (long_mode == 0 && long_active && live && (g_hi - g_lo) > LONG_LEAF_KEYS) live = false;   // built by the long-leaf kernel
 
   // which half does leaf j belong to (two_layer.rs:147-175), in global indices
   u64 half_lo, half_hi, first_leaf;
@@ -1049,9 +1154,26 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
                       double* d_params, u64* d_errors, u64* d_counts) {
   u64 blocks = (N + LEAF_THREADS - 1) / LEAF_THREADS;
   constexpr size_t smem = leaf_smem_bytes();
-  cudaFuncSetAttribute(k_leaf<T, I, LEAF, DUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_leaf<T, I, LEAF, DUPS><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts);
+  cudaFuncSetAttribute(k_leaf<T, I, LEAF, DUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  const bool fork = LEAF == M_LINEAR && L.side && L.ev_fork && L.ev_join && L.d_long && N < 0xffffffffull;
+  if (fork) {
+    // Long leaves (the two end leaves of a regression top model collect every key it places
+    // outside [0, N)) are single serial chains: they get their own one-warp blocks on a
+    // high-priority stream, with enough shared memory reserved that few other blocks share
+    // their SM, and run concurrently with the bulk kernel.
+    cudaMemsetAsync(L.d_long, 0, sizeof(u32), L.stream);
+    k_find_long<T><<<(unsigned)((N + BOUNDS_THREADS - 1) / BOUNDS_THREADS), BOUNDS_THREADS, 0, L.stream>>>(sh, N, d_S, L.d_long);
+    count_launch();
+    cudaEventRecord(L.ev_fork, L.stream);
+    cudaStreamWaitEvent(L.side, L.ev_fork, 0);
+    k_leaf<T, I, LEAF, DUPS><<<LONG_LEAF_CAP, 32, 160 * 1024, L.side>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts, L.d_long, 1);
+    count_launch();
+    cudaEventRecord(L.ev_join, L.side);
+  }
+  k_leaf<T, I, LEAF, DUPS><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts,
+                                                                              fork ? L.d_long : nullptr, 0);
   count_launch();
+  if (fork) cudaStreamWaitEvent(L.stream, L.ev_join, 0);
 }
 template <class T, int LEAF>
 void launch_leaf(const Launch& L, const T* keys, const Shard<T>& sh, u64 N, const u64* d_S, BuildAux* d_aux,

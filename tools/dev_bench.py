@@ -4,23 +4,27 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import rmi_b200
 
-n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 200_000_000
-torch.manual_seed(42)
+pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+opt = {a.split("=")[0]: (a.split("=") + ["1"])[1] for a in sys.argv[1:] if a.startswith("--")}
+n = int(float(pos[0])) if pos else 200_000_000
+torch.manual_seed(int(opt.get("--seed", 42)))
 dev = torch.device("cuda:0")
-k = torch.randint(0, 2**63 - 1, (n,), dtype=torch.int64, device=dev)
+k = torch.randint(0, (2**63 - 1) // int(opt.get("--div", 1)), (n,), dtype=torch.int64, device=dev)
 k, _ = torch.sort(k)
 torch.cuda.synchronize()
 ds = rmi_b200.RMITrainingData.from_device(k.data_ptr(), n, rmi_b200.KEY_U64, 0, keep_alive=k)
 configs = [("linear,linear", 1 << 20, 0), ("radix,linear", 1 << 19, 0), ("cubic,linear", 1 << 18, 0),
            ("linear,linear", 1 << 20, rmi_b200.FLAG_STATS_ONLY), ("linear_spline,cubic", 1 << 18, 0),
            ("radix18,linear", 1 << 16, 0), ("bradix,linear", 1 << 18, 0), ("histogram,linear", 1 << 16, 0)]
-if "--quick" in sys.argv:
+if "--quick" in opt:
     configs = configs[:3]
-if "--exact" in sys.argv:
+if "--one" in opt:
+    configs = configs[:1]
+if "--exact" in opt:
     configs.append(("linear,linear", 1 << 20, rmi_b200.FLAG_TOP_FIT_EXACT))
 for spec, bf, flags in configs:
     try:
-        for it in range(3):
+        for it in range(int(opt.get("--iters", 3))):
             t0 = time.perf_counter()
             r = rmi_b200.train(ds, spec, bf, flags)
             t1 = time.perf_counter()
