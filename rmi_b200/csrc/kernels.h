@@ -70,7 +70,7 @@ struct Launch {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   u32* d_long = nullptr;             // [0] = number of long leaves found, [1 + i] = their indices
 };
-constexpr u32 LONG_LEAF_CAP = 256;   // more long leaves than this: no separate kernel (heavy skew)
+constexpr u32 LONG_LEAF_CAP = 16;    // more long leaves than this: no separate kernel (skewed data; they stay in the bulk kernel)
 
 void count_launch();   // bumps the process-wide kernel launch counter (api.cu)
 

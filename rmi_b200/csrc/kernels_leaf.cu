@@ -791,6 +791,7 @@ __device__ __forceinline__ I leaf_predict_clamped(const double* f, double x, I n
 }
 
 constexpr u64 LONG_LEAF_KEYS = 2048;   // leaves longer than this go to the long-leaf kernel (linear leaves)
+constexpr int LONG_LEAF_SMEM = 227 * 1024;   // its blocks ask for a whole SM's shared memory: nothing else is resident beside the chain
 
 // Owned leaves longer than LONG_LEAF_KEYS -> list (count in list[0], capped at LONG_LEAF_CAP + 1).
 template <class T>
@@ -964,47 +965,73 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
       const bool c_have_prev = __shfl_sync(FULL, (int)have_prev, src) != 0;
       I carry_F = (I)(c_lo + sh.base);
       I w_err = 0, w_run = 0;
-      for (u64 b0 = c_lo; b0 < c_hi; b0 += 32) {
-        const u64 i = b0 + lane;
-        const bool valid = i < c_hi;
-        const T k = valid ? keys[i] : T();
-        T kp = __shfl_up_sync(FULL, k, 1);
-        if (lane == 0) kp = carry_k;
-        // a run starts where the key differs from its predecessor (the leaf's first key always
-        // differs from the key before the leaf; at global index 0 there is no predecessor)
-        const bool starts = valid && (k != kp || (i == c_lo && !c_have_prev));
-        I F = starts ? (I)(i + sh.base) : (I)0;
+      // 8 coalesced batches of 32 keys in flight per outer step (one global-memory latency per
+      // 256 keys instead of per 32)
+      constexpr int DEPTH = 8;
+      for (u64 b0 = c_lo; b0 < c_hi; b0 += 32 * DEPTH) {
+        T kk[DEPTH];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          I t = __shfl_up_sync(FULL, F, o);
-          if (lane >= o && t > F) F = t;
+        for (int u = 0; u < DEPTH; ++u) {
+          const u64 iu = b0 + (u64)(u * 32 + lane);
+          kk[u] = iu < c_hi ? keys[iu] : T();
         }
-        if (carry_F > F) F = carry_F;
-        if (valid) {
-          I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, Key<T>::as_float(k), nI);
-          I e = pred > F ? pred - F : F - pred;
-          w_err = e > w_err ? e : w_err;
+        const u64 inext = b0 + 32 * DEPTH;
+        const T k_after = (DUPS && inext < c_hi) ? keys[inext] : T();   // first key of the next outer step
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) {
+          const u64 s0 = b0 + (u64)(u * 32);
+          if (s0 >= c_hi) break;   // warp-uniform
+          const u64 i = s0 + lane;
+          const bool valid = i < c_hi;
+          const T k = kk[u];
+          if (!DUPS) {
+            if (valid) {
+              const I Fi = (I)(i + sh.base);
+              I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, Key<T>::as_float(k), nI);
+              I e = pred > Fi ? pred - Fi : Fi - pred;
+              w_err = e > w_err ? e : w_err;
+            }
+            continue;
+          }
+          T kp = __shfl_up_sync(FULL, k, 1);
+          if (lane == 0) kp = carry_k;
+          // a run starts where the key differs from its predecessor (the leaf's first key always
+          // differs from the key before the leaf; at global index 0 there is no predecessor)
+          const bool starts = valid && (k != kp || (i == c_lo && !c_have_prev));
+          I F = starts ? (I)(i + sh.base) : (I)0;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            I t = __shfl_up_sync(FULL, F, o);
+            if (lane >= o && t > F) F = t;
+          }
+          if (carry_F > F) F = carry_F;
+          if (valid) {
+            I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, Key<T>::as_float(k), nI);
+            I e = pred > F ? pred - F : F - pred;
+            w_err = e > w_err ? e : w_err;
+          }
+          // a run ends at i when the next key differs or the leaf ends; its length counts unless
+          // it is the data set's final run (lower_bound_correction.rs:108-119)
+          T kn = __shfl_down_sync(FULL, k, 1);
+          const T k_next_batch = u + 1 < DEPTH ? __shfl_sync(FULL, kk[u + 1 < DEPTH ? u + 1 : u], 0) : k_after;
+          if (lane == 31) kn = k_next_batch;
+          const bool last_of_leaf = valid && i + 1 == c_hi;
+          const bool ends = valid && (last_of_leaf || kn != k);
+          if (ends && !(last_of_leaf && c_ghi >= n)) {
+            I len = (I)(i + sh.base) - F + 1;
+            w_run = len > w_run ? len : w_run;
+          }
+          const int lastv = (c_hi - s0) < 32 ? (int)(c_hi - s0) - 1 : 31;
+          carry_F = __shfl_sync(FULL, F, lastv);
+          carry_k = __shfl_sync(FULL, k, lastv);
         }
-        // a run ends at i when the next key differs or the leaf ends; its length counts unless
-        // it is the data set's final run (lower_bound_correction.rs:108-119)
-        T kn = __shfl_down_sync(FULL, k, 1);
-        if (lane == 31 && i + 1 < c_hi) kn = keys[i + 1];
-        const bool last_of_leaf = valid && i + 1 == c_hi;
-        const bool ends = valid && (last_of_leaf || kn != k);
-        if (ends && !(last_of_leaf && c_ghi >= n)) {
-          I len = (I)(i + sh.base) - F + 1;
-          w_run = len > w_run ? len : w_run;
-        }
-        const int lastv = (c_hi - b0) < 32 ? (int)(c_hi - b0) - 1 : 31;
-        carry_F = __shfl_sync(FULL, F, lastv);
-        carry_k = __shfl_sync(FULL, k, lastv);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         I t = __shfl_xor_sync(FULL, w_err, o); w_err = t > w_err ? t : w_err;
         t = __shfl_xor_sync(FULL, w_run, o); w_run = t > w_run ? t : w_run;
       }
-      if (lane == src) { max_err = w_err; run_max = w_run; }
+      if (lane == src) { max_err = w_err; if (DUPS) run_max = w_run; }
     }
   }
   if (bad) set_status(aux, bad);
@@ -1154,19 +1181,19 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
                       double* d_params, u64* d_errors, u64* d_counts) {
   u64 blocks = (N + LEAF_THREADS - 1) / LEAF_THREADS;
   constexpr size_t smem = leaf_smem_bytes();
-  cudaFuncSetAttribute(k_leaf<T, I, LEAF, DUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_leaf<T, I, LEAF, DUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LONG_LEAF_SMEM);
   const bool fork = LEAF == M_LINEAR && L.side && L.ev_fork && L.ev_join && L.d_long && N < 0xffffffffull;
   if (fork) {
     // Long leaves (the two end leaves of a regression top model collect every key it places
     // outside [0, N)) are single serial chains: they get their own one-warp blocks on a
-    // high-priority stream, with enough shared memory reserved that few other blocks share
-    // their SM, and run concurrently with the bulk kernel.
+    // high-priority stream, each with an SM to itself (a serial FP64 chain slows down with
+    // every co-resident warp that shares its issue port), concurrently with the bulk kernel.
     cudaMemsetAsync(L.d_long, 0, sizeof(u32), L.stream);
     k_find_long<T><<<(unsigned)((N + BOUNDS_THREADS - 1) / BOUNDS_THREADS), BOUNDS_THREADS, 0, L.stream>>>(sh, N, d_S, L.d_long);
     count_launch();
     cudaEventRecord(L.ev_fork, L.stream);
     cudaStreamWaitEvent(L.side, L.ev_fork, 0);
-    k_leaf<T, I, LEAF, DUPS><<<LONG_LEAF_CAP, 32, 160 * 1024, L.side>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts, L.d_long, 1);
+    k_leaf<T, I, LEAF, DUPS><<<LONG_LEAF_CAP, 32, LONG_LEAF_SMEM, L.side>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts, L.d_long, 1);
     count_launch();
     cudaEventRecord(L.ev_join, L.side);
   }
