@@ -73,7 +73,9 @@ typedef struct rmi_dataset rmi_dataset;
 int rmi_dataset_create(const void* host_keys, uint64_t n, rmi_key_type key_type, int device,
                        rmi_dataset** out);
 /* Borrow keys that already live in device memory on `device` (no copy, caller keeps ownership
- * and must keep them alive and unmodified while the dataset exists). */
+ * and must keep them alive and unmodified while the dataset exists).  device_keys must be
+ * 16-byte aligned and readable up to the next 16-byte boundary after the last key (always the
+ * case for a buffer that starts a CUDA allocation: those are at least 256-byte granular). */
 int rmi_dataset_wrap_device(const void* device_keys, uint64_t n, rmi_key_type key_type, int device,
                             rmi_dataset** out);
 /* Read a reference-format key file (u64 LE count + packed keys, README.md:26-31; key type from

@@ -228,7 +228,7 @@ int rmi_dataset_create(const void* host_keys, uint64_t n, rmi_key_type key_type,
   cudaStream_t st = nullptr;
   unsigned* d_flag = nullptr;
   cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMallocAsync(&ds->d_keys, bytes, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&ds->d_keys, (bytes + 15) & ~(size_t)15, st);
   if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_flag, sizeof(unsigned), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, sizeof(unsigned), st);
   unsigned h_flag = 0;
@@ -306,7 +306,7 @@ int rmi_dataset_load_file(const char* path, int key_type_or_negative, int device
     fclose(f);
   };
   if (bytes) {
-    if (cudaMalloc(&ds->d_keys, bytes) != cudaSuccess || cudaStreamCreate(&st) != cudaSuccess ||
+    if (cudaMalloc(&ds->d_keys, (bytes + 15) & ~(size_t)15) != cudaSuccess || cudaStreamCreate(&st) != cudaSuccess ||
         cudaMallocHost(&stage[0], CHUNK) != cudaSuccess || cudaMallocHost(&stage[1], CHUNK) != cudaSuccess ||
         cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess) {
       rc = fail(RMI_ERR_CUDA, "rmi_dataset_load_file: allocation failed");

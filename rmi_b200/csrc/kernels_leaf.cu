@@ -24,6 +24,7 @@
 // bit-identical; parallelism comes from the N independent leaves.
 #include "device_util.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace rmi {
 
@@ -197,8 +198,7 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
   rowg[lane] = (u32)((u64)a / KPP);
   rownp[lane] = (u32)(((u64)rlen + KPP - 1) / KPP);
   __syncwarp();
-  const u32 g_full = (u32)(n_keys / KPP);                       // pieces that lie fully inside the array
-  const int tail_bytes = (int)((n_keys % KPP) * sizeof(T));    // bytes of the partial piece at the array end
+  (void)n_keys;
   const int prow = lane >> 3, piece = lane & 7;
   u32 g0[8], np[8];   // this lane's 8 (row, piece) streams: first piece index, pieces available
 #pragma unroll
@@ -211,21 +211,19 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
   const unsigned char* kb = reinterpret_cast<const unsigned char*>(keys);
   const unsigned st0 = (unsigned)__cvta_generic_to_shared(wsm) + (unsigned)(prow * ROW_BYTES + piece * 16);
   const u32 nchunks = (u32)(((u64)maxlen + SW - 1) / SW);
+  // One predicated 16-byte copy per (row, piece) stream: address = chunk base + piece index * 16.
+  // Pieces are whole 16-byte units; the one that holds the array's last key may extend past it
+  // (the buffer is readable up to the next 16-byte boundary, include/rmi_b200.h), and nothing
+  // past a lane's range is ever consumed.
   auto issue = [&](u32 c) {
     const unsigned st = st0 + (c % SSTAGES) * (32 * ROW_BYTES);
+    const unsigned char* cb = kb + (u64)c * 128u;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      if (c < np[q]) {
-        const u32 g = g0[q] + 8u * c;
-        u64 src;
-        asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(src) : "r"(g), "l"(kb));
-        if (g < g_full) {   // the only partial piece is the one that straddles the end of the key array
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)), "l"(src) : "memory");
-        } else {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)),
-                       "l"(src), "r"(tail_bytes) : "memory");
-        }
-      }
+      u64 src;
+      asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(src) : "r"(g0[q]), "l"(cb));
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n"
+                   ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)), "l"(src), "r"(c), "r"(np[q]) : "memory");
     }
     cp_async_commit();
   };
@@ -408,6 +406,41 @@ template <bool CHECKED> struct LeafWelford {
     ra += (unsigned)sizeof(double);
     asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
     push_rc(x, y, rc);
+  }
+  // Items whose y are CONSECUTIVE integers y0, y0+1, ... (a data set without equal keys): the
+  // reference's mean_y recurrence is then exact at every step — dy = k/2, dy/k = 0.5, mean_y =
+  // y0 + (k-1)/2, y - mean_y' = (k-1)/2, all representable — so the y chain collapses to one
+  // addition and the step needs 13 FP64 operations instead of 19, with bit-identical results.
+  // hy = (items pushed) / 2; mean_y is materialised by nd_finish() before any general step.
+  double hy;
+  __device__ __forceinline__ void nd_init() { hy = 0.0; }
+  __device__ __forceinline__ void push_rc_nd(double x, double rc) {
+    nf = __dadd_rn(nf, 1.0);
+    double dx = __dadd_rn(x, -mean_x);
+    mean_x = __dadd_rn(mean_x, dv(dx, rc));
+    c = __dadd_rn(c, __dmul_rn(dx, hy));
+    hy = __dadd_rn(hy, 0.5);
+    double dx2 = __dadd_rn(x, -mean_x);
+    m2 = __dadd_rn(m2, __dmul_rn(dx, dx2));
+  }
+  __device__ __forceinline__ void push_nd(double x) {
+    double rc;
+    if (ra < ra_end) {
+      ra += (unsigned)sizeof(double);
+      asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
+    } else {
+      rc = rcp_beyond_table(__dadd_rn(nf, 1.0));
+    }
+    push_rc_nd(x, rc);
+  }
+  __device__ __forceinline__ void push_t_nd(double x) {
+    double rc;
+    ra += (unsigned)sizeof(double);
+    asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
+    push_rc_nd(x, rc);
+  }
+  __device__ __forceinline__ void nd_finish(double y0) {
+    mean_y = nf > 0.0 ? __dadd_rn(y0, __dadd_rn(hy, -0.5)) : 0.0;
   }
   // the same step with the count's reciprocal supplied by the caller (solo mode)
   __device__ __forceinline__ void push_rc(double x, double y, double rc) {
@@ -594,18 +627,41 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     // Warps in which no vector reaches the end of the reciprocal table (almost all of them)
     // take the branch-free step.
     const bool all_short = !__any_sync(0xffffffffu, (u64)L + 2 >= (u64)RCP_TABLE);
+    constexpr bool ND = LEAF == M_LINEAR && !DUPS;   // consecutive offsets: LeafWelford::push_rc_nd
+    // after an ND pass: the state the general steps (solo chain, the repeated final item) expect
+    auto nd_materialise = [&](I upto) {   // `upto` = local index one past the last item consumed
+      w.nd_finish(f0d);
+      it.idxd = __dadd_rn(f0d, w.nf);
+      it.pyd = __dadd_rn(it.idxd, -1.0);
+      it.pk = upto > r.vs ? keys[upto - 1] : kfirst;
+    };
+    if (ND) w.nd_init();
     if (LEAF == M_LINEAR && all_short) {
-      auto item_t = [&](T k, I) { w.push_t(Key<T>::as_float(k), it.next(k)); };
-      if (r.p_remote) item_t(r.pkey, (I)0);
-      stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item_t);
+      if (ND) {
+        auto item_nd = [&](T k, I) { w.push_t_nd(Key<T>::as_float(k)); };
+        if (r.p_remote) item_nd(r.pkey, (I)0);
+        stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item_nd);
+        nd_materialise(r.ve);
+      } else {
+        auto item_t = [&](T k, I) { w.push_t(Key<T>::as_float(k), it.next(k)); };
+        if (r.p_remote) item_t(r.pkey, (I)0);
+        stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item_t);
+      }
       finalize();
       return;
     }
-    if (r.p_remote) item(r.pkey, (I)0);
     int solo_lane;
     I solo_at;
-    if (LEAF == M_LINEAR) stream_pass<T, I, decltype(item)&, true>(keys, n_keys, wsm, r.vs, r.ve, item, &solo_lane, &solo_at);
-    else { stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item); solo_lane = -1; solo_at = 0; }
+    if (ND) {
+      auto item_nd = [&](T k, I) { w.push_nd(Key<T>::as_float(k)); };
+      if (r.p_remote) item_nd(r.pkey, (I)0);
+      stream_pass<T, I, decltype(item_nd)&, true>(keys, n_keys, wsm, r.vs, r.ve, item_nd, &solo_lane, &solo_at);
+      nd_materialise((solo_lane == (int)(threadIdx.x & 31)) ? solo_at : r.ve);
+    } else {
+      if (r.p_remote) item(r.pkey, (I)0);
+      if (LEAF == M_LINEAR) stream_pass<T, I, decltype(item)&, true>(keys, n_keys, wsm, r.vs, r.ve, item, &solo_lane, &solo_at);
+      else { stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item); solo_lane = -1; solo_at = 0; }
+    }
     if (solo_lane < 0) {
       finalize();
     } else {
@@ -1180,7 +1236,8 @@ template <class T, class I, int LEAF, bool DUPS>
 void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N, const u64* d_S, BuildAux* d_aux,
                       double* d_params, u64* d_errors, u64* d_counts) {
   u64 blocks = (N + LEAF_THREADS - 1) / LEAF_THREADS;
-  constexpr size_t smem = leaf_smem_bytes();
+  static const size_t pad = [] { const char* e = getenv("RMI_DEV_LEAF_SMEM_PAD"); return e ? (size_t)atol(e) : (size_t)0; }();
+  const size_t smem = leaf_smem_bytes() + pad;   // dev knob: extra shared memory = fewer resident blocks
   cudaFuncSetAttribute(k_leaf<T, I, LEAF, DUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LONG_LEAF_SMEM);
   const bool fork = LEAF == M_LINEAR && L.side && L.ev_fork && L.ev_join && L.d_long && N < 0xffffffffull;
   if (fork) {
