@@ -145,7 +145,8 @@ void rmi_result_free(rmi_result* r);
  * are global, so a build is a sequence of local phases separated by three small collectives
  * that the HOST issues on the buffers below (rmi_b200/sharded.py does it with
  * torch.distributed over NCCL):
- *     RMI_PHASE_TOP_LOCAL   -> all-reduce SUM  of buffers.sums   (8 doubles)
+ *     RMI_PHASE_TOP_LOCAL   -> first top-model collective  (see rmi_shard_top_rounds)
+ *    [RMI_PHASE_TOP_MID     -> second top-model collective; two-round tops only]
  *     RMI_PHASE_TOP_FINISH, RMI_PHASE_BOUNDS
  *                           -> all-reduce MIN  of buffers.S      ((N+1) u64)
  *     RMI_PHASE_SPLIT       -> halo: copy the keys of this rank's last leaf that live on the
@@ -155,7 +156,9 @@ void rmi_result_free(rmi_result* r);
  *     RMI_PHASE_STATS, rmi_shard_finish()
  * All phases are enqueued on the caller's CUDA stream and do not synchronise.  The result is
  * identical on every rank and equal to a single-GPU build of the concatenated array (same
- * tolerance rules).  Offered for the top models linear, robust_linear, linear_spline, radix. */
+ * tolerance rules).  Offered for the top models linear, robust_linear, linear_spline, cubic,
+ * normal, lognormal, radix (the table / histogram tops need a table-sized exchange and are
+ * single-GPU only). */
 typedef struct {          /* what a rank publishes about its slab (host struct) */
   uint64_t first_key_bits, last_key_bits;  /* raw key bits (u32 zero-extended, f64 bit pattern) */
   uint64_t last_run_start;                 /* local index of the first key equal to the last key */
@@ -175,7 +178,7 @@ typedef struct {
 } rmi_shard_info;
 
 typedef struct {          /* device buffers owned by the caller (the collectives run on them) */
-  void* sums;             /* 8 x f64 */
+  void* sums;             /* 16 x 8 bytes: [0,8) f64 sums (SUM rounds), [8,16) i64 slots (MIN round) */
   void* S;                /* (N+1) x u64 */
   void* params;           /* N x params_per_model x f64 */
   void* errors;           /* N x u64 */
@@ -184,7 +187,18 @@ typedef struct {          /* device buffers owned by the caller (the collectives
 } rmi_shard_buffers;
 
 enum { RMI_PHASE_TOP_LOCAL = 0, RMI_PHASE_TOP_FINISH = 1, RMI_PHASE_BOUNDS = 2, RMI_PHASE_SPLIT = 3,
-       RMI_PHASE_LEAF = 4, RMI_PHASE_STATS = 5 };
+       RMI_PHASE_LEAF = 4, RMI_PHASE_STATS = 5, RMI_PHASE_TOP_MID = 6, RMI_NUM_PHASES = 7 };
+
+/* Which collectives the top-model fit of a range-partitioned build needs (the host issues them):
+ *   -1  this top model is not offered for range-partitioned builds
+ *    0  none:  TOP_LOCAL, TOP_FINISH                                   (linear_spline, radix:
+ *       O(1) functions of the global end keys, cubic_spline.rs / radix.rs need no pass)
+ *    1  TOP_LOCAL -> all-reduce SUM of sums[0,8) as f64 -> TOP_FINISH  (linear, robust_linear)
+ *    2  TOP_LOCAL -> SUM f64 sums[0,8) -> TOP_MID -> SUM f64 sums[0,8) -> TOP_FINISH
+ *                                                                       (normal, lognormal)
+ *    3  TOP_LOCAL -> all-reduce MIN of sums[8,12) as SIGNED 64-bit integers -> TOP_MID
+ *                 -> SUM f64 sums[0,8) -> TOP_FINISH                    (cubic) */
+int rmi_shard_top_rounds(const char* top_model_name);
 
 typedef struct rmi_shard_build rmi_shard_build;
 int rmi_shard_build_create(const rmi_dataset* local, const rmi_shard_info* info, const char* model_spec,

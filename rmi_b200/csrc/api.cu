@@ -635,9 +635,9 @@ struct rmi_shard_build {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   u32* d_long = nullptr;
-  cudaEvent_t ev_begin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_end[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool ran[6] = {false, false, false, false, false, false};
+  cudaEvent_t ev_begin[RMI_NUM_PHASES] = {};
+  cudaEvent_t ev_end[RMI_NUM_PHASES] = {};
+  bool ran[RMI_NUM_PHASES] = {};
 };
 
 namespace {
@@ -698,12 +698,13 @@ template <class T> int shard_phase_typed(rmi_shard_build* b, int phase) {
   Launch L{b->st, b->num_sms};
   L.side = b->side; L.ev_fork = b->ev_fork; L.ev_join = b->ev_join; L.d_long = b->d_long;
   const int ppm = leaf_params_per_model(b->leaf->kind);
-  if (phase >= 0 && phase < 6) { cudaEventRecord(b->ev_begin[phase], b->st); b->ran[phase] = true; }
+  if (phase >= 0 && phase < RMI_NUM_PHASES) { cudaEventRecord(b->ev_begin[phase], b->st); b->ran[phase] = true; }
   if (phase == RMI_PHASE_TOP_LOCAL) {   // a build object may be reused for many builds
     b->t_start = std::chrono::steady_clock::now();
     b->host_status = 0;
-    for (int q = 1; q < 6; ++q) b->ran[q] = false;
+    for (int q = 1; q < RMI_NUM_PHASES; ++q) b->ran[q] = false;
   }
+  const T first_key = key_from_bits<T>(b->info.first_key_bits), last_key = key_from_bits<T>(b->info.last_key_bits);
   switch (phase) {
     case RMI_PHASE_TOP_LOCAL:
       cudaMemsetAsync(b->d_aux, 0, sizeof(BuildAux), b->st);
@@ -713,16 +714,18 @@ template <class T> int shard_phase_typed(rmi_shard_build* b, int phase) {
         h.kind = b->top->kind; h.high = 1;
         cudaMemcpyAsync(b->d_top, &h, sizeof(h), cudaMemcpyHostToDevice, b->st);
       }
-      b->host_status |= shard_top_local<T>(L, keys, sh, b->top->kind, b->N, b->info.pivot_x, b->info.pivot_y, b->d_scratch,
-                                           (double*)b->buf.sums);
+      b->host_status |= shard_top_local<T>(L, keys, sh, b->top->kind, b->N, b->info.pivot_x, b->info.pivot_y, first_key,
+                                           last_key, b->d_scratch, (double*)b->buf.sums);
+      break;
+    case RMI_PHASE_TOP_MID:
+      shard_top_mid<T>(L, keys, sh, b->top->kind, b->N, first_key, last_key, b->d_scratch, (double*)b->buf.sums, b->d_aux);
       break;
     case RMI_PHASE_TOP_FINISH:
       shard_top_finish<T>(L, sh, b->top->kind, b->N, b->info.pivot_x, b->info.pivot_y, (const double*)b->buf.sums,
-                          key_from_bits<T>(b->info.first_key_bits), key_from_bits<T>(b->info.last_key_bits),
-                          b->info.last_F, b->d_top, b->d_aux);
+                          first_key, last_key, b->info.last_F, b->d_scratch, b->d_top, b->d_aux);
       break;
     case RMI_PHASE_BOUNDS:
-      shard_bounds<T>(L, keys, sh, b->top->kind, b->d_top, b->N, (u64*)b->buf.S);
+      shard_bounds<T>(L, keys, sh, b->top->kind, b->d_top, b->N, (u64*)b->buf.S, b->d_aux);
       break;
     case RMI_PHASE_SPLIT:
       shard_split<T>(L, keys, sh, b->top->kind, b->d_top, b->N, (const u64*)b->buf.S, b->d_aux);
@@ -741,7 +744,7 @@ template <class T> int shard_phase_typed(rmi_shard_build* b, int phase) {
     default:
       return fail(RMI_ERR_INVALID, "rmi_shard_phase: unknown phase");
   }
-  if (phase >= 0 && phase < 6) cudaEventRecord(b->ev_end[phase], b->st);
+  if (phase >= 0 && phase < RMI_NUM_PHASES) cudaEventRecord(b->ev_end[phase], b->st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(RMI_ERR_CUDA, std::string("rmi_shard_phase: ") + cudaGetErrorString(e));
   return RMI_OK;
@@ -754,6 +757,18 @@ extern "C" {
 uint32_t rmi_params_per_model(const char* leaf_model_name) {
   const ModelName* m = leaf_model_name ? find_model(leaf_model_name) : nullptr;
   return m ? (uint32_t)leaf_params_per_model(m->kind) : 0;
+}
+
+int rmi_shard_top_rounds(const char* top_model_name) {
+  const ModelName* m = top_model_name ? find_model(top_model_name) : nullptr;
+  if (!m) return -1;
+  switch (m->kind) {
+    case M_LINEAR_SPLINE: case M_RADIX: return 0;
+    case M_LINEAR: case M_ROBUST_LINEAR: return 1;
+    case M_NORMAL: case M_LOGNORMAL: return 2;
+    case M_CUBIC: return 3;
+    default: return -1;
+  }
 }
 
 int rmi_shard_ends_get(const rmi_dataset* ds, rmi_shard_ends* out) {
@@ -781,8 +796,9 @@ int rmi_shard_build_create(const rmi_dataset* local, const rmi_shard_info* info,
   if (!leaf) return fail(RMI_ERR_PANIC, "Unknown model type: " + s.substr(c + 1));
   if (leaf->kind == M_RADIX || leaf->kind == M_BRADIX || leaf->kind == M_HISTOGRAM)
     return fail(RMI_ERR_PANIC, "if used, model type " + s.substr(c + 1) + " must be the root model");
-  if (!(top->kind == M_LINEAR || top->kind == M_ROBUST_LINEAR || top->kind == M_LINEAR_SPLINE || top->kind == M_RADIX))
-    return fail(RMI_ERR_UNSUPPORTED, "range-partitioned builds offer the top models linear, robust_linear, linear_spline, radix");
+  if (rmi_shard_top_rounds(top->name) < 0)
+    return fail(RMI_ERR_UNSUPPORTED, "range-partitioned builds offer the top models linear, robust_linear, linear_spline, "
+                                     "cubic, normal, lognormal, radix");
   if (leaf->kind == M_RADIX_TABLE) return fail(RMI_ERR_UNSUPPORTED, "radix tables are only offered as the top model");
   if (branch_factor < 1) return fail(RMI_ERR_PANIC, "branching factor must be at least 1");
   if (info->n_global == 0) return fail(RMI_ERR_PANIC, "start index was 0 but end index was 0");
@@ -797,7 +813,7 @@ int rmi_shard_build_create(const rmi_dataset* local, const rmi_shard_info* info,
   bool ok = cudaMalloc(&b->d_top, sizeof(TopModel)) == cudaSuccess && cudaMalloc(&b->d_aux, sizeof(BuildAux)) == cudaSuccess &&
             cudaMalloc(&b->d_scratch, shard_scratch_bytes()) == cudaSuccess &&
             cudaMalloc(&b->d_stats, stats_scratch_bytes(branch_factor)) == cudaSuccess;
-  for (int q = 0; q < 6; ++q) ok = ok && cudaEventCreate(&b->ev_begin[q]) == cudaSuccess && cudaEventCreate(&b->ev_end[q]) == cudaSuccess;
+  for (int q = 0; q < RMI_NUM_PHASES; ++q) ok = ok && cudaEventCreate(&b->ev_begin[q]) == cudaSuccess && cudaEventCreate(&b->ev_end[q]) == cudaSuccess;
   {
     int lo_prio = 0, hi_prio = 0;
     cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
@@ -872,7 +888,8 @@ int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
   R.model_max_log2_error = std::log2((double)h_aux.max_error);
   R.l0_model_id = b->top->kind;
   R.l0_bradix_high = 1;
-  if (b->top->kind == M_RADIX) R.l0_num_iparams = 2; else R.l0_num_fparams = 2;
+  if (b->top->kind == M_RADIX) R.l0_num_iparams = 2;
+  else R.l0_num_fparams = b->top->kind == M_CUBIC ? 4 : ((b->top->kind == M_NORMAL || b->top->kind == M_LOGNORMAL) ? 3 : 2);
   for (int q = 0; q < 4; ++q) { R.l0_fparams[q] = h_top.f[q]; R.l0_iparams[q] = h_top.ip[q]; }
   R.l1_model_id = b->leaf->kind;
   R.l1_params_per_model = ppm;
@@ -880,8 +897,8 @@ int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
   R.l1_errors = stats_only ? nullptr : box->l1_errors.data();
   R.l1_counts = want_counts ? box->l1_counts.data() : nullptr;
   {   // device time of this rank's phases (collectives between them are not included)
-    const int map[6] = {0, 0, 1, 1, 2, 3};
-    for (int q = 0; q < 6; ++q) {
+    const int map[RMI_NUM_PHASES] = {0, 0, 1, 1, 2, 3, 0};
+    for (int q = 0; q < RMI_NUM_PHASES; ++q) {
       if (!b->ran[q]) continue;
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, b->ev_begin[q], b->ev_end[q]) == cudaSuccess) {
@@ -899,7 +916,7 @@ int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
 void rmi_shard_build_destroy(rmi_shard_build* b) {
   if (!b) return;
   cudaFree(b->d_top); cudaFree(b->d_aux); cudaFree(b->d_scratch); cudaFree(b->d_stats);
-  for (int q = 0; q < 6; ++q) { if (b->ev_begin[q]) cudaEventDestroy(b->ev_begin[q]); if (b->ev_end[q]) cudaEventDestroy(b->ev_end[q]); }
+  for (int q = 0; q < RMI_NUM_PHASES; ++q) { if (b->ev_begin[q]) cudaEventDestroy(b->ev_begin[q]); if (b->ev_end[q]) cudaEventDestroy(b->ev_end[q]); }
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->side) cudaStreamDestroy(b->side);

@@ -68,6 +68,13 @@ __device__ __forceinline__ u64 scale_offset(u64 off, double sf, int use_sf) {
   return use_sf ? f64_to_u64_sat(__dmul_rn(__ull2double_rn(off), sf)) : off;
 }
 
+// The x a normal / lognormal model sees for a key (normal.rs:30-33, :56-63: ln(x), non-finite -> 0).
+template <class T, int LOGN> __device__ __forceinline__ double normal_x(T k) {
+  double x = Key<T>::as_float(k);
+  if (LOGN) { double l = log(x); x = isfinite(l) ? l : 0.0; }
+  return x;
+}
+
 // utils.rs:13-21
 __device__ __forceinline__ int num_bits_of(u64 largest) {
   int nbits = 0;

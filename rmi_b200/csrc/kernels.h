@@ -109,12 +109,16 @@ size_t stats_scratch_bytes(u64 num_leaves);
 size_t shard_scratch_bytes();
 template <class T>
 unsigned shard_top_local(const Launch& L, const T* keys, const Shard<T>& sh, int kind, u64 N, double px, double py,
-                         void* scratch, double* d_sums);
+                         T first_key, T last_key, void* scratch, double* d_sums);
+template <class T>
+void shard_top_mid(const Launch& L, const T* keys, const Shard<T>& sh, int kind, u64 N, T first_key, T last_key,
+                   void* scratch, double* d_sums, BuildAux* d_aux);
 template <class T>
 void shard_top_finish(const Launch& L, const Shard<T>& sh, int kind, u64 N, double px, double py, const double* d_sums,
-                      T first_key, T last_key, u64 last_F, TopModel* d_top, BuildAux* d_aux);
+                      T first_key, T last_key, u64 last_F, const void* scratch, TopModel* d_top, BuildAux* d_aux);
 template <class T>
-void shard_bounds(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N, u64* d_S);
+void shard_bounds(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N, u64* d_S,
+                  BuildAux* d_aux);
 template <class T>
 void shard_split(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N,
                  const u64* d_S, BuildAux* d_aux);

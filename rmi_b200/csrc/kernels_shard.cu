@@ -5,9 +5,19 @@
 //
 //   phase TOP_LOCAL   k_shard_slr_partial / k_shard_slr_reduce   -> 5 partial sums per rank
 //        [all-reduce SUM of 5 doubles]                             (linear, robust_linear)
-//   phase TOP_FINISH  k_shard_slr_solve  or  k_shard_top_from_ends (linear_spline, radix: O(1)
-//                     functions of the global first / last key)
-//   phase BOUNDS      k_shard_bounds_search -> S_local (global indices, n_global where none)
+//                     k_shard_cubic_local: this rank's candidates for the two interior points
+//        [all-reduce MIN of 4 order-encoded u64]                   (cubic)
+//                     k_shard_normal_partial<pass 0>: sum(x - pivot)
+//        [all-reduce SUM]                                          (normal, lognormal)
+//   phase TOP_MID     (two-round tops only) cubic: closed form from the gathered points, then
+//                     the local part of the two L1 sums; normal: mean, then sum((x - mean)^2)
+//        [all-reduce SUM]
+//   phase TOP_FINISH  k_shard_slr_solve, k_shard_top_from_ends (linear_spline, radix: O(1)
+//                     functions of the global first / last key), k_shard_cubic_pick,
+//                     k_shard_normal_solve
+//   phase BOUNDS      k_shard_bounds_search (monotone-by-construction tops) or the streaming
+//                     k_shard_bounds_stream (cubic, normal: also verifies monotonicity)
+//                     -> S_local (global indices, n_global where none)
 //        [all-reduce MIN of (N+1) u64]
 //   phase SPLIT       k_split_from_S
 //        [halo: each rank receives the keys of its last leaf that live on the next rank(s)]
@@ -19,6 +29,7 @@
 // (base + local) and the item before local index 0 comes from the previous rank.
 #include "device_util.cuh"
 #include "kernels.h"
+#include "spline.cuh"
 
 namespace rmi {
 
@@ -165,6 +176,238 @@ __global__ void k_shard_top_from_ends(int kind, T first_key, T last_key, u64 las
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// cubic top (cubic_spline.rs:18-136) over a range-partitioned array.
+// The closed form needs four points: the global first / last item (known everywhere from the
+// gathered slab ends) and two interior ones — the first item whose scaled x is > 0 and the
+// last raw item whose scaled x is < 1.  Each rank binary-searches its slab for its own
+// candidates; ONE all-reduce MIN over four order-encoded u64 picks the winners:
+//   slot 0: global index of the first candidate        slot 1: its key (order-preserving code)
+//   slot 2: ~(global index + 1) of the last candidate  slot 3: ~(its key's code)
+// Keys are sorted, so the smallest candidate index carries the smallest candidate key and
+// index and key can be reduced independently.  The host reduces signed 64-bit integers, so
+// every slot is stored with its top bit flipped (unsigned order == signed order).
+// ------------------------------------------------------------------------------------------
+constexpr u64 ORD_SIGN = 0x8000000000000000ull;
+template <class T> __device__ __forceinline__ u64 key_code(T k) { return (u64)k; }
+template <> __device__ __forceinline__ u64 key_code<double>(double k) {
+  u64 b = (u64)__double_as_longlong(k);
+  return (b & ORD_SIGN) ? ~b : (b | ORD_SIGN);
+}
+template <class T> __device__ __forceinline__ T key_decode(u64 c) { return (T)c; }
+template <> __device__ __forceinline__ double key_decode<double>(u64 c) {
+  u64 b = (c & ORD_SIGN) ? (c & ~ORD_SIGN) : ~c;
+  return __longlong_as_double((long long)b);
+}
+
+template <class T>
+__global__ void k_shard_cubic_local(const T* __restrict__ keys, const Shard<T> sh, T first_key, T last_key,
+                                    u64* __restrict__ slots) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  u64 v0 = ~0ull, v1 = ~0ull, v2 = ~0ull, v3 = ~0ull;
+  if (sh.n_global >= 2 && !(first_key == last_key) && sh.n_local > 0) {
+    double xmin = Key<T>::as_float(first_key), xmax = Key<T>::as_float(last_key);
+    u64 lo = 0, hi = sh.n_local;          // :46-54 first local item with scaled x > 0
+    while (lo < hi) {
+      u64 mid = lo + ((hi - lo) >> 1);
+      if (scale3(Key<T>::as_float(keys[mid]), xmin, xmax) > 0.0) hi = mid; else lo = mid + 1;
+    }
+    if (lo < sh.n_local) { v0 = sh.base + lo; v1 = key_code<T>(keys[lo]); }
+    u64 lo2 = 0, hi2 = sh.n_local;        // :56-65 first local index with !(scaled x < 1)
+    while (lo2 < hi2) {
+      u64 mid = lo2 + ((hi2 - lo2) >> 1);
+      if (scale3(Key<T>::as_float(keys[mid]), xmin, xmax) < 1.0) lo2 = mid + 1; else hi2 = mid;
+    }
+    if (lo2 > 0) { v2 = ~(sh.base + lo2); v3 = ~key_code<T>(keys[lo2 - 1]); }
+  }
+  slots[0] = v0 ^ ORD_SIGN; slots[1] = v1 ^ ORD_SIGN; slots[2] = v2 ^ ORD_SIGN; slots[3] = v3 ^ ORD_SIGN;
+}
+
+// cand[0..4) = cubic (a,b,c,d), cand[4..6) = linear spline (alpha, beta)  — as k_spline_prepare
+template <class T>
+__global__ void k_shard_cubic_closed_form(const Shard<T> sh, T first_key, T last_key, double sf, int use_sf,
+                                          const u64* __restrict__ slots, double* __restrict__ cand, BuildAux* aux) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const u64 n = sh.n_global;
+  double y_first = __ull2double_rn(scale_offset(0, sf, use_sf));
+  double la, lb, a, b, c, d;
+  if (n == 1 || first_key == last_key) { la = y_first; lb = 0.0; a = b = c = 0.0; d = y_first; }   // :23-36
+  else {
+    double xmin = Key<T>::as_float(first_key), xmax = Key<T>::as_float(last_key);
+    double ymin = y_first, ymax = __ull2double_rn(scale_offset(n - 1, sf, use_sf));
+    double slope = __ddiv_rn(__dadd_rn(ymin, -ymax), __dadd_rn(xmin, -xmax));     // linear_spline.rs:28-33
+    la = __dadd_rn(ymin, -__dmul_rn(slope, xmin));
+    lb = slope;
+    u64 v0 = slots[0] ^ ORD_SIGN, v1 = slots[1] ^ ORD_SIGN, v2 = slots[2] ^ ORD_SIGN, v3 = slots[3] ^ ORD_SIGN;
+    if (v0 == ~0ull || v2 == ~0ull) {
+      atomicOr(&aux->status, ST_CUBIC_UNWRAP);
+      a = b = c = d = 0.0;
+    } else {
+      // the first item with scaled x > 0 starts a run of equal keys, so its duplicate-fixed
+      // offset is its own index; the last item with scaled x < 1 is taken raw (:56-65)
+      u64 lo = v0, ip = ~v2 - 1ull;
+      cubic_from_points(xmin, ymin, xmax, ymax, Key<T>::as_float(key_decode<T>(v1)),
+                        __ull2double_rn(scale_offset(lo, sf, use_sf)), Key<T>::as_float(key_decode<T>(~v3)),
+                        __ull2double_rn(scale_offset(ip, sf, use_sf)), a, b, c, d);
+    }
+  }
+  cand[0] = a; cand[1] = b; cand[2] = c; cand[3] = d; cand[4] = la; cand[5] = lb;
+}
+
+// cubic_spline.rs:117-126 over the local slab: partials[2b] = sum |cubic(x) - y|,
+// partials[2b+1] = sum |linear_spline(x) - y|, y = scaled duplicate-fixed GLOBAL offset.
+template <class T>
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_cubic_l1_partial(const T* __restrict__ keys, const Shard<T> sh, double sf, int use_sf,
+                         const double* __restrict__ cand, double* __restrict__ partials) {
+  __shared__ double sm[32];
+  double cf[4] = {cand[0], cand[1], cand[2], cand[3]};
+  double lf[2] = {cand[4], cand[5]};
+  double ec = 0, el = 0;
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < sh.n_local; i += stride) {
+    double x = Key<T>::as_float(keys[i]);
+    u64 F = global_run_start(keys, i, sh.base, sh.has_prev, sh.prev_key, sh.prev_F);
+    double y = __ull2double_rn(scale_offset(F, sf, use_sf));
+    ec += fabs(predict_float<M_CUBIC>(cf, x) - y);
+    el += fabs(predict_float<M_LINEAR>(lf, x) - y);
+  }
+  double r0 = block_sum(ec, sm), r1 = block_sum(el, sm);
+  if (threadIdx.x == 0) { partials[2 * blockIdx.x] = r0; partials[2 * blockIdx.x + 1] = r1; }
+}
+template <class T>
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_cubic_l1_reduce(const T* __restrict__ keys, const Shard<T> sh, double sf, int use_sf,
+                        const double* __restrict__ cand, const double* __restrict__ partials, int nblocks,
+                        double* __restrict__ sums) {
+  __shared__ double sm[32];
+  double ec = 0, el = 0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) { ec += partials[2 * b]; el += partials[2 * b + 1]; }
+  double r0 = block_sum(ec, sm), r1 = block_sum(el, sm);
+  if (threadIdx.x != 0) return;
+  if (sh.is_last && sh.n_local > 0) {   // the drained iterator's repeated final item
+    u64 i = sh.n_local - 1;
+    double x = Key<T>::as_float(keys[i]);
+    u64 F = global_run_start(keys, i, sh.base, sh.has_prev, sh.prev_key, sh.prev_F);
+    double y = __ull2double_rn(scale_offset(F, sf, use_sf));
+    double lf[2] = {cand[4], cand[5]};
+    r0 += fabs(predict_float<M_CUBIC>(cand, x) - y);
+    r1 += fabs(predict_float<M_LINEAR>(lf, x) - y);
+  }
+  sums[0] = r0; sums[1] = r1;
+  for (int q = 2; q < 8; ++q) sums[q] = 0.0;
+}
+// cubic_spline.rs:128-135: keep the linear spline (0, 0, beta, alpha) if it is strictly better.
+__global__ void k_shard_cubic_pick(const double* __restrict__ sums, const double* __restrict__ cand, TopModel* top) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (sums[1] < sums[0]) { top->f[0] = 0.0; top->f[1] = 0.0; top->f[2] = cand[5]; top->f[3] = cand[4]; }
+  else { top->f[0] = cand[0]; top->f[1] = cand[1]; top->f[2] = cand[2]; top->f[3] = cand[3]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// normal / lognormal top (normal.rs:28-76): mean over the drained stream (n+1 items, divisor
+// n), then sum((x - mean)^2) — two rounds of one all-reduce SUM each.
+// PASS 0: sums[0] = local sum(x - px), px a pivot every rank derives from the global end keys.
+// PASS 1: state[0] = mean (from the reduced sums[0]); sums[0] = local sum((x - mean)^2).
+// ------------------------------------------------------------------------------------------
+template <class T, int LOGN> __device__ __forceinline__ double normal_pivot(T first_key, T last_key) {
+  return 0.5 * normal_x<T, LOGN>(first_key) + 0.5 * normal_x<T, LOGN>(last_key);
+}
+template <class T, int LOGN, int PASS>
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_normal_partial(const T* __restrict__ keys, const Shard<T> sh, T first_key, T last_key,
+                       const double* __restrict__ sums, double* __restrict__ partials) {
+  __shared__ double sm[32];
+  const double pivot = normal_pivot<T, LOGN>(first_key, last_key);
+  double px = pivot;
+  if (PASS == 1) px = (sums[0] + __ull2double_rn(sh.n_global + 1) * pivot) / __ull2double_rn(sh.n_global);   // mean
+  double s = 0;
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < sh.n_local; i += stride) {
+    double d = normal_x<T, LOGN>(keys[i]) - px;
+    s += PASS == 0 ? d : d * d;
+  }
+  double r = block_sum(s, sm);
+  if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
+template <class T, int LOGN, int PASS>
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_normal_reduce(const T* __restrict__ keys, const Shard<T> sh, T first_key, T last_key,
+                      const double* __restrict__ partials, int nblocks, double* __restrict__ sums,
+                      double* __restrict__ state) {
+  __shared__ double sm[32];
+  double s = 0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partials[b];
+  double r = block_sum(s, sm);
+  if (threadIdx.x != 0) return;
+  const double pivot = normal_pivot<T, LOGN>(first_key, last_key);
+  double px = pivot;
+  if (PASS == 1) {
+    px = (sums[0] + __ull2double_rn(sh.n_global + 1) * pivot) / __ull2double_rn(sh.n_global);
+    state[0] = px;
+  }
+  if (sh.is_last && sh.n_local > 0) {   // repeated final item
+    double d = normal_x<T, LOGN>(keys[sh.n_local - 1]) - px;
+    r += PASS == 0 ? d : d * d;
+  }
+  sums[0] = r;
+  for (int q = 1; q < 8; ++q) sums[q] = 0.0;
+}
+__global__ void k_shard_normal_solve(const double* __restrict__ sums, const double* __restrict__ state, u64 n,
+                                     u64 last_F, double sf, int use_sf, TopModel* top) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double stdev = sqrt(sums[0] / __ull2double_rn(n));
+  double scale = __ull2double_rn(scale_offset(last_F, sf, use_sf));   // max y = y of the last run (n > 0)
+  top->f[0] = state[0]; top->f[1] = stdev; top->f[2] = scale;
+}
+
+// ------------------------------------------------------------------------------------------
+// Streaming leaf boundaries for tops whose prediction is not monotone by construction
+// (cubic, normal, lognormal): as k_bounds (kernels_leaf.cu) on the local slab, writing global
+// indices; the key before local index 0 is the previous rank's last key, so the
+// non-decreasing-target assertion (two_layer.rs:50) is checked across cuts too.  S must be
+// pre-filled with n_global; the all-reduce MIN then yields the global S.
+// ------------------------------------------------------------------------------------------
+__global__ void k_shard_fill(u64* __restrict__ p, u64 len, u64 v) {
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) p[i] = v;
+}
+template <class T, int TOP>
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_bounds_stream(const T* __restrict__ keys, const Shard<T> sh, const TopModel* __restrict__ top_ptr, u64 N,
+                      u64* __restrict__ S, BuildAux* aux) {
+  TopModel m = *top_ptr;
+  const bool aligned = is_aligned16(keys);
+  constexpr bool nbc = !(TOP == M_CUBIC || TOP == M_RADIX || TOP == M_RADIX_TABLE || TOP == M_BRADIX || TOP == M_HISTOGRAM);
+  u64 stride = (u64)gridDim.x * blockDim.x * 4;
+  unsigned bad = 0;
+  for (u64 b = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; b < sh.n_local; b += stride) {
+    T k[4];
+    int cnt = load_keys4(keys, b, sh.n_local, aligned, k);
+    T kp = b > 0 ? keys[b - 1] : (sh.has_prev ? sh.prev_key : k[0]);
+    u64 pp = top_predict<TOP>(m, kp);
+    u64 tp = pp < N - 1 ? pp : N - 1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e >= cnt) break;
+      u64 i = b + e;
+      u64 p = top_predict<TOP>(m, k[e]);
+      if (!nbc && p >= N) bad |= ST_TOP_OUT_OF_BOUNDS;
+      u64 t = p < N - 1 ? p : N - 1;
+      if (i == 0 && !sh.has_prev) {
+        for (u64 q = 0; q <= t; ++q) S[q] = 0;
+      } else {
+        if (k[e] < kp) bad |= ST_NOT_SORTED;
+        if (t < tp) bad |= ST_NON_MONOTONE;
+        for (u64 q = tp + 1; q <= t; ++q) S[q] = sh.base + i;
+      }
+      kp = k[e]; tp = t;
+    }
+  }
+  if (bad) set_status(aux, bad);
+}
+
 // S_local[j] = global index of the first LOCAL key whose prediction reaches j, n_global if
 // none (the all-reduce MIN over ranks then yields the global S).
 template <class T, int TOP>
@@ -230,11 +473,14 @@ int sh_grid(u64 n, int num_sms) {
 
 }  // namespace
 
-size_t shard_scratch_bytes() { return (size_t)SH_MAX_BLOCKS * 5 * sizeof(double); }
+// block partials (5 doubles per block) followed by 8 doubles of per-build state:
+// cand[0..6) (cubic / linear-spline candidates) and state[0] (normal: the mean)
+size_t shard_scratch_bytes() { return ((size_t)SH_MAX_BLOCKS * 5 + 8) * sizeof(double); }
+static inline double* shard_cand(void* scratch) { return (double*)scratch + (size_t)SH_MAX_BLOCKS * 5; }
 
 template <class T>
 unsigned shard_top_local(const Launch& L, const T* keys, const Shard<T>& sh, int kind, u64 N, double px, double py,
-                         void* scratch, double* d_sums) {
+                         T first_key, T last_key, void* scratch, double* d_sums) {
   double sf = (double)N / (double)sh.n_global;
   int use_sf = std::fabs(sf - 1.0) > DBL_EPSILON ? 1 : 0;
   double* partials = (double*)scratch;
@@ -256,38 +502,103 @@ unsigned shard_top_local(const Launch& L, const T* keys, const Shard<T>& sh, int
     count_launch();
     k_shard_slr_reduce<T><<<1, SH_THREADS, 0, L.stream>>>(keys, sh, repeat, sf, use_sf, px, py, partials, g, d_sums);
     count_launch();
+  } else if (kind == M_CUBIC) {
+    cudaMemsetAsync(d_sums, 0, 8 * sizeof(double), L.stream);
+    k_shard_cubic_local<T><<<1, 32, 0, L.stream>>>(keys, sh, first_key, last_key, (u64*)d_sums + 8);
+    count_launch();
+  } else if (kind == M_NORMAL || kind == M_LOGNORMAL) {
+    int g = sh_grid(sh.n_local, L.num_sms);
+    if (kind == M_NORMAL) {
+      k_shard_normal_partial<T, 0, 0><<<g, SH_THREADS, 0, L.stream>>>(keys, sh, first_key, last_key, d_sums, partials);
+      k_shard_normal_reduce<T, 0, 0><<<1, SH_THREADS, 0, L.stream>>>(keys, sh, first_key, last_key, partials, g, d_sums, shard_cand(scratch) + 6);
+    } else {
+      k_shard_normal_partial<T, 1, 0><<<g, SH_THREADS, 0, L.stream>>>(keys, sh, first_key, last_key, d_sums, partials);
+      k_shard_normal_reduce<T, 1, 0><<<1, SH_THREADS, 0, L.stream>>>(keys, sh, first_key, last_key, partials, g, d_sums, shard_cand(scratch) + 6);
+    }
+    count_launch(); count_launch();
   } else {
     cudaMemsetAsync(d_sums, 0, 8 * sizeof(double), L.stream);
   }
   return 0;
 }
 
+// Second round of the two-round tops (between the two collectives).
+template <class T>
+void shard_top_mid(const Launch& L, const T* keys, const Shard<T>& sh, int kind, u64 N, T first_key, T last_key,
+                   void* scratch, double* d_sums, BuildAux* d_aux) {
+  double sf = (double)N / (double)sh.n_global;
+  int use_sf = std::fabs(sf - 1.0) > DBL_EPSILON ? 1 : 0;
+  double* partials = (double*)scratch;
+  double* cand = shard_cand(scratch);
+  if (kind == M_CUBIC) {
+    k_shard_cubic_closed_form<T><<<1, 32, 0, L.stream>>>(sh, first_key, last_key, sf, use_sf, (const u64*)d_sums + 8, cand, d_aux);
+    int g = sh_grid(sh.n_local, L.num_sms);
+    k_shard_cubic_l1_partial<T><<<g, SH_THREADS, 0, L.stream>>>(keys, sh, sf, use_sf, cand, partials);
+    k_shard_cubic_l1_reduce<T><<<1, SH_THREADS, 0, L.stream>>>(keys, sh, sf, use_sf, cand, partials, g, d_sums);
+    count_launch(); count_launch(); count_launch();
+  } else if (kind == M_NORMAL || kind == M_LOGNORMAL) {
+    int g = sh_grid(sh.n_local, L.num_sms);
+    if (kind == M_NORMAL) {
+      k_shard_normal_partial<T, 0, 1><<<g, SH_THREADS, 0, L.stream>>>(keys, sh, first_key, last_key, d_sums, partials);
+      k_shard_normal_reduce<T, 0, 1><<<1, SH_THREADS, 0, L.stream>>>(keys, sh, first_key, last_key, partials, g, d_sums, cand + 6);
+    } else {
+      k_shard_normal_partial<T, 1, 1><<<g, SH_THREADS, 0, L.stream>>>(keys, sh, first_key, last_key, d_sums, partials);
+      k_shard_normal_reduce<T, 1, 1><<<1, SH_THREADS, 0, L.stream>>>(keys, sh, first_key, last_key, partials, g, d_sums, cand + 6);
+    }
+    count_launch(); count_launch();
+  }
+}
+
 template <class T>
 void shard_top_finish(const Launch& L, const Shard<T>& sh, int kind, u64 N, double px, double py, const double* d_sums,
-                      T first_key, T last_key, u64 last_F, TopModel* d_top, BuildAux* d_aux) {
+                      T first_key, T last_key, u64 last_F, const void* scratch, TopModel* d_top, BuildAux* d_aux) {
   double sf = (double)N / (double)sh.n_global;
   int use_sf = std::fabs(sf - 1.0) > DBL_EPSILON ? 1 : 0;
   if (kind == M_LINEAR || kind == M_ROBUST_LINEAR) {
     k_shard_slr_solve<<<1, 32, 0, L.stream>>>(d_sums, px, py, d_top, d_aux);
+  } else if (kind == M_CUBIC) {
+    k_shard_cubic_pick<<<1, 32, 0, L.stream>>>(d_sums, shard_cand(const_cast<void*>(scratch)), d_top);
+  } else if (kind == M_NORMAL || kind == M_LOGNORMAL) {
+    k_shard_normal_solve<<<1, 32, 0, L.stream>>>(d_sums, shard_cand(const_cast<void*>(scratch)) + 6, sh.n_global, last_F, sf,
+                                                 use_sf, d_top);
   } else {
     k_shard_top_from_ends<T><<<1, 32, 0, L.stream>>>(kind, first_key, last_key, last_F, sh.n_global, sf, use_sf, d_top, d_aux);
   }
   count_launch();
 }
 
-template <class T>
-void shard_bounds(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N, u64* d_S) {
-  unsigned blocks = (unsigned)((N + 1 + SH_THREADS - 1) / SH_THREADS);
-  if (kind == M_RADIX) k_shard_bounds_search<T, M_RADIX><<<blocks, SH_THREADS, 0, L.stream>>>(keys, sh, d_top, N, d_S);
-  else k_shard_bounds_search<T, M_LINEAR><<<blocks, SH_THREADS, 0, L.stream>>>(keys, sh, d_top, N, d_S);
+template <class T, int TOP>
+static void shard_bounds_stream(const Launch& L, const T* keys, const Shard<T>& sh, const TopModel* d_top, u64 N, u64* d_S,
+                                BuildAux* d_aux) {
+  k_shard_fill<<<sh_grid(N + 1, L.num_sms), SH_THREADS, 0, L.stream>>>(d_S, N + 1, sh.n_global);
   count_launch();
+  k_shard_bounds_stream<T, TOP><<<sh_grid((sh.n_local + 3) / 4, L.num_sms), SH_THREADS, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux);
+  count_launch();
+}
+
+template <class T>
+void shard_bounds(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N, u64* d_S,
+                  BuildAux* d_aux) {
+  unsigned blocks = (unsigned)((N + 1 + SH_THREADS - 1) / SH_THREADS);
+  switch (kind) {
+    case M_RADIX: k_shard_bounds_search<T, M_RADIX><<<blocks, SH_THREADS, 0, L.stream>>>(keys, sh, d_top, N, d_S); count_launch(); break;
+    case M_CUBIC: shard_bounds_stream<T, M_CUBIC>(L, keys, sh, d_top, N, d_S, d_aux); break;
+    case M_NORMAL: shard_bounds_stream<T, M_NORMAL>(L, keys, sh, d_top, N, d_S, d_aux); break;
+    case M_LOGNORMAL: shard_bounds_stream<T, M_LOGNORMAL>(L, keys, sh, d_top, N, d_S, d_aux); break;
+    default: k_shard_bounds_search<T, M_LINEAR><<<blocks, SH_THREADS, 0, L.stream>>>(keys, sh, d_top, N, d_S); count_launch(); break;
+  }
 }
 
 template <class T>
 void shard_split(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N,
                  const u64* d_S, BuildAux* d_aux) {
-  if (kind == M_RADIX) k_split_from_S<T, M_RADIX><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux);
-  else k_split_from_S<T, M_LINEAR><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux);
+  switch (kind) {
+    case M_RADIX: k_split_from_S<T, M_RADIX><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
+    case M_CUBIC: k_split_from_S<T, M_CUBIC><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
+    case M_NORMAL: k_split_from_S<T, M_NORMAL><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
+    case M_LOGNORMAL: k_split_from_S<T, M_LOGNORMAL><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
+    default: k_split_from_S<T, M_LINEAR><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
+  }
   count_launch();
 }
 
@@ -297,10 +608,11 @@ void shard_copy_status(const Launch& L, const BuildAux* d_aux, unsigned* d_out) 
 }
 
 #define INST(T)                                                                                                     \
-  template unsigned shard_top_local<T>(const Launch&, const T*, const Shard<T>&, int, u64, double, double, void*, double*); \
+  template unsigned shard_top_local<T>(const Launch&, const T*, const Shard<T>&, int, u64, double, double, T, T, void*, double*); \
+  template void shard_top_mid<T>(const Launch&, const T*, const Shard<T>&, int, u64, T, T, void*, double*, BuildAux*); \
   template void shard_top_finish<T>(const Launch&, const Shard<T>&, int, u64, double, double, const double*, T, T, u64,   \
-                                    TopModel*, BuildAux*);                                                          \
-  template void shard_bounds<T>(const Launch&, const T*, const Shard<T>&, int, const TopModel*, u64, u64*);          \
+                                    const void*, TopModel*, BuildAux*);                                             \
+  template void shard_bounds<T>(const Launch&, const T*, const Shard<T>&, int, const TopModel*, u64, u64*, BuildAux*); \
   template void shard_split<T>(const Launch&, const T*, const Shard<T>&, int, const TopModel*, u64, const u64*, BuildAux*);
 INST(u64)
 INST(u32)

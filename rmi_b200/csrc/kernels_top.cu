@@ -14,6 +14,7 @@
 // passes are grid-stride with a fixed grid so reductions are deterministic run to run.
 #include "device_util.cuh"
 #include "kernels.h"
+#include "spline.cuh"
 
 namespace rmi {
 
@@ -253,10 +254,6 @@ __device__ void linear_spline_params(const T* __restrict__ keys, u64 n, double s
   beta = slope;
 }
 
-__device__ __forceinline__ double scale3(double v, double mn, double mx) {
-  return __ddiv_rn(__dadd_rn(v, -mn), __dadd_rn(mx, -mn));
-}
-
 template <class T>
 __global__ void k_spline_prepare(const T* __restrict__ keys, u64 n, double sf, int use_sf, int want_cubic,
                                  double* cand, TopModel* top, BuildAux* aux) {
@@ -289,38 +286,10 @@ __global__ void k_spline_prepare(const T* __restrict__ keys, u64 n, double sf, i
       set_status(aux, ST_CUBIC_UNWRAP);
       a = b = c = d = 0.0;
     } else {
-      double sxn = scale3(Key<T>::as_float(keys[lo]), xmin, xmax);
-      double syn = scale3(__ull2double_rn(scale_offset(run_start(keys, lo), sf, use_sf)), ymin, ymax);
-      double m1 = __ddiv_rn(__dadd_rn(syn, -0.0), __dadd_rn(sxn, -0.0));
       u64 ip = lo2 - 1;
-      double sxp = scale3(Key<T>::as_float(keys[ip]), xmin, xmax);
-      double syp = scale3(__ull2double_rn(scale_offset(ip, sf, use_sf)), ymin, ymax);
-      double m2 = __ddiv_rn(__dadd_rn(1.0, -syp), __dadd_rn(1.0, -sxp));
-      double ss = __dadd_rn(__dmul_rn(m1, m1), __dmul_rn(m2, m2));
-      if (ss > 9.0) {
-        double tau = __ddiv_rn(3.0, __dsqrt_rn(ss));
-        m1 = __dmul_rn(m1, tau);
-        m2 = __dmul_rn(m2, tau);
-      }
-      double d3 = cube_dd(__dadd_rn(xmax, -xmin));
-      // (m1 + m2 - 2) / d3
-      a = __ddiv_rn(__dadd_rn(__dadd_rn(m1, m2), -2.0), d3);
-      // -(xmax*(2*m1 + m2 - 3) + xmin*(m1 + 2*m2 - 3)) / d3
-      double t1 = __dmul_rn(xmax, __dadd_rn(__dadd_rn(__dmul_rn(2.0, m1), m2), -3.0));
-      double t2 = __dmul_rn(xmin, __dadd_rn(__dadd_rn(m1, __dmul_rn(2.0, m2)), -3.0));
-      b = __ddiv_rn(-__dadd_rn(t1, t2), d3);
-      // (m1*xmax^2 + m2*xmin^2 + xmax*xmin*(2*m1 + 2*m2 - 6)) / d3
-      double xmax2 = __dmul_rn(xmax, xmax), xmin2 = __dmul_rn(xmin, xmin);
-      double u1 = __dmul_rn(m1, xmax2), u2 = __dmul_rn(m2, xmin2);
-      double u3 = __dmul_rn(__dmul_rn(xmax, xmin), __dadd_rn(__dadd_rn(__dmul_rn(2.0, m1), __dmul_rn(2.0, m2)), -6.0));
-      c = __ddiv_rn(__dadd_rn(__dadd_rn(u1, u2), u3), d3);
-      // -xmin*(m1*xmax^2 + xmax*xmin*(m2 - 3) + xmin^2) / d3
-      double v2 = __dmul_rn(__dmul_rn(xmax, xmin), __dadd_rn(m2, -3.0));
-      double inner = __dadd_rn(__dadd_rn(u1, v2), xmin2);
-      d = __ddiv_rn(__dmul_rn(-xmin, inner), d3);
-      double dy = __dadd_rn(ymax, -ymin);
-      a = __dmul_rn(a, dy); b = __dmul_rn(b, dy); c = __dmul_rn(c, dy); d = __dmul_rn(d, dy);
-      d = __dadd_rn(d, ymin);
+      cubic_from_points(xmin, ymin, xmax, ymax, Key<T>::as_float(keys[lo]),
+                        __ull2double_rn(scale_offset(run_start(keys, lo), sf, use_sf)), Key<T>::as_float(keys[ip]),
+                        __ull2double_rn(scale_offset(ip, sf, use_sf)), a, b, c, d);
     }
   }
   cand[0] = a; cand[1] = b; cand[2] = c; cand[3] = d;
@@ -372,11 +341,6 @@ k_cubic_finish(const T* __restrict__ keys, u64 n, double sf, int use_sf, const d
 // normal / lognormal (normal.rs:28-76).  Parallel: mean = sum(x)/n over the drained stream
 // (n+1 items, divisor n), scale = max y, stdev = sqrt(sum((x-mean)^2)/n).
 // ------------------------------------------------------------------------------------------
-template <class T, int LOGN> __device__ __forceinline__ double normal_x(T k) {
-  double x = Key<T>::as_float(k);
-  if (LOGN) { double l = log(x); x = isfinite(l) ? l : 0.0; }
-  return x;
-}
 template <class T, int LOGN, int PASS>
 __global__ void __launch_bounds__(TOP_THREADS)
 k_normal_partial(const T* __restrict__ keys, u64 n, const double* __restrict__ state, double* __restrict__ partials) {

@@ -8,7 +8,9 @@ concatenated key array (reference semantics: rmi_lib::train on the whole data se
     rmi  = train_sharded(data, "linear,linear", 1 << 20)
 
 Data path per build:
-    all-reduce SUM   8 doubles          top-model sums (linear / robust_linear)
+    top model        0, 1 or 2 tiny all-reduces (TOP_ROUNDS): SUM of 8 doubles (linear /
+                     robust_linear sums; normal / lognormal mean, then variance; cubic L1
+                     comparison), MIN of 4 x i64 (cubic: the two interior points of the spline)
     all-reduce MIN   (N+1) x u64        leaf boundaries S
     send/recv        halo keys          the tail of a rank's last leaf that lives on the next rank(s)
     all-reduce SUM   N x (ppm+2) x 8 B  leaf parameters, error bounds, key counts (zero where not owned)
@@ -26,8 +28,14 @@ import torch.distributed as dist
 
 from . import api
 
-PHASE_TOP_LOCAL, PHASE_TOP_FINISH, PHASE_BOUNDS, PHASE_SPLIT, PHASE_LEAF, PHASE_STATS = range(6)
-SHARDED_TOPS = ("linear", "robust_linear", "linear_spline", "radix")
+PHASE_TOP_LOCAL, PHASE_TOP_FINISH, PHASE_BOUNDS, PHASE_SPLIT, PHASE_LEAF, PHASE_STATS, PHASE_TOP_MID = range(7)
+# Collectives of the top-model fit (include/rmi_b200.h rmi_shard_top_rounds): the first one follows
+# TOP_LOCAL, the second one (two-round tops) follows TOP_MID.  "sum": all-reduce SUM of sums[0:8]
+# as f64; "min": all-reduce MIN of sums[8:12] as signed 64-bit integers.
+TOP_ROUNDS = {"linear_spline": (), "radix": (), "linear": ("sum",), "robust_linear": ("sum",),
+              "normal": ("sum", "sum"), "lognormal": ("sum", "sum"), "cubic": ("min", "sum")}
+SHARDED_TOPS = tuple(TOP_ROUNDS)
+_TOP_NFPARAMS = {"cubic": 4, "normal": 3, "lognormal": 3}
 _PPM = {"linear": 2, "robust_linear": 2, "linear_spline": 2, "loglinear": 2, "cubic": 4, "normal": 3, "lognormal": 3}
 _TORCH_OF_KEY = {api.KEY_U64: torch.int64, api.KEY_U32: torch.int32, api.KEY_F64: torch.float64}
 
@@ -264,7 +272,7 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
     if bufs is None or bufs["S"].numel() != N + 1 or bufs["params"].numel() != N * ppm:
         # params | errors | counts live in ONE allocation so that a single all-reduce combines them
         rec = torch.empty(N * (ppm + 2), dtype=torch.int64, device=dev)
-        bufs = dict(sums=torch.zeros(8, dtype=torch.float64, device=dev),
+        bufs = dict(sums=torch.zeros(16, dtype=torch.float64, device=dev),   # [0:8] f64 sums, [8:16] i64 slots
                     S=torch.empty(N + 1, dtype=torch.int64, device=dev),
                     params=rec[: N * ppm].view(torch.float64),
                     errors=rec[N * ppm: N * (ppm + 1)],
@@ -273,10 +281,22 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
         data._bufs = bufs
     eng.begin(info, model_spec, N, bufs)
 
-    # 2. top model: local sums -> all-reduce -> closed form (identical on every rank)
+    # 2. top model: local part -> tiny all-reduce(s) -> closed form (identical on every rank)
+    def top_collective(kind):
+        if world <= 1:
+            return
+        if kind == "sum":
+            dist.all_reduce(bufs["sums"][:8], op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.all_reduce(bufs["sums"].view(torch.int64)[8:12], op=dist.ReduceOp.MIN, group=group)
+
+    rounds = TOP_ROUNDS[parts[0]]
     eng.phase(PHASE_TOP_LOCAL)
-    if world > 1:
-        dist.all_reduce(bufs["sums"], op=dist.ReduceOp.SUM, group=group)
+    if rounds:
+        top_collective(rounds[0])
+    if len(rounds) > 1:
+        eng.phase(PHASE_TOP_MID)
+        top_collective(rounds[1])
     eng.phase(PHASE_TOP_FINISH)
     # 3. leaf boundaries: local lower bounds -> all-reduce MIN
     eng.phase(PHASE_BOUNDS)

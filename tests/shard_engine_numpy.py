@@ -28,6 +28,42 @@ def _scale(off: int, sf: float) -> int:
     return int(float(off) * sf) if abs(sf - 1.0) > np.finfo(np.float64).eps else off
 
 
+def _fma(a: float, b: float, c: float) -> float:
+    """fma(a, b, c) with one rounding (exact rational arithmetic, then the correctly rounded conversion)."""
+    if any(math.isnan(v) or math.isinf(v) for v in (a, b, c)):
+        return a * b + c
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+def _floor_u64(v: float) -> int:
+    """max(0, floor(v)) as u64 with Rust's saturating cast (models/mod.rs:735-737)."""
+    if math.isnan(v) or v <= 0:
+        return 0
+    if math.isinf(v):
+        return U64
+    return min(int(math.floor(v)), U64)
+
+
+_SIGN = 1 << 63
+
+
+def _to_i64(v: int) -> int:
+    """u64 slot value -> what the signed all-reduce MIN sees (top bit flipped: unsigned order == signed order)."""
+    v = (v ^ _SIGN) & U64
+    return v - (1 << 64) if v >= _SIGN else v
+
+
+def _from_i64(v: int) -> int:
+    return ((v + (1 << 64)) & U64) ^ _SIGN
+
+
+def _exp1(v: float) -> float:
+    x = 1.0 + v / 64.0
+    for _ in range(6):
+        x = x * x
+    return x
+
+
 def _fma_floor_u64(beta: float, x: float, alpha: float) -> int:
     """max(0, floor(fma(beta, x, alpha))) as u64 (models/mod.rs:735-737), exactly."""
     if any(math.isnan(v) or math.isinf(v) for v in (beta, x, alpha)):
@@ -96,11 +132,22 @@ class NumpyShardEngine:
         if t[0] == "radix":
             prefix, bits = t[1], t[2]
             return (((key << (prefix & 63)) & U64) >> ((64 - bits) & 63))
+        if t[0] == "cubic":       # cubic_spline.rs:140-151: three chained FMAs
+            a, b, c, d = t[1]
+            x = float(key)
+            return _floor_u64(_fma(_fma(_fma(a, x, b), x, c), x, d))
+        if t[0] in ("normal", "lognormal"):   # normal.rs:89-92, :163-167
+            mean, stdev, scale = t[1]
+            x = float(key)
+            if t[0] == "lognormal":
+                x = max(math.log(x), 0.0) if x > 0 else 0.0
+            z = (x - mean) / stdev
+            return _floor_u64((1.0 / (1.0 + _exp1(-1.65451 * z))) * scale)
         return _fma_floor_u64(t[2], float(key), t[1])
 
     # -- phases ------------------------------------------------------------------------------
     def phase(self, ph):
-        getattr(self, ["_top_local", "_top_finish", "_bounds", "_split", "_leaf", "_stats"][ph])()
+        getattr(self, ["_top_local", "_top_finish", "_bounds", "_split", "_leaf", "_stats", "_top_mid"][ph])()
 
     def _top_local(self):
         sums = np.zeros(8)
@@ -119,7 +166,92 @@ class NumpyShardEngine:
                 dx = float(k[i]) - px
                 dy = float(_scale(self.gF(i, k), self.sf)) - py
                 sums[:5] += (dx, dy, dx * dx, dx * dy, 1.0)
-        self.bufs["sums"][:] = torch.from_numpy(sums)
+        elif self.top_name == "cubic":
+            self._cubic_local()
+        elif self.top_name in ("normal", "lognormal"):
+            px = 0.5 * self._nx(self.info["first_key_bits"]) + 0.5 * self._nx(self.info["last_key_bits"])
+            k = self.keys(self.n_local)
+            sums[0] = sum(self._nx(int(v)) - px for v in k)
+            if self.info["is_last"] and self.n_local:
+                sums[0] += self._nx(int(k[-1])) - px          # the drained iterator's repeated final item
+            self._npx = px
+        self.bufs["sums"][:8] = torch.from_numpy(sums)
+
+    # -- two-round tops ----------------------------------------------------------------------
+    def _nx(self, key: int) -> float:
+        x = float(key)
+        if self.top_name == "lognormal":
+            x = math.log(x) if x > 0 else float("-inf")
+            x = x if math.isfinite(x) else 0.0
+        return x
+
+    def _sx(self, key: int) -> float:
+        xmin, xmax = float(self.info["first_key_bits"]), float(self.info["last_key_bits"])
+        return (float(key) - xmin) / (xmax - xmin)
+
+    def _cubic_local(self):
+        """this rank's candidates for the spline's two interior points (cubic_spline.rs:46-65)"""
+        v = [U64, U64, U64, U64]
+        k = self.keys(self.n_local)
+        if self.n >= 2 and self.info["first_key_bits"] != self.info["last_key_bits"] and self.n_local:
+            sx = [self._sx(int(x)) for x in k]
+            lo = next((i for i, t in enumerate(sx) if t > 0.0), None)
+            if lo is not None:
+                v[0], v[1] = self.base + lo, int(k[lo])
+            below = [i for i, t in enumerate(sx) if t < 1.0]
+            if below:
+                v[2], v[3] = (~(self.base + below[-1] + 1)) & U64, (~int(k[below[-1]])) & U64
+        slots = self.bufs["sums"].view(torch.int64)
+        for q in range(4):
+            slots[8 + q] = _to_i64(v[q])
+
+    def _top_mid(self):
+        sums = np.zeros(8)
+        k = self.keys(self.n_local)
+        if self.top_name == "cubic":
+            n, sf = self.n, self.sf
+            k0, k1 = self.info["first_key_bits"], self.info["last_key_bits"]
+            y_first = float(_scale(0, sf))
+            if n == 1 or k0 == k1:
+                lin, cub = (y_first, 0.0), (0.0, 0.0, 0.0, y_first)
+            else:
+                xmin, xmax, ymin, ymax = float(k0), float(k1), y_first, float(_scale(n - 1, sf))
+                slope = (ymin - ymax) / (xmin - xmax)
+                lin = (ymin - slope * xmin, slope)
+                slots = [_from_i64(int(x)) for x in self.bufs["sums"].view(torch.int64)[8:12]]
+                assert slots[0] != U64 and slots[2] != U64, "cubic: find(..).unwrap() on None"
+                lo, key_lo = slots[0], slots[1]
+                ip, key_ip = ((~slots[2]) & U64) - 1, (~slots[3]) & U64
+                sc = lambda v, mn, mx: (v - mn) / (mx - mn)          # noqa: E731
+                m1 = (sc(float(_scale(lo, sf)), ymin, ymax) - 0.0) / (sc(float(key_lo), xmin, xmax) - 0.0)
+                m2 = (1.0 - sc(float(_scale(ip, sf)), ymin, ymax)) / (1.0 - sc(float(key_ip), xmin, xmax))
+                if m1 * m1 + m2 * m2 > 9.0:
+                    tau = 3.0 / math.sqrt(m1 * m1 + m2 * m2)
+                    m1 *= tau
+                    m2 *= tau
+                d3 = math.pow(xmax - xmin, 3.0)
+                a = (m1 + m2 - 2.0) / d3
+                b = -(xmax * (2.0 * m1 + m2 - 3.0) + xmin * (m1 + 2.0 * m2 - 3.0)) / d3
+                c = (m1 * (xmax * xmax) + m2 * (xmin * xmin) + xmax * xmin * (2.0 * m1 + 2.0 * m2 - 6.0)) / d3
+                d = -xmin * (m1 * (xmax * xmax) + xmax * xmin * (m2 - 3.0) + xmin * xmin) / d3
+                dy = ymax - ymin
+                cub = (a * dy, b * dy, c * dy, d * dy + ymin)
+            self._cand = (cub, lin)
+            items = list(range(self.n_local))
+            if self.info["is_last"] and self.n_local:
+                items.append(self.n_local - 1)
+            for i in items:
+                x, y = float(k[i]), float(_scale(self.gF(i, k), self.sf))
+                a, b, c, d = cub
+                sums[0] += abs(_fma(_fma(_fma(a, x, b), x, c), x, d) - y)
+                sums[1] += abs(_fma(lin[1], x, lin[0]) - y)
+        else:   # normal / lognormal: mean from the reduced sum, then the local sum of squares
+            mean = (float(self.bufs["sums"][0]) + float(self.n + 1) * self._npx) / float(self.n)
+            self._mean = mean
+            sums[0] = sum((self._nx(int(v)) - mean) ** 2 for v in k)
+            if self.info["is_last"] and self.n_local:
+                sums[0] += (self._nx(int(k[-1])) - mean) ** 2
+        self.bufs["sums"][:8] = torch.from_numpy(sums)
 
     def _top_finish(self):
         if self.top_name in ("linear", "robust_linear"):
@@ -131,6 +263,13 @@ class NumpyShardEngine:
             beta = cov / var
             alpha = (py + my) - beta * (px + mx)
             self.top = ("linear", alpha, beta)
+        elif self.top_name == "cubic":
+            cub, lin = self._cand
+            our, lin_err = self.bufs["sums"][:2].tolist()
+            self.top = ("cubic", (0.0, 0.0, lin[1], lin[0]) if lin_err < our else cub)
+        elif self.top_name in ("normal", "lognormal"):
+            stdev = math.sqrt(float(self.bufs["sums"][0]) / float(self.n))
+            self.top = (self.top_name, (self._mean, stdev, float(_scale(self.info["last_F"], self.sf))))
         elif self.top_name == "linear_spline":
             k0, k1 = self.info["first_key_bits"], self.info["last_key_bits"]
             y0, y1 = float(_scale(0, self.sf)), float(_scale(self.n - 1, self.sf))
@@ -151,6 +290,9 @@ class NumpyShardEngine:
     def _bounds(self):
         k = self.keys(self.n_local)
         t = [min(self.N - 1, self.top_predict(int(x))) for x in k]
+        if any(b < a for a, b in zip(t, t[1:])) or (
+                t and self.info["has_prev"] and t[0] < min(self.N - 1, self.top_predict(self.info["prev_key_bits"]))):
+            self.status |= 2          # two_layer.rs:50 assert!(target >= last_target)
         S = np.full(self.N + 1, self.n, dtype=np.int64)
         S[0] = 0
         for j in range(1, self.N):
@@ -259,7 +401,7 @@ class NumpyShardEngine:
         m_err = int(err.max())
         m_idx = int(np.flatnonzero(err == err.max())[-1])
         t = self.top
-        fp = np.array([t[1], t[2]]) if t[0] == "linear" else np.zeros(0)
+        fp = np.array([t[1], t[2]]) if t[0] == "linear" else (np.array(t[1]) if t[0] in ("cubic", "normal", "lognormal") else np.zeros(0))
         ip = np.array([t[1], t[2]], dtype=np.uint64) if t[0] == "radix" else np.zeros(0, dtype=np.uint64)
         return api.TrainedRMI(
             num_rmi_rows=n, num_data_rows=n, branching_factor=N,

@@ -50,3 +50,17 @@ def test_errors_without_a_device_are_reported_not_fatal():
         assert "rmi_b200 error 3" in str(e)   # RMI_ERR_CUDA, with the CUDA message
     else:
         raise AssertionError("dataset creation must fail loudly without a GPU")
+
+
+def test_shard_top_rounds_agree_with_the_orchestrator():
+    """rmi_shard_top_rounds (the C side's statement of which collectives a top model needs) and
+    rmi_b200/sharded.py's TOP_ROUNDS must describe the same protocol."""
+    from rmi_b200 import build, sharded
+    lib = ctypes.CDLL(build.build_library())
+    lib.rmi_shard_top_rounds.argtypes = [ctypes.c_char_p]
+    lib.rmi_shard_top_rounds.restype = ctypes.c_int
+    code = {(): 0, ("sum",): 1, ("sum", "sum"): 2, ("min", "sum"): 3}
+    for name in ("linear", "robust_linear", "linear_spline", "cubic", "loglinear", "normal", "lognormal", "radix",
+                 "radix18", "bradix", "histogram", "no_such_model"):
+        want = code[sharded.TOP_ROUNDS[name]] if name in sharded.TOP_ROUNDS else -1
+        assert lib.rmi_shard_top_rounds(name.encode()) == want, name

@@ -54,10 +54,12 @@ def _worker(rank, world, port, kind, n, spec, N, uneven, out_q):
         from tests.shard_engine_numpy import NumpyShardedData
         keys = _make_keys(kind, n)
         c = _cuts(n, world, uneven)
-        data = NumpyShardedData(keys[c[rank]:c[rank + 1]].copy())
+        data = NumpyShardedData(keys[c[rank]:c[rank + 1]].copy(), halo_capacity=n)
         g = sharded.train_sharded(data, spec, N)
         top = spec.split(",")[0]
-        if top in ("linear", "robust_linear"):
+        if top in ("linear", "robust_linear", "normal", "lognormal", "cubic"):
+            # order-dependent sums (and libm's pow for cubic): coefficients within tolerance, and
+            # with the same coefficients everything downstream bit for bit
             o_ref = oracle.train(keys, spec, N)
             parity.assert_top_equal(g, o_ref, exact=False, N=N)
             o = oracle.train(keys, spec, N, l0_override=g.l0_fparams)
@@ -89,6 +91,11 @@ CASES = [
     (3, "lognormal", "linear_spline,linear_spline", 64, False),
     (2, "uniform", "radix,cubic", 32, True),
     (2, "lognormal", "robust_linear,linear", 16, False),
+    (2, "uniform", "cubic,linear", 64, True),
+    (3, "dups", "cubic,linear", 48, False),
+    (3, "lognormal", "cubic,linear_spline", 32, True),
+    (2, "uniform", "normal,linear", 32, False),
+    (3, "lognormal", "lognormal,linear", 32, True),
 ]
 
 
