@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -348,6 +349,43 @@ void rmi_result_free(rmi_result* r) { delete reinterpret_cast<ResultBox*>(r); }
 
 namespace {
 
+// Streams / events of the sliced leaf launch (kernels.h: LeafCopyOut), created once per host
+// thread and device and reused by every rmi_train call of that thread.
+struct SliceResources {
+  int device = -1;
+  LeafCopyOut co;
+  void release() {
+    if (device < 0) return;
+    for (int c = 0; c < MAX_LEAF_SLICES; ++c) {
+      if (co.streams[c]) cudaStreamDestroy(co.streams[c]);
+      if (co.ev_kernel[c]) cudaEventDestroy(co.ev_kernel[c]);
+      if (co.ev_copied[c]) cudaEventDestroy(co.ev_copied[c]);
+    }
+    if (co.ev_ready) cudaEventDestroy(co.ev_ready);
+    co = LeafCopyOut();
+    device = -1;
+  }
+  LeafCopyOut* get(int dev) {
+    if (device == dev) return &co;
+    release();
+    bool ok = cudaEventCreateWithFlags(&co.ev_ready, cudaEventDisableTiming) == cudaSuccess;
+    for (int c = 0; c < MAX_LEAF_SLICES && ok; ++c)
+      ok = cudaStreamCreateWithFlags(&co.streams[c], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&co.ev_kernel[c], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&co.ev_copied[c], cudaEventDisableTiming) == cudaSuccess;
+    device = dev;
+    if (!ok) { release(); cudaGetLastError(); return nullptr; }
+    return &co;
+  }
+  ~SliceResources() {}   // process exit: the driver reclaims them (destroying here could run after CUDA shut down)
+};
+thread_local SliceResources t_slices;
+
+int leaf_slices_default() {
+  static const int k = [] { const char* e = getenv("RMI_DEV_LEAF_SLICES"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > MAX_LEAF_SLICES ? MAX_LEAF_SLICES : v); }();
+  return k;
+}
+
 struct Arena {   // stream-ordered scratch; everything is released when the call ends
   cudaStream_t st;
   std::vector<void*> ptrs;
@@ -442,6 +480,7 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
       cudaMemcpyAsync(d_top, &h_top, sizeof(h_top), cudaMemcpyHostToDevice, st);
       cudaMemsetAsync(d_aux, 0, sizeof(BuildAux), st);
       unsigned host_status = 0;
+      bool leaf_results_copied = false;
       bool exact = (flags & RMI_FLAG_TOP_FIT_EXACT) != 0;
       if (!l0_over)
         host_status = fit_top_model<T>(L, keys, n, top.kind, top.table_bits, N, exact, d_top, d_aux, d_scratch, d_table,
@@ -454,6 +493,15 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
         {
           Shard<T> whole = whole_array<T>(n);
           whole.no_dups = ds->no_dups ? 1 : 0;
+          // leaf results go to the host slice by slice while later slices compute (kernels.h: LeafCopyOut)
+          LeafCopyOut* co = stats_only ? nullptr : t_slices.get(ds->device);
+          if (co) {
+            co->h_params = box->l1_params.data(); co->h_errors = reinterpret_cast<u64*>(box->l1_errors.data());
+            co->h_counts = want_counts ? reinterpret_cast<u64*>(box->l1_counts.data()) : nullptr;
+            co->slices = leaf_slices_default(); co->used = 0;
+            L.copy = co;
+            leaf_results_copied = true;
+          }
           fit_leaves<T>(L, keys, whole, leaf.kind, N, d_S, d_aux, d_params, d_errors, d_counts);
         }
         cudaEventRecord(evp[2], st);
@@ -469,7 +517,8 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
       memset(&h_aux, 0, sizeof(h_aux));
       cudaMemcpyAsync(&h_aux, d_aux, sizeof(h_aux), cudaMemcpyDeviceToHost, st);
       cudaMemcpyAsync(&h_top_back, d_top, sizeof(h_top), cudaMemcpyDeviceToHost, st);
-      if (host_status == 0 && !stats_only) {
+      leaf_copy_join(L);   // slice copies issued by fit_leaves
+      if (host_status == 0 && !stats_only && !leaf_results_copied) {
         cudaMemcpyAsync(box->l1_params.data(), d_params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(box->l1_errors.data(), d_errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
         if (want_counts) cudaMemcpyAsync(box->l1_counts.data(), d_counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);

@@ -62,9 +62,29 @@ template <class T> inline Shard<T> whole_array(u64 n) {
   return s;
 }
 
+// Optional: hand the leaf results to the host slice by slice while later slices still compute
+// (N x (8*ppm + 8) bytes cross PCIe in about the time the leaf kernel itself takes; copied after
+// the kernel they would add ~45% to a 200M-key build).  The bulk leaf kernel is launched as
+// `slices` consecutive block ranges on separate streams (so a slice's tail overlaps the next
+// slice's start); each slice's parameter / error (/ count) ranges are copied to pinned host
+// memory on the slice's stream as soon as the slice is done.
+constexpr int MAX_LEAF_SLICES = 16;
+struct LeafCopyOut {
+  double* h_params = nullptr;   // N x ppm (pinned)
+  u64* h_errors = nullptr;      // N
+  u64* h_counts = nullptr;      // N or null
+  int slices = 0;               // <= 1: disabled
+  cudaStream_t streams[MAX_LEAF_SLICES] = {};
+  cudaEvent_t ev_ready = nullptr;                 // main stream: leaf boundaries are final
+  cudaEvent_t ev_kernel[MAX_LEAF_SLICES] = {};    // slice kernel finished
+  cudaEvent_t ev_copied[MAX_LEAF_SLICES] = {};    // slice results are on the host
+  mutable int used = 0;                           // slices actually launched (set by fit_leaves)
+};
+
 struct Launch {
   cudaStream_t stream;
   int num_sms;
+  const LeafCopyOut* copy = nullptr;   // optional sliced launch + overlapped result copies (fit_leaves)
   // optional fork/join resources for the long-leaf kernel (kernels_leaf.cu); all null = disabled
   cudaStream_t side = nullptr;       // high-priority stream
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -100,6 +120,8 @@ void compute_leaf_bounds(const Launch& L, const T* keys, u64 n, int top_kind, co
 template <class T>
 void fit_leaves(const Launch& L, const T* keys, const Shard<T>& shard, int leaf_kind, u64 num_leaves, const u64* d_S,
                 BuildAux* d_aux, double* d_params, u64* d_errors, u64* d_counts);
+// After fit_leaves with L.copy set: makes L.stream wait until every slice's results are on the host.
+void leaf_copy_join(const Launch& L);
 // Summary statistics over the N leaves (two_layer.rs:267-284) into d_aux.
 void leaf_statistics(const Launch& L, u64 n, u64 num_leaves, const u64* d_errors, const u64* d_counts,
                      BuildAux* d_aux, void* scratch);

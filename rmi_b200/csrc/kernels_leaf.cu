@@ -155,6 +155,14 @@ constexpr int ROW_BYTES = 144;   // 128 B of keys + 16 B pad: rows stay 16-byte 
 constexpr int SSTAGES = RMI_SSTAGES;
 constexpr int WARP_STREAM_BYTES = SSTAGES * 32 * ROW_BYTES + 32 * 4 + 32 * 4;
 
+// createpolicy for an L2 eviction priority: 0 evict_normal, 1 evict_first, 2 evict_last.
+__device__ __forceinline__ u64 l2_policy_of(int kind) {
+  u64 p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
@@ -166,14 +174,17 @@ template <int N_> __device__ __forceinline__ void cp_async_wait() {
 
 // Calls fn(key, index) for index = b .. e-1 of THIS lane's range (I = u32 or u64 index type),
 // all 32 lanes of the warp taking part in the copies.  Must be called by every lane of the
-// warp (empty ranges allowed).  `keys` must be 16-byte aligned.
+// warp (empty ranges allowed).  `keys` must be 16-byte aligned.  `l2_policy` is the L2 eviction
+// policy of the copies (l2_policy_of): a leaf's keys are read twice, by the fit pass and — one
+// whole leaf later — by the forward pass, so the first read asks L2 to keep the lines and the
+// second one releases them.
 // With SOLO = true the pass stops as soon as exactly one lane still has at least SOLO_MIN keys
 // to go and every other lane is done; it then reports that lane and the index it stopped at
 // (*solo_lane = -1 if the pass ran to completion), so that the caller can finish the long
 // leaf with solo_pass(), where the whole warp serves the one remaining chain.
 constexpr int SOLO_MIN = 384;
 template <class T, class I, class Fn, bool SOLO = false>
-__device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_keys, unsigned char* wsm, I b, I e,
+__device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_policy, unsigned char* wsm, I b, I e,
                                             Fn&& fn, int* solo_lane = nullptr, I* solo_resume = nullptr) {
   constexpr int KPP = 16 / (int)sizeof(T);   // keys per 16-byte piece
   constexpr int SW = 8 * KPP;                // keys per row per chunk
@@ -198,7 +209,6 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
   rowg[lane] = (u32)((u64)a / KPP);
   rownp[lane] = (u32)(((u64)rlen + KPP - 1) / KPP);
   __syncwarp();
-  (void)n_keys;
   const int prow = lane >> 3, piece = lane & 7;
   u32 g0[8], np[8];   // this lane's 8 (row, piece) streams: first piece index, pieces available
 #pragma unroll
@@ -222,8 +232,8 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 n_ke
     for (int q = 0; q < 8; ++q) {
       u64 src;
       asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(src) : "r"(g0[q]), "l"(cb));
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n"
-                   ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)), "l"(src), "r"(c), "r"(np[q]) : "memory");
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %4;\n\t}\n"
+                   ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)), "l"(src), "r"(c), "r"(np[q]), "l"(l2_policy) : "memory");
     }
     cp_async_commit();
   };
@@ -593,8 +603,9 @@ __device__ __forceinline__ void solo_chain(const T* __restrict__ keys, I s_b, I 
 // no leaf or an empty vector).
 template <class T, class I, int LEAF, bool DUPS>
 __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard<T>& sh, unsigned char* wsm,
-                                         const LeafRange<T, I>& r, const double* rcp, double* f, unsigned& bad) {
-  const u64 n_keys = sh.n_avail;
+                                         const LeafRange<T, I>& r, const double* rcp, double* f, unsigned& bad,
+                                         u64 l2_policy) {
+  const u64 n_keys = l2_policy;   // handed to every stream_pass below
   const I L = (I)(r.ve - r.vs) + (r.p_remote ? (I)1 : (I)0);
   const T kfirst = r.p_remote ? r.pkey : (L ? keys[r.vs] : T());
   const double vsd = __ull2double_rn(r.vs_global), f0d = __ull2double_rn(r.F0);
@@ -871,7 +882,7 @@ template <class T, class I, int LEAF, bool DUPS>
 __global__ void __launch_bounds__(LEAF_THREADS)
 k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restrict__ S, BuildAux* aux,
        double* __restrict__ params, u64* __restrict__ errors, u64* __restrict__ counts,
-       const u32* __restrict__ long_list, int long_mode) {
+       const u32* __restrict__ long_list, int mode_word, u32 block_offset, u32 total_blocks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_rcp = reinterpret_cast<double*>(smem_raw);
   unsigned char* wsm = smem_raw + (size_t)RCP_TABLE * sizeof(double) + (size_t)(threadIdx.x >> 5) * WARP_STREAM_BYTES;
@@ -885,8 +896,14 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   // long_mode 0: the ordinary kernel, which leaves those leaves to the long-leaf kernel.
   const u32 n_long = long_list ? long_list[0] : 0u;
   const bool long_active = LEAF == M_LINEAR && long_list != nullptr && n_long > 0 && n_long <= LONG_LEAF_CAP;
+  // mode_word: bits 0-3 long_mode, bits 4-5 / 6-7 L2 eviction priority of the fit / forward pass copies
+  const int long_mode = mode_word & 0xf;
   if (long_mode == 1 && (!long_active || blockIdx.x >= n_long)) return;
-  const u64 group = (blockIdx.x & 1u) ? (u64)gridDim.x - 1 - (blockIdx.x >> 1) : (u64)(blockIdx.x >> 1);
+  // The bulk kernel may be launched as several consecutive slices of the block range
+  // [block_offset, block_offset + gridDim.x) of total_blocks (results of a slice are copied to
+  // the host while the next slice computes); slice 0 starts with the outermost groups.
+  const u32 gb = blockIdx.x + block_offset;
+  const u64 group = (gb & 1u) ? (u64)total_blocks - 1 - (gb >> 1) : (u64)(gb >> 1);
   const u64 j = long_mode == 1 ? (threadIdx.x == 0 ? (u64)long_list[1 + blockIdx.x] : N)
                                : group * blockDim.x + threadIdx.x;
   constexpr int PPM = leaf_params_per_model(LEAF);
@@ -947,7 +964,8 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   if (live && g_hi > sh.base + sh.n_avail) { bad |= ST_HALO_TOO_SMALL; r.hi = r.lo; }
 
   double f[4] = {0.0, 0.0, 0.0, 0.0};
-  fit_leaf<T, I, LEAF, DUPS>(keys, sh, wsm, r, s_rcp, f, bad);
+  fit_leaf<T, I, LEAF, DUPS>(keys, sh, wsm, r, s_rcp, f, bad, l2_policy_of((mode_word >> 4) & 3));
+  const u64 pol_fwd = l2_policy_of((mode_word >> 6) & 3);
 
   // two_layer.rs:186-197: empty leaves (lower-bound-correction sense) except the last
   const u64 next_idx = g_hi;                                        // lb.next_index(j) = S[j+1]
@@ -981,7 +999,7 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
     T pk = (live && g_lo == 0 && g_hi > 0) ? keys[0] : prev_key;
     I F = (I)g_lo, run = 0;
     if (DUPS) {
-      stream_pass<T, I>(keys, sh.n_avail, wsm, r.lo, long_leaf ? r.lo : r.hi, [&](T k, I i) {
+      stream_pass<T, I>(keys, pol_fwd, wsm, r.lo, long_leaf ? r.lo : r.hi, [&](T k, I i) {
         if (k != pk) { run_max = run > run_max ? run : run_max; run = 0; F = (I)(i + baseI); }
         run += 1;
         pk = k;
@@ -993,7 +1011,7 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
     } else {
       // no two keys of the data set are equal: the offset of a key is its index, every run has
       // length 1 (and the data set's final run is never recorded)
-      stream_pass<T, I>(keys, sh.n_avail, wsm, r.lo, long_leaf ? r.lo : r.hi, [&](T k, I i) {
+      stream_pass<T, I>(keys, pol_fwd, wsm, r.lo, long_leaf ? r.lo : r.hi, [&](T k, I i) {
         I Fi = (I)(i + baseI);
         I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
         I e = pred > Fi ? pred - Fi : Fi - pred;
@@ -1238,6 +1256,14 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
   u64 blocks = (N + LEAF_THREADS - 1) / LEAF_THREADS;
   static const size_t pad = [] { const char* e = getenv("RMI_DEV_LEAF_SMEM_PAD"); return e ? (size_t)atol(e) : (size_t)0; }();
   const size_t smem = leaf_smem_bytes() + pad;   // dev knob: extra shared memory = fewer resident blocks
+  // L2 eviction priority of the key copies: fit pass (bits 4-5), forward pass (bits 6-7);
+  // 0 normal, 1 evict_first, 2 evict_last.  Default: keep what the fit pass read, release after the re-read.
+  static const int l2_mode = [] {
+    const char* e = getenv("RMI_DEV_L2_HINT");
+    int fit = 2, fwd = 1;
+    if (e && e[0] && e[1]) { fit = (e[0] - '0') & 3; fwd = (e[1] - '0') & 3; }
+    return (fit << 4) | (fwd << 6);
+  }();
   cudaFuncSetAttribute(k_leaf<T, I, LEAF, DUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LONG_LEAF_SMEM);
   const bool fork = LEAF == M_LINEAR && L.side && L.ev_fork && L.ev_join && L.d_long && N < 0xffffffffull;
   if (fork) {
@@ -1250,13 +1276,70 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
     count_launch();
     cudaEventRecord(L.ev_fork, L.stream);
     cudaStreamWaitEvent(L.side, L.ev_fork, 0);
-    k_leaf<T, I, LEAF, DUPS><<<LONG_LEAF_CAP, 32, LONG_LEAF_SMEM, L.side>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts, L.d_long, 1);
+    k_leaf<T, I, LEAF, DUPS><<<LONG_LEAF_CAP, 32, LONG_LEAF_SMEM, L.side>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts, L.d_long,
+                                                                            1 | l2_mode, 0u, LONG_LEAF_CAP);
     count_launch();
     cudaEventRecord(L.ev_join, L.side);
   }
-  k_leaf<T, I, LEAF, DUPS><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts,
-                                                                              fork ? L.d_long : nullptr, 0);
-  count_launch();
+  const u32* long_list = fork ? L.d_long : nullptr;
+  const LeafCopyOut* co = L.copy;
+  int K = (co && co->slices > 1) ? (co->slices < MAX_LEAF_SLICES ? co->slices : MAX_LEAF_SLICES) : 1;
+  if (blocks < (u64)K * 64 || blocks >= 0xffffffffull) K = 1;   // too small to be worth slicing
+  if (K == 1) {
+    k_leaf<T, I, LEAF, DUPS><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts,
+                                                                                long_list, l2_mode, 0u, (u32)blocks);
+    count_launch();
+    if (fork) cudaStreamWaitEvent(L.stream, L.ev_join, 0);
+    if (co) {
+      co->used = 0;
+      if (co->h_params) {   // unsliced, but the caller still expects the results on the host
+        constexpr int PPM = leaf_params_per_model(LEAF);
+        cudaMemcpyAsync(co->h_params, d_params, sizeof(double) * N * PPM, cudaMemcpyDeviceToHost, L.stream);
+        cudaMemcpyAsync(co->h_errors, d_errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, L.stream);
+        if (co->h_counts) cudaMemcpyAsync(co->h_counts, d_counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, L.stream);
+      }
+    }
+    return;
+  }
+  // ---- sliced launch: slice c = blocks [c*per, (c+1)*per) of the front/back-alternating block order,
+  // i.e. leaf groups [c*per/2, (c+1)*per/2) from the front and the mirrored range from the back ----
+  constexpr int PPM = leaf_params_per_model(LEAF);
+  const u32 total = (u32)blocks;
+  const u32 per = (u32)((((blocks + K - 1) / K) + 1) & ~1ull);   // even
+  cudaEventRecord(co->ev_ready, L.stream);
+  int used = 0;
+  for (int c = 0; c < K; ++c) {
+    const u32 off = (u32)c * per;
+    if (off >= total) break;
+    const u32 cnt = total - off < per ? total - off : per;
+    cudaStream_t st = co->streams[c];
+    cudaStreamWaitEvent(st, co->ev_ready, 0);
+    k_leaf<T, I, LEAF, DUPS><<<cnt, LEAF_THREADS, smem, st>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts, long_list,
+                                                              l2_mode, off, total);
+    count_launch();
+    cudaEventRecord(co->ev_kernel[c], st);
+    cudaStreamWaitEvent(L.stream, co->ev_kernel[c], 0);
+    if (fork) cudaStreamWaitEvent(st, L.ev_join, 0);   // long leaves (built on the side stream) may lie in any slice
+    // groups of this slice: even block ids -> front groups, odd ones -> back groups
+    const u64 f0 = off / 2, f1 = (off + cnt + 1) / 2;                 // front groups [f0, f1)
+    const u64 nb = (off + cnt) / 2 - off / 2;                          // number of odd ids in [off, off+cnt) (off is even)
+    const u64 b1 = (u64)total - off / 2, b0 = b1 - nb;                 // back groups [b0, b1)
+    auto copy_groups = [&](u64 g0, u64 g1) {
+      u64 l0 = g0 * LEAF_THREADS, l1 = g1 * LEAF_THREADS;
+      if (l1 > N) l1 = N;
+      if (l0 >= l1) return;
+      cudaMemcpyAsync(co->h_params + l0 * PPM, d_params + l0 * PPM, sizeof(double) * (l1 - l0) * PPM, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(co->h_errors + l0, d_errors + l0, sizeof(u64) * (l1 - l0), cudaMemcpyDeviceToHost, st);
+      if (co->h_counts) cudaMemcpyAsync(co->h_counts + l0, d_counts + l0, sizeof(u64) * (l1 - l0), cudaMemcpyDeviceToHost, st);
+    };
+    // a front and a back range can only meet in the last slice; never copy a leaf twice
+    const u64 fe = f1 < b0 ? f1 : b0;
+    copy_groups(f0, fe);
+    copy_groups(b0, b1);
+    cudaEventRecord(co->ev_copied[c], st);
+    ++used;
+  }
+  co->used = used;
   if (fork) cudaStreamWaitEvent(L.stream, L.ev_join, 0);
 }
 template <class T, int LEAF>
@@ -1336,6 +1419,11 @@ template <class T> void check_sorted(const Launch& L, const T* keys, u64 n, u64 
 template void check_sorted<u64>(const Launch&, const u64*, u64, u64, u64, unsigned*);
 template void check_sorted<u32>(const Launch&, const u32*, u64, u64, u64, unsigned*);
 template void check_sorted<double>(const Launch&, const double*, u64, u64, u64, unsigned*);
+
+void leaf_copy_join(const Launch& L) {
+  if (!L.copy) return;
+  for (int c = 0; c < L.copy->used; ++c) cudaStreamWaitEvent(L.stream, L.copy->ev_copied[c], 0);
+}
 
 size_t stats_scratch_bytes(u64) { return sizeof(StatsPartial) * STATS_MAX_BLOCKS; }
 
