@@ -22,8 +22,17 @@
 #include <vector>
 
 #include "../include/rmi_b200.h"
+#include "cache_fix.hpp"
 
 namespace rmihost {
+
+// TrainedRMI.cache_fix (train/mod.rs:31) of a `--bounded` build: the spline's knots, the line
+// size, and the length of the ORIGINAL data set (train_bounded, train/mod.rs:175-176).
+struct CacheFixInfo {
+  uint64_t line_size = 0;
+  const std::vector<SplinePoint>* spline = nullptr;
+  uint64_t num_data_rows = 0;
+};
 
 // ---- ModelParam (models/mod.rs:509-674) ------------------------------------------------------
 struct Param {
@@ -287,13 +296,48 @@ inline std::vector<Param> top_params(const rmi_result& r) {   // Model::params()
   return p;
 }
 
-// codegen.rs:375-394 (no cache-fix in this build)
-inline uint64_t rmi_size(const rmi_result& r, bool with_errors) {
+// codegen.rs:375-394
+inline uint64_t rmi_size(const rmi_result& r, bool with_errors, const CacheFixInfo* cf = nullptr) {
   uint64_t total = 0;
   for (auto& p : top_params(r)) total += p.size();
   total += (uint64_t)r.l1_params_per_model * 8 * r.branching_factor;
   if (with_errors) total += r.branching_factor * 8;
+  if (cf) total += (uint64_t)cf->spline->size() * 16;
   return total;
+}
+
+// codegen.rs:396-448 generate_cache_fix_code: the public lookup() of a `--bounded` RMI — the RMI
+// finds the spline segment, the segment interpolates the position, rounded down to its line.
+inline void generate_cache_fix_code(std::ostream& t, const CacheFixInfo& cf, const std::string& array_name) {
+  const std::string ls = std::to_string(cf.line_size);
+  t << "\nstruct __attribute__((packed)) SplinePoint {\n  uint64_t key;\n  uint64_t value;\n};\n\n"
+       "uint64_t lookup(uint64_t key, size_t* err) {\n"
+       "  const uint64_t num_spline_pts = " << cf.spline->size() << ";\n"
+       "  const uint64_t total_keys = " << cf.num_data_rows << ";\n"
+       "  size_t error_on_spline_search;\n\n"
+       "  struct SplinePoint* begin = (struct SplinePoint*) " << array_name << ";\n\n"
+       "  *err = " << ls << ";\n"
+       "  uint64_t start = _rmi_lookup_pre_cachefix(key, &error_on_spline_search);\n\n"
+       "  size_t upper = (start + error_on_spline_search > num_spline_pts\n"
+       "                  ? num_spline_pts : start + error_on_spline_search);\n"
+       "  size_t lower = (error_on_spline_search > start\n"
+       "                  ? 0 : start - error_on_spline_search);\n"
+       "                  \n"
+       "  \n"
+       "  struct SplinePoint* res = std::lower_bound(begin + lower,\n"
+       "                                             begin + upper,\n"
+       "                                             key,\n"
+       "                                             [](const auto& lhs, const auto rhs) { return lhs.key < rhs; });\n\n"
+       "  if (res == begin + num_spline_pts)\n"
+       "    // we've searched for something past the last point\n"
+       "    return total_keys - 1;\n\n"
+       "  auto pt1 = *(res - 1);\n"
+       "  auto pt2 = *res;\n\n"
+       "  auto v0 = (double)pt1.value;\n"
+       "  auto v1 = (double)pt2.value;\n"
+       "  auto t = ((double)(key - pt1.key)) / (double)(pt2.key - pt1.key);\n"
+       "  return (((uint64_t) std::fma(1.0 - t, v0, t * v1)) / " << ls << ") * " << ls << ";\n"
+       "}\n";
 }
 
 struct KeyTypeInfo { const char* c_type; bool is_float; };
@@ -304,7 +348,8 @@ inline KeyTypeInfo key_type_info(int key_type) {
 
 // codegen.rs:757-788 output_rmi + :450-754 generate_code.  Files are written relative to `out_dir`.
 inline void output_rmi(const std::string& ns, const rmi_result& r, const std::string& data_dir, int key_type,
-                       bool include_errors, uint64_t build_time_ns, const std::string& out_dir = ".") {
+                       bool include_errors, uint64_t build_time_ns, const std::string& out_dir = ".",
+                       const CacheFixInfo* cache_fix = nullptr) {
   const uint64_t N = r.branching_factor;
   if (!r.l1_params || (include_errors && !r.l1_errors)) throw std::runtime_error("result was trained with STATS_ONLY");
   ModelInfo top = model_info(r.l0_model_id, r.l0_bradix_high != 0, (unsigned)r.l0_iparams[0], r.l0_table_bits);
@@ -339,6 +384,13 @@ inline void output_rmi(const std::string& ns, const rmi_result& r, const std::st
     } else {
       report_line = "  *err = " + std::to_string(r.l1_errors[0]) + ";";
     }
+  }
+
+  if (cache_fix) {   // codegen.rs:487-496: the knots become one more parameter array, {key, offset} per knot
+    std::vector<Param> cfv;
+    cfv.reserve(cache_fix->spline->size() * 2);
+    for (const auto& pt : *cache_fix->spline) { cfv.push_back(Param::make_int(pt.first)); cfv.push_back(Param::make_int(pt.second)); }
+    layers.push_back(LayerParams::make(layers.size(), true, 2, cfv));
   }
 
   std::ofstream code(out_dir + "/" + ns + ".cpp"), data(out_dir + "/" + ns + "_data.h"), header(out_dir + "/" + ns + ".h");
@@ -379,6 +431,7 @@ inline void output_rmi(const std::string& ns, const rmi_result& r, const std::st
 
   code << "#include \"" << ns << ".h\"\n" << "#include \"" << ns << "_data.h\"\n" << "#include <math.h>\n#include <cmath>\n#include <fstream>\n"
        << "#include <filesystem>\n#include <iostream>\n";
+  if (cache_fix) code << "#include <algorithm>\n";   // :580-582
   code << "namespace " << ns << " {\n";
   for (auto& l : read_code) code << l << "\n";
   for (auto& l : free_code) code << l << "\n";
@@ -391,8 +444,9 @@ inline void output_rmi(const std::string& ns, const rmi_result& r, const std::st
   code << "\ninline size_t FCLAMP(double inp, double bound) {\n  if (inp < 0.0) return 0;\n  return (inp > bound ? bound : (size_t)inp);\n}\n\n";
 
   KeyTypeInfo kt = key_type_info(key_type);
-  std::string lookup_sig = report_lle ? std::string("uint64_t lookup(") + kt.c_type + " key, size_t* err)"
-                                      : std::string("uint64_t lookup(") + kt.c_type + " key)";
+  const std::string lookup_name = cache_fix ? "_rmi_lookup_pre_cachefix" : "lookup";   // :621-625
+  std::string lookup_sig = report_lle ? "uint64_t " + lookup_name + "(" + kt.c_type + " key, size_t* err)"
+                                      : "uint64_t " + lookup_name + "(" + kt.c_type + " key)";
   code << lookup_sig << " {\n";
   std::vector<std::string> vars;
   add_unique(vars, "size_t modelIndex;");
@@ -419,15 +473,17 @@ inline void output_rmi(const std::string& ns, const rmi_result& r, const std::st
   code << report_line << "\n";
   code << "  return " << model_index_from_output(leaf.output_float, r.num_rmi_rows, true) << ";\n";
   code << "}\n";
+  if (cache_fix) generate_cache_fix_code(code, *cache_fix, layers.back().array_name());   // :720-722
   code << "} // namespace\n";
 
   header << "#include <cstddef>\n#include <cstdint>\n";
   header << "namespace " << ns << " {\n";
   header << "bool load(char const* dataPath);\nvoid cleanup();\n";
-  header << "const size_t RMI_SIZE = " << rmi_size(r, include_errors) << ";\n";
+  header << "const size_t RMI_SIZE = " << rmi_size(r, include_errors, cache_fix) << ";\n";
   header << "const uint64_t BUILD_TIME_NS = " << build_time_ns << ";\n";
   header << "const char NAME[] = \"" << ns << "\";\n";
-  header << lookup_sig << ";\n";
+  if (cache_fix) header << "uint64_t lookup(uint64_t key, size_t* err);\n";   // :746-750
+  else header << lookup_sig << ";\n";
   header << "}\n";
 }
 

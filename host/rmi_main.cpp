@@ -2,12 +2,16 @@
 //   rmi <input> [namespace] [models] [branching factor]
 //       [--no-code] [--param-grid <file>] [--data-path|-d <dir>] [--no-errors] [--threads|-t <n>]
 //       [--max-size <bytes>] [--disable-parallel-training] [--zero-build-time] [--optimize <file>]
+//       [--bounded <line_size>]
 // plus  --exact-top-fit (RMI_FLAG_TOP_FIT_EXACT) and --device <n>.
 // The build itself is librmi_b200.so (CUDA); this binary only loads the data set into HBM,
-// calls rmi_train and writes the artefacts (codegen.hpp).  `--bounded` (cache-fix, a serial
-// CPU pre-pass in the reference) is not offered.  There is no CPU training path: without a
-// usable GPU every build fails with the CUDA error text.
+// calls rmi_train and writes the artefacts (codegen.hpp).  `--bounded` runs the reference's
+// serial cache-fix scan on the host (cache_fix.hpp) and then builds the RMI over the spline's
+// knots on the GPU like any other data set.  There is no CPU training path: without a usable
+// GPU every build fails with the CUDA error text.
 #include <cerrno>
+#include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -141,7 +145,6 @@ int main(int argc, char** argv) {
   const std::string data_dir = a.has("--data-path") ? a.opt["--data-path"] : "rmi_data";
   const bool have_ns = a.pos.size() > 1;
   if (have_ns && a.has("--param-grid")) die("Can only specify one of namespace or param-grid");
-  if (a.has("--bounded")) die("--bounded (cache-fix) is not offered by this build");
   const int device = a.has("--device") ? std::atoi(a.opt["--device"].c_str()) : 0;
   const uint32_t flags = a.has("--exact-top-fit") ? RMI_FLAG_TOP_FIT_EXACT : 0;
   const bool verbose = a.has("--verbose") || std::getenv("RUST_LOG") != nullptr;
@@ -226,6 +229,10 @@ int main(int argc, char** argv) {
   } else if (have_ns) {   // main.rs:263-333
     const std::string ns = a.pos[1];
     rmi_result* r = nullptr;
+    CacheFixInfo cf;
+    std::vector<SplinePoint> spline;
+    bool bounded = false;
+    uint64_t bounded_build_ns = 0;
     if (a.has("--max-size")) {   // train_for_size, train/mod.rs:128-154
       uint64_t max_size = std::strtoull(a.opt["--max-size"].c_str(), nullptr, 10);
       std::vector<RMIStatistics> pareto;
@@ -236,13 +243,46 @@ int main(int argc, char** argv) {
       std::fprintf(stderr, "Found RMI config %s %llu with size %llu and average log2 %g\n", pick->models.c_str(),
                    (unsigned long long)pick->branching_factor, (unsigned long long)pick->size, pick->average_log2_error);
       train_one(pick->models, pick->branching_factor, &r);
+    } else if (a.has("--bounded")) {
+      // train_bounded (train/mod.rs:156-184): the serial cache-fix scan on the host, then the
+      // ordinary GPU build with the spline's knots as the data set (their offsets are 0, 1, 2, ...)
+      if (a.pos.size() < 4) die("called `Option::unwrap()` on a `None` value (models and branching factor are required)");
+      char* endp = nullptr;
+      const std::string ls = a.opt["--bounded"];
+      cf.line_size = std::strtoull(ls.c_str(), &endp, 10);
+      if (ls.empty() || *endp) die("Line size must be a positive integer.");
+      if (file_kt != RMI_KEY_U64) die("Can only construct a bounded RMI on u64 data.");
+      auto t0 = std::chrono::steady_clock::now();
+      std::vector<uint64_t> host_keys(num_rows);
+      {
+        std::ifstream in(fp, std::ios::binary);
+        uint64_t cnt = 0;
+        in.read(reinterpret_cast<char*>(&cnt), 8);
+        in.read(reinterpret_cast<char*>(host_keys.data()), (std::streamsize)(num_rows * 8));
+        if (!in || cnt != num_rows) die("Unable to read the data file at " + fp);
+      }
+      try { spline = cache_fix(host_keys.data(), num_rows, cf.line_size); } catch (std::exception& e) { die(e.what()); }
+      host_keys.clear(); host_keys.shrink_to_fit();
+      std::fprintf(stderr, "Bounded spline compressed data to %.0f%% of original (%zu points, constructed from %llu points).\n",
+                   std::round((double)spline.size() / (double)num_rows * 100.0), spline.size(), (unsigned long long)num_rows);
+      std::vector<uint64_t> knot_keys(spline.size());
+      for (size_t i = 0; i < spline.size(); ++i) knot_keys[i] = spline[i].first;
+      rmi_dataset* kds = nullptr;
+      if (rmi_dataset_create(knot_keys.data(), knot_keys.size(), RMI_KEY_U64, device, &kds) != RMI_OK) die(rmi_last_error());
+      if (rmi_train(kds, a.pos[2].c_str(), std::strtoull(a.pos[3].c_str(), nullptr, 10), flags, &r) != RMI_OK) die(rmi_last_error());
+      rmi_dataset_destroy(kds);
+      cf.spline = &spline;
+      cf.num_data_rows = num_rows;
+      bounded = true;
+      bounded_build_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     } else {
       if (a.pos.size() < 4) die("called `Option::unwrap()` on a `None` value (models and branching factor are required)");
       train_one(a.pos[2], std::strtoull(a.pos[3].c_str(), nullptr, 10), &r);
     }
     print_stats(*r, num_rows);
     if (!a.has("--no-code")) {
-      try { output_rmi(ns, *r, data_dir, code_kt, !a.has("--no-errors"), a.has("--zero-build-time") ? 0 : r->build_time_ns); }
+      const uint64_t bt = a.has("--zero-build-time") ? 0 : (bounded ? bounded_build_ns : r->build_time_ns);
+      try { output_rmi(ns, *r, data_dir, code_kt, !a.has("--no-errors"), bt, ".", bounded ? &cf : nullptr); }
       catch (std::exception& e) { die(e.what()); }
     }
     rmi_result_free(r);

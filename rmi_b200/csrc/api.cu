@@ -381,8 +381,41 @@ struct SliceResources {
 };
 thread_local SliceResources t_slices;
 
+// The build's own stream, the high-priority side stream of the long-leaf kernel and the timing
+// events, likewise kept per host thread and device (creating and destroying two streams and
+// seven events per call cost more host time than the launches of a small build).
+struct BuildContext {
+  int device = -1;
+  cudaStream_t st = nullptr, side = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[3] = {nullptr, nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr;
+  void release() {
+    if (device < 0) return;
+    if (st) cudaStreamDestroy(st);
+    if (side) cudaStreamDestroy(side);
+    for (cudaEvent_t e : {ev0, ev1, evp[0], evp[1], evp[2], ev_fork, ev_join}) if (e) cudaEventDestroy(e);
+    *this = BuildContext();
+  }
+  BuildContext* get(int dev) {
+    if (device == dev) return this;
+    release();
+    int lo_prio = 0, hi_prio = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+    bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess &&
+              cudaEventCreate(&evp[0]) == cudaSuccess && cudaEventCreate(&evp[1]) == cudaSuccess &&
+              cudaEventCreate(&evp[2]) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) == cudaSuccess;
+    if (ok && cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi_prio) != cudaSuccess) { side = nullptr; cudaGetLastError(); }
+    device = dev;
+    if (!ok) { release(); cudaGetLastError(); return nullptr; }
+    return this;
+  }
+};
+thread_local BuildContext t_build_ctx;
+
 int leaf_slices_default() {
-  static const int k = [] { const char* e = getenv("RMI_DEV_LEAF_SLICES"); int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > MAX_LEAF_SLICES ? MAX_LEAF_SLICES : v); }();
+  static const int k = [] { const char* e = getenv("RMI_DEV_LEAF_SLICES"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > MAX_LEAF_SLICES ? MAX_LEAF_SLICES : v); }();
   return k;
 }
 
@@ -411,22 +444,13 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
   DeviceInfo di;
   if (int rc = device_info(ds->device, &di)) return rc;
 
-  cudaStream_t st;
-  CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[3] = {nullptr, nullptr, nullptr};
-  cudaEventCreate(&ev0);
-  cudaEventCreate(&ev1);
-  for (auto& e : evp) cudaEventCreate(&e);
-  // fork/join resources of the long-leaf kernel
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  {
-    int lo_prio = 0, hi_prio = 0;
-    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
-    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi_prio) != cudaSuccess) side = nullptr;
-    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
-  }
+  // stream + events of a build: created once per host thread and device, reused by later calls
+  BuildContext* bc = t_build_ctx.get(ds->device);
+  if (!bc) return fail(RMI_ERR_CUDA, "could not create the build's CUDA streams / events");
+  cudaStream_t st = bc->st;
+  cudaEvent_t ev0 = bc->ev0, ev1 = bc->ev1, *evp = bc->evp;
+  cudaStream_t side = bc->side;
+  cudaEvent_t ev_fork = bc->ev_fork, ev_join = bc->ev_join;
   int rc = RMI_OK;
   auto box = new ResultBox();
   {
@@ -585,13 +609,6 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
     }
   }   // arena frees (stream-ordered)
   cudaStreamSynchronize(st);
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
-  for (auto& e : evp) cudaEventDestroy(e);
-  if (ev_fork) cudaEventDestroy(ev_fork);
-  if (ev_join) cudaEventDestroy(ev_join);
-  if (side) cudaStreamDestroy(side);
-  cudaStreamDestroy(st);
   if (rc != RMI_OK) { delete box; return rc; }
   box->pub.build_time_ns =
       (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_start).count();

@@ -1,17 +1,36 @@
 // Test tool: rebuild an rmi_result from a flat dump (written by tests/test_codegen.py from an
 // oracle- or GPU-trained model) and run the product's code generator (host/codegen.hpp) on it.
 //   codegen_tool <dump.bin> <namespace> <data_dir> <out_dir> <include_errors 0|1> <key_type>
+//                [<spline.bin> <line_size> <num_data_rows>]      (a --bounded RMI, codegen.rs cache_fix)
+//   codegen_tool cachefix <keyfile (reference format, uint64)> <line_size> <spline.bin>
+//                runs host/cache_fix.hpp and writes the knots as (u64 key, u64 offset) pairs
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
+#include <string>
 #include <vector>
 
 #include "../../host/codegen.hpp"
 
 static uint64_t rd(std::ifstream& in) { uint64_t v = 0; in.read((char*)&v, 8); return v; }
 
+static int run_cachefix(char** argv) {
+  std::ifstream in(argv[2], std::ios::binary);
+  uint64_t n = rd(in);
+  std::vector<uint64_t> keys(n);
+  in.read((char*)keys.data(), (std::streamsize)(n * 8));
+  try {
+    auto sp = rmihost::cache_fix(keys.data(), n, std::strtoull(argv[3], nullptr, 10));
+    std::ofstream out(argv[4], std::ios::binary);
+    for (auto& p : sp) { out.write((const char*)&p.first, 8); out.write((const char*)&p.second, 8); }
+  } catch (std::exception& e) { std::fprintf(stderr, "cache_fix: %s\n", e.what()); return 1; }
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc == 5 && std::string(argv[1]) == "cachefix") return run_cachefix(argv);
   if (argc < 7) { std::fprintf(stderr, "usage\n"); return 2; }
   std::ifstream in(argv[1], std::ios::binary);
   rmi_result r{};
@@ -41,8 +60,17 @@ int main(int argc, char** argv) {
   for (auto& v : errs) v = rd(in);
   r.l1_params = params.data();
   r.l1_errors = errs.data();
+  std::vector<rmihost::SplinePoint> spline;
+  rmihost::CacheFixInfo cf;
+  if (argc >= 10) {
+    std::ifstream sp(argv[7], std::ios::binary);
+    for (;;) { uint64_t k = 0, v = 0; sp.read((char*)&k, 8); sp.read((char*)&v, 8); if (!sp) break; spline.emplace_back(k, v); }
+    cf.line_size = std::strtoull(argv[8], nullptr, 10);
+    cf.spline = &spline;
+    cf.num_data_rows = std::strtoull(argv[9], nullptr, 10);
+  }
   try {
-    rmihost::output_rmi(argv[2], r, argv[3], std::atoi(argv[6]), std::atoi(argv[5]) != 0, 0, argv[4]);
+    rmihost::output_rmi(argv[2], r, argv[3], std::atoi(argv[6]), std::atoi(argv[5]) != 0, 0, argv[4], argc >= 10 ? &cf : nullptr);
   } catch (std::exception& e) { std::fprintf(stderr, "codegen: %s\n", e.what()); return 1; }
   return 0;
 }

@@ -1,0 +1,115 @@
+"""`--bounded <line_size>` (reference: cache_fix.rs, train_bounded in train/mod.rs:156-184, the
+cache-fix parts of codegen.rs): the host pre-pass host/cache_fix.hpp against the Python
+restatement oracle/cache_fix.py knot for knot, and the whole flow — knots -> two-layer RMI over
+the knots -> generated code with the spline lookup — against the reference's own property
+(tests/cache_fix_wiki/main.cpp: every key's lookup lands within one line of its lower bound).
+CPU-only: the RMI over the knots comes from the oracle; the GPU test at the bottom runs the
+`rmi` CLI with --bounded end to end."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import datasets
+from tests.test_codegen import ROOT, build_and_check, dump_model, tool, write_keyfile  # noqa: F401  (tool is a fixture)
+
+
+def host_cache_fix(tool_exe, work, keys, line):
+    keyfile = os.path.join(work, "keys_cf.bin")
+    write_keyfile(keyfile, keys)
+    out = os.path.join(work, "spline.bin")
+    r = subprocess.run([tool_exe, "cachefix", keyfile, str(line), out], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    raw = np.fromfile(out, dtype="<u8").reshape(-1, 2)
+    return raw, out
+
+
+DATA = {
+    "uniform": lambda: datasets.uniform_u64(6_000, seed=5),
+    "dups": lambda: datasets.with_duplicates(datasets.uniform_u64(6_000, seed=6), frac=0.3),
+    "lognormal": lambda: datasets.lognormal_u64(6_000, seed=7),
+    "dense": lambda: np.arange(10, 1_510, dtype=np.uint64),                        # consecutive keys: key-1 == last key
+    "steps": lambda: np.sort(np.repeat(np.arange(1, 601, dtype=np.uint64) * 1000, 10)),   # long runs of equal keys
+}
+
+
+@pytest.mark.parametrize("dname", list(DATA))
+@pytest.mark.parametrize("line", [1, 8, 64])
+def test_host_cache_fix_equals_python_restatement(tool, tmp_path, dname, line):
+    from oracle import cache_fix as ocf
+    keys = DATA[dname]()
+    want = ocf.cache_fix(keys.tolist(), line)
+    got, _ = host_cache_fix(tool, str(tmp_path), keys, line)
+    assert got.shape[0] == len(want)
+    assert [tuple(map(int, r)) for r in got] == want
+    # knots: strictly increasing keys, non-decreasing offsets, first knot = (first key - 1 or first key, 0)
+    assert np.all(np.diff(got[:, 0].astype(object)) > 0) and np.all(np.diff(got[:, 1].astype(np.int64)) >= 0)
+    assert int(got[-1, 0]) == int(keys[-1])
+
+
+def test_cache_fix_panics_like_the_reference(tool, tmp_path):
+    from oracle import cache_fix as ocf
+    few = np.arange(1, 6, dtype=np.uint64)
+    with pytest.raises(ocf.CacheFixPanic):
+        ocf.cache_fix(few.tolist(), 8)              # fewer items than the line size (cache_fix.rs:107-108)
+    with pytest.raises(RuntimeError, match="fewer items"):
+        host_cache_fix(tool, str(tmp_path), few, 8)
+    zero = np.arange(0, 100, dtype=np.uint64)       # key 0: key - 1 wraps, with_new_dest's assert fires
+    with pytest.raises(ocf.CacheFixPanic):
+        ocf.cache_fix(zero.tolist(), 4)
+    with pytest.raises(RuntimeError):
+        host_cache_fix(tool, str(tmp_path), zero, 4)
+
+
+@pytest.mark.parametrize("spec,bf,dname,line", [("linear_spline,linear", 64, "uniform", 8), ("cubic,linear", 32, "dups", 8),
+                                                ("radix,linear", 128, "uniform", 4), ("linear,linear", 64, "uniform", 16)])
+def test_bounded_rmi_holds_the_reference_property(oracle, tool, tmp_path, spec, bf, dname, line):
+    keys = DATA[dname]() if dname != "uniform" else datasets.uniform_u64(100_000, seed=8)
+    work = str(tmp_path)
+    os.makedirs(os.path.join(work, "rmi_data"))
+    knots, spline_path = host_cache_fix(tool, work, keys, line)
+    knot_keys = np.ascontiguousarray(knots[:, 0])
+    try:
+        o = oracle.train(knot_keys, spec, bf)       # train_bounded: the RMI indexes the knots (train/mod.rs:165-174)
+    except oracle.OraclePanic as e:
+        pytest.skip(f"reference panics: {e}")
+    dump = os.path.join(work, "model.bin")
+    dump_model(dump, o, spec)
+    subprocess.run([tool, dump, "rmi", os.path.join(work, "rmi_data"), work, "1", "0", spline_path, str(line), str(keys.size)],
+                   check=True)
+    # artefacts: the knots are one more parameter array, byte for byte {key, offset} pairs
+    blob = open(os.path.join(work, "rmi_data", "rmi_L2_PARAMETERS"), "rb").read()
+    assert blob == knots.astype("<u8").tobytes()
+    code = open(os.path.join(work, "rmi.cpp")).read()
+    assert "#include <algorithm>" in code and "uint64_t _rmi_lookup_pre_cachefix(uint64_t key, size_t* err)" in code
+    assert f"const uint64_t num_spline_pts = {knots.shape[0]};" in code and f"const uint64_t total_keys = {keys.size};" in code
+    assert f"  *err = {line};" in code and f"/ {line}) * {line};" in code
+    hdr = open(os.path.join(work, "rmi.h")).read()
+    assert "uint64_t lookup(uint64_t key, size_t* err);" in hdr and "_rmi_lookup_pre_cachefix" not in hdr
+    ppm = o.l1_params.shape[1]
+    top_bytes = 8 * (len(o.l0.fp) + (len(o.l0.ip) if o.l0.kind in ("radix", "bradix") else 0))
+    assert f"const size_t RMI_SIZE = {top_bytes + o.branching_factor * (8 * ppm + 8) + 16 * knots.shape[0]};" in hdr
+    # the reference's cache-fix test: |lookup(key) - lower_bound(key)| <= line size, for every key
+    out = build_and_check(work, keys)
+    assert out.startswith("ok")
+    assert int(out.split()[2]) <= line
+
+
+@pytest.mark.gpu
+def test_cli_bounded_end_to_end_on_gpu(tmp_path):
+    """`rmi <file> rmi linear_spline,linear 4096 --bounded 8` (tests/cache_fix_wiki/Makefile:8 at small scale)."""
+    from rmi_b200 import build
+    cli = build.build_cli()
+    keys = datasets.uniform_u64(1_000_000, seed=9)
+    keys = keys[keys > 0]
+    work = str(tmp_path)
+    datafile = os.path.join(work, "synthetic_1M_uint64")
+    write_keyfile(datafile, keys)
+    r = subprocess.run([cli, datafile, "rmi", "linear_spline,linear", "4096", "--bounded", "8", "--zero-build-time"], cwd=work,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = build_and_check(work, keys)
+    assert out.startswith("ok") and int(out.split()[2]) <= 8
