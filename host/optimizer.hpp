@@ -4,6 +4,7 @@
 // optimizer.rs:163-171), so no leaf table ever leaves the GPU during a sweep.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -11,6 +12,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../include/rmi_b200.h"
@@ -116,34 +118,62 @@ inline std::vector<Config> second_phase_configs(const std::vector<RMIStatistics>
   return out;
 }
 
-// measure_rmis (:220-231).  A panicking configuration aborts the sweep, as in the reference.
-inline std::vector<RMIStatistics> measure_rmis(const rmi_dataset* ds, const std::vector<Config>& configs, uint32_t flags,
-                                               bool verbose) {
-  std::vector<RMIStatistics> out;
-  for (auto& c : configs) {
-    rmi_result* r = nullptr;
-    int rc = rmi_train(ds, c.first.c_str(), c.second, flags | RMI_FLAG_STATS_ONLY, &r);
-    if (rc != RMI_OK) throw std::runtime_error("training " + c.first + " " + std::to_string(c.second) + ": " + rmi_last_error());
-    RMIStatistics s;
-    s.models = c.first; s.branching_factor = c.second;
-    s.average_log2_error = r->model_avg_log2_error; s.max_log2_error = r->model_max_log2_error;
-    s.size = rmi_size(*r, true);
-    if (verbose) std::fprintf(stderr, "  %-28s %10llu  avg_log2 %.5f  size %llu  (%.2f ms)\n", c.first.c_str(),
-                              (unsigned long long)c.second, s.average_log2_error, (unsigned long long)s.size, r->device_time_ns / 1e6);
-    rmi_result_free(r);
-    out.push_back(s);
+// measure_rmis (:220-231).  The reference maps the configurations over a rayon pool on one shared
+// data set (optimizer.rs:224-229); here `replicas` holds the SAME key set on one or more devices
+// (rmi_dataset_replicate) and one host thread per replica pulls the next configuration from a
+// shared counter — independent builds, no communication, results in configuration order.
+// A panicking configuration aborts the sweep, as in the reference.
+inline std::vector<RMIStatistics> measure_rmis(const std::vector<const rmi_dataset*>& replicas, const std::vector<Config>& configs,
+                                               uint32_t flags, bool verbose) {
+  std::vector<RMIStatistics> out(configs.size());
+  std::atomic<size_t> next{0};
+  std::atomic<bool> failed{false};
+  std::vector<std::string> errors(replicas.size());
+  auto worker = [&](size_t w) {
+    const rmi_dataset* ds = replicas[w];
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= configs.size() || failed.load()) return;
+      const Config& c = configs[i];
+      rmi_result* r = nullptr;
+      int rc = rmi_train(ds, c.first.c_str(), c.second, flags | RMI_FLAG_STATS_ONLY, &r);
+      if (rc != RMI_OK) {
+        errors[w] = "training " + c.first + " " + std::to_string(c.second) + ": " + rmi_last_error();
+        failed.store(true);
+        return;
+      }
+      RMIStatistics& s = out[i];
+      s.models = c.first; s.branching_factor = c.second;
+      s.average_log2_error = r->model_avg_log2_error; s.max_log2_error = r->model_max_log2_error;
+      s.size = rmi_size(*r, true);
+      if (verbose) std::fprintf(stderr, "  [replica %zu] %-28s %10llu  avg_log2 %.5f  size %llu  (%.2f ms)\n", w, c.first.c_str(),
+                                (unsigned long long)c.second, s.average_log2_error, (unsigned long long)s.size, r->device_time_ns / 1e6);
+      rmi_result_free(r);
+    }
+  };
+  if (replicas.size() == 1) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (size_t w = 0; w < replicas.size(); ++w) th.emplace_back(worker, w);
+    for (auto& t : th) t.join();
   }
+  for (auto& e : errors) if (!e.empty()) throw std::runtime_error(e);
   return out;
 }
 
-inline std::vector<RMIStatistics> find_pareto_efficient_configs(const rmi_dataset* ds, size_t restrict_to, uint32_t flags,
-                                                                bool verbose) {   // :233-249
-  auto first = measure_rmis(ds, first_phase_configs(), flags, verbose);
-  auto second = measure_rmis(ds, second_phase_configs(first), flags, verbose);
+inline std::vector<RMIStatistics> find_pareto_efficient_configs(const std::vector<const rmi_dataset*>& replicas, size_t restrict_to,
+                                                                uint32_t flags, bool verbose) {   // :233-249
+  auto first = measure_rmis(replicas, first_phase_configs(), flags, verbose);
+  auto second = measure_rmis(replicas, second_phase_configs(first), flags, verbose);
   auto front = narrow_front(pareto_front(second), restrict_to);
   std::stable_sort(front.begin(), front.end(),
                    [](const RMIStatistics& a, const RMIStatistics& b) { return a.average_log2_error < b.average_log2_error; });
   return front;
+}
+
+inline std::vector<RMIStatistics> find_pareto_efficient_configs(const rmi_dataset* ds, size_t restrict_to, uint32_t flags,
+                                                                bool verbose) {
+  return find_pareto_efficient_configs(std::vector<const rmi_dataset*>{ds}, restrict_to, flags, verbose);
 }
 
 inline void display_table(const std::vector<RMIStatistics>& items) {   // :193-206

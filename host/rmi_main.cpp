@@ -3,7 +3,9 @@
 //       [--no-code] [--param-grid <file>] [--data-path|-d <dir>] [--no-errors] [--threads|-t <n>]
 //       [--max-size <bytes>] [--disable-parallel-training] [--zero-build-time] [--optimize <file>]
 //       [--bounded <line_size>]
-// plus  --exact-top-fit (RMI_FLAG_TOP_FIT_EXACT) and --device <n>.
+// plus  --exact-top-fit (RMI_FLAG_TOP_FIT_EXACT), --device <n> and, for the configuration sweeps
+// (--optimize, --max-size), --devices <a,b,...>: the key set is replicated to every listed GPU
+// (device-to-device copies) and the independent configurations are spread over them.
 // The build itself is librmi_b200.so (CUDA); this binary only loads the data set into HBM,
 // calls rmi_train and writes the artefacts (codegen.hpp).  `--bounded` runs the reference's
 // serial cache-fix scan on the host (cache_fix.hpp) and then builds the RMI over the spline's
@@ -106,7 +108,7 @@ Args parse_args(int argc, char** argv) {
       {"--no-code", false}, {"--dump-ll-model-data", true}, {"--dump-ll-errors", false}, {"--stats-file", true},
       {"--param-grid", true}, {"--data-path", true}, {"--no-errors", false}, {"--threads", true}, {"--bounded", true},
       {"--max-size", true}, {"--disable-parallel-training", false}, {"--zero-build-time", false}, {"--optimize", true},
-      {"--exact-top-fit", false}, {"--device", true}, {"--verbose", false}};
+      {"--exact-top-fit", false}, {"--device", true}, {"--devices", true}, {"--verbose", false}};
   Args a;
   for (int i = 1; i < argc; ++i) {
     std::string s = argv[i];
@@ -145,7 +147,8 @@ int main(int argc, char** argv) {
   const std::string data_dir = a.has("--data-path") ? a.opt["--data-path"] : "rmi_data";
   const bool have_ns = a.pos.size() > 1;
   if (have_ns && a.has("--param-grid")) die("Can only specify one of namespace or param-grid");
-  const int device = a.has("--device") ? std::atoi(a.opt["--device"].c_str()) : 0;
+  const int device = a.has("--device") ? std::atoi(a.opt["--device"].c_str())
+                                       : (a.has("--devices") ? std::atoi(a.opt["--devices"].c_str()) : 0);
   const uint32_t flags = a.has("--exact-top-fit") ? RMI_FLAG_TOP_FIT_EXACT : 0;
   const bool verbose = a.has("--verbose") || std::getenv("RUST_LOG") != nullptr;
 
@@ -161,9 +164,29 @@ int main(int argc, char** argv) {
   if (rmi_dataset_load_file(fp.c_str(), file_kt, device, &ds) != RMI_OK) die(rmi_last_error());
   const uint64_t num_rows = rmi_dataset_len(ds);
 
+  // replicas of the key set for the sweeps: the first listed device holds the loaded copy
+  std::vector<const rmi_dataset*> replicas{ds};
+  std::vector<rmi_dataset*> owned_replicas;
+  if (a.has("--devices") && (a.has("--optimize") || a.has("--max-size"))) {
+    std::stringstream dl(a.opt["--devices"]);
+    std::string tok;
+    bool first_tok = true;
+    while (std::getline(dl, tok, ',')) {
+      if (tok.empty()) continue;
+      int d = std::atoi(tok.c_str());
+      if (first_tok) { first_tok = false; if (d == device) continue; }
+      rmi_dataset* rep = nullptr;
+      if (rmi_dataset_replicate(ds, d, &rep) != RMI_OK) die(rmi_last_error());
+      owned_replicas.push_back(rep);
+      replicas.push_back(rep);
+    }
+  }
+  auto free_replicas = [&]() { for (auto* r : owned_replicas) rmi_dataset_destroy(r); owned_replicas.clear(); };
+
   if (a.has("--optimize")) {   // main.rs:134-161
     std::vector<RMIStatistics> results;
-    try { results = find_pareto_efficient_configs(ds, 10, flags, verbose); } catch (std::exception& e) { die(e.what()); }
+    try { results = find_pareto_efficient_configs(replicas, 10, flags, verbose); } catch (std::exception& e) { die(e.what()); }
+    free_replicas();
     display_table(results);
     std::string prefix;
     if (have_ns) prefix = a.pos[1];
@@ -236,7 +259,8 @@ int main(int argc, char** argv) {
     if (a.has("--max-size")) {   // train_for_size, train/mod.rs:128-154
       uint64_t max_size = std::strtoull(a.opt["--max-size"].c_str(), nullptr, 10);
       std::vector<RMIStatistics> pareto;
-      try { pareto = find_pareto_efficient_configs(ds, 1000, flags, verbose); } catch (std::exception& e) { die(e.what()); }
+      try { pareto = find_pareto_efficient_configs(replicas, 1000, flags, verbose); } catch (std::exception& e) { die(e.what()); }
+      free_replicas();
       const RMIStatistics* pick = nullptr;
       for (auto& c : pareto) if (c.size < max_size) { pick = &c; break; }
       if (!pick) die("Could not find any configurations smaller than " + std::to_string(max_size));

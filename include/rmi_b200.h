@@ -82,6 +82,12 @@ int rmi_dataset_wrap_device(const void* device_keys, uint64_t n, rmi_key_type ke
  * the file-name suffix as src/main.rs:122-132 does when key_type < 0) straight into HBM through
  * a double-buffered pinned staging ring. */
 int rmi_dataset_load_file(const char* path, int key_type_or_negative, int device, rmi_dataset** out);
+/* A replica of `src` on another device: one device-to-device copy (NVLink peer copy when the two
+ * GPUs are peers, staged by the driver otherwise; a plain copy when device == src's device).
+ * Sortedness / duplicate-freeness are inherited, not re-verified.  This is how an --optimize
+ * sweep spreads over the GPUs of a node (replicas, zero communication per
+ * configuration) after the key file has been read once. */
+int rmi_dataset_replicate(const rmi_dataset* src, int device, rmi_dataset** out);
 uint64_t rmi_dataset_len(const rmi_dataset* ds);
 int rmi_dataset_key_type(const rmi_dataset* ds);
 void rmi_dataset_destroy(rmi_dataset* ds);

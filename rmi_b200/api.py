@@ -64,6 +64,7 @@ def load_library():
         L.rmi_dataset_create.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.rmi_dataset_wrap_device.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.rmi_dataset_load_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rmi_dataset_replicate.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.rmi_dataset_len.restype = C.c_uint64
         L.rmi_dataset_len.argtypes = [C.c_void_p]
         L.rmi_dataset_key_type.argtypes = [C.c_void_p]
@@ -134,6 +135,16 @@ class RMITrainingData:
         _check(load_library().rmi_dataset_load_file(path.encode(), key_type, device, C.byref(self._h)))
         self.key_type = int(load_library().rmi_dataset_key_type(self._h))
         return self
+
+    def replicate(self, device: int) -> "RMITrainingData":
+        """A copy of this key set on another GPU (one device-to-device copy; RMITrainingData::soft_copy's
+        role, models/mod.rs:311-316, for sweeps that spread independent builds over the GPUs of a node)."""
+        other = type(self).__new__(type(self))
+        other._h = C.c_void_p()
+        other.key_type = self.key_type
+        other._keep = None
+        _check(load_library().rmi_dataset_replicate(self._h, int(device), C.byref(other._h)))
+        return other
 
     def __len__(self) -> int:
         return int(load_library().rmi_dataset_len(self._h))

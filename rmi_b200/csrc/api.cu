@@ -332,6 +332,32 @@ int rmi_dataset_load_file(const char* path, int key_type_or_negative, int device
   return RMI_OK;
 }
 
+int rmi_dataset_replicate(const rmi_dataset* src, int device, rmi_dataset** out) {
+  g_last_error.clear();
+  if (!src || !out) return fail(RMI_ERR_INVALID, "rmi_dataset_replicate: null argument");
+  const size_t ksz = src->key_type == RMI_KEY_U32 ? 4 : 8;
+  const size_t bytes = ((size_t)src->n * ksz + 15) & ~(size_t)15;   // readable up to the next 16-byte boundary
+  CUDA_TRY(cudaSetDevice(device));
+  void* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, bytes ? bytes : 16));
+  cudaError_t e = cudaSuccess;
+  if (src->n) {
+    if (device != src->device) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, device, src->device);
+      if (can) { cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0); if (pe != cudaSuccess) cudaGetLastError(); }
+    }
+    e = cudaMemcpyPeer(d, device, src->d_keys, src->device, (size_t)src->n * ksz);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  }
+  if (e != cudaSuccess) { cudaFree(d); return fail(RMI_ERR_CUDA, std::string("rmi_dataset_replicate: ") + cudaGetErrorString(e)); }
+  auto* ds = new rmi_dataset();
+  ds->d_keys = d; ds->n = src->n; ds->key_type = src->key_type; ds->device = device;
+  ds->owned = true; ds->pooled = false; ds->sorted = src->sorted; ds->no_dups = src->no_dups;
+  *out = ds;
+  return RMI_OK;
+}
+
 uint64_t rmi_dataset_len(const rmi_dataset* ds) { return ds ? ds->n : 0; }
 int rmi_dataset_key_type(const rmi_dataset* ds) { return ds ? ds->key_type : -1; }
 void rmi_dataset_destroy(rmi_dataset* ds) {

@@ -193,3 +193,27 @@ def test_baseline_config0_linear_linear_100_on_1M(rmi, oracle):
     parity.assert_top_equal(gf, o, exact=False, N=100)
     o2 = oracle.train(keys, "linear,linear", 100, l0_override=gf.l0_fparams)
     parity.assert_same_rmi(gf, o2)
+
+
+def test_replica_and_concurrent_builds(rmi, oracle):
+    """rmi_dataset_replicate + re-entrancy (may be entered concurrently from
+    several host threads on shared data): two threads building on two replicas must both equal the oracle."""
+    import threading
+    keys = datasets.uniform_u64(300_000, seed=77)
+    a = rmi.RMITrainingData(keys, device=0)
+    b = a.replicate(0)
+    assert len(b) == len(a)
+    o = oracle.train(keys, "radix,linear", 4096)
+    out = {}
+
+    def work(name, ds):
+        out[name] = [rmi.train(ds, "radix,linear", 4096) for _ in range(5)]
+
+    th = [threading.Thread(target=work, args=(n, d)) for n, d in (("a", a), ("b", b), ("a2", a))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for name in ("a", "b", "a2"):
+        for g in out[name]:
+            parity.assert_same_rmi(g, o)

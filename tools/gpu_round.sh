@@ -17,7 +17,7 @@ timeout 300 python tools/dev_bench.py --iters=3 > $out/${tag}_dev_bench.jsonl 2>
 if [ "$2" != "skip-ncu" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
      --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_bench.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_leaf -s 3 -c 1 \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_leaf -s 10 -c 5 \
      -o $out/${tag}_k_leaf_full -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1
 fi
 tail -3 $out/${tag}_pytest_gpu.log

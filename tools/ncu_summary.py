@@ -70,11 +70,17 @@ def full(rep, dst, traffic=None):
         def to_bytes(s):
             v, u = s.split()[0], (s.split() + [""])[1]
             return float(v.replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
-        r0 = res[0]
-        rd, wr = to_bytes(r0["dram__bytes_read.sum"]), to_bytes(r0["dram__bytes_write.sum"])
-        json.dump({"kernel": r0["kernel"], "source": dst, "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
-                   "dram_bytes_per_launch": int(rd + wr), "gpu_time": r0["gpu__time_duration.sum"],
-                   "lts_hit_rate": r0.get("lts__t_sector_hit_rate.pct")}, open(traffic, "w"), indent=1)
+        # the bulk leaf kernel of ONE build may be several launches (slices of the block range): sum them
+        bulk = [r for r in res if not r.get("launch__grid_size", "").strip().startswith("16")]
+        rd = sum(to_bytes(r["dram__bytes_read.sum"]) for r in bulk)
+        wr = sum(to_bytes(r["dram__bytes_write.sum"]) for r in bulk)
+        def to_us(s):
+            v, u = s.split()[0], (s.split() + [""])[1]
+            return float(v.replace(",", "")) * {"ms": 1e3, "us": 1.0, "ns": 1e-3, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}.get(u, 1.0)
+        json.dump({"kernel": bulk[0]["kernel"], "source": dst, "launches_summed": len(bulk),
+                   "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "dram_bytes_per_launch": int(rd + wr),
+                   "gpu_time_us_sum": sum(to_us(r["gpu__time_duration.sum"]) for r in bulk),
+                   "lts_hit_rate": [r.get("lts__t_sector_hit_rate.pct") for r in bulk]}, open(traffic, "w"), indent=1)
 
 
 if __name__ == "__main__":
