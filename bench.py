@@ -348,6 +348,10 @@ def main():
                       "all-reduce of top-model sums (64 B), leaf boundaries ((N+1)*8 B) and leaf records (N*32 B), "
                       "halo send/recv between neighbours",
                       "timing": "CUDA events around K synchronous builds, max over ranks",
+                      "roofline_note": "dominant kernel = the fused leaf fit + forward pass (k_leaf); on one GPU it runs as 4 launch "
+                                       "slices per build (their results cross PCIe while the next slice computes): achieved = "
+                                       "algorithmic bytes of all slices / the leaf phase's device time, traffic = ncu DRAM bytes "
+                                       "summed over the slices of one build (profiles/dominant_kernel_traffic.json)",
                       "wall_ms_per_step": 1e3 * wall / args.steps},
            "clocks": clk,
            "e2e": {"value": e2e_val, "unit": "keys/s", "h2d_bytes_per_step": n * key_bytes,

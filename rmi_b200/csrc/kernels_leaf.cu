@@ -90,7 +90,9 @@ k_bounds(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr
 // keys.  ~28 probes per leaf instead of a pass over all n keys; neighbouring leaves share
 // the upper levels of the search in L1/L2.  Sortedness (and with it monotonicity of the
 // targets) is verified by k_leaf, which visits every consecutive key pair anyway.
-template <class T, int TOP>
+// ARITY 4: every level probes the three quartile points at once (independent loads, one memory
+// latency per level, half as many levels) before the last few keys are bisected.
+template <class T, int TOP, int ARITY>
 __global__ void __launch_bounds__(BOUNDS_THREADS)
 k_bounds_search(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr, u64 N,
                 u64* __restrict__ S) {
@@ -100,27 +102,16 @@ k_bounds_search(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ 
   u64 lo = 0, hi = n;
   if (j == N) lo = n;
   else if (j > 0) {
-    // The top model approximates the CDF scaled to [0, N), so boundary j lies near index j*n/N.
-    // Bracket it by galloping outwards from that guess (x8 per step) before bisecting: on data the
-    // top model fits well that is ~15 probes inside one 32 KB window instead of ~28 spread over
-    // the array (the last ~18 levels of a full bisection each cost a DRAM sector per boundary);
-    // a bad guess costs at most a few extra probes.  Any monotone predicate gives the same S.
-    const u64 guess = (u64)(((unsigned __int128)j * n) / N);
-    u64 pos = guess < n ? guess : n - 1;
-    u64 step = 512;
-    if (top_predict<TOP>(m, keys[pos]) >= j) {
-      hi = pos;
-      while (hi > lo) {
-        const u64 q = hi > step ? hi - step : 0;
-        if (top_predict<TOP>(m, keys[q]) >= j) { hi = q; step <<= 3; if (q == 0) break; }
-        else { lo = q + 1; break; }
-      }
-    } else {
-      lo = pos + 1;
-      while (lo < hi) {
-        const u64 q = lo + step < hi ? lo + step : hi - 1;
-        if (top_predict<TOP>(m, keys[q]) >= j) { hi = q; break; }
-        lo = q + 1; step <<= 3;
+    if (ARITY == 4) {
+      while (hi - lo > 8) {
+        const u64 w = hi - lo;
+        const u64 q1 = lo + (w >> 2), q2 = lo + (w >> 1), q3 = lo + (w >> 1) + (w >> 2);
+        const T k1 = keys[q1], k2 = keys[q2], k3 = keys[q3];
+        const bool p1 = top_predict<TOP>(m, k1) >= j, p2 = top_predict<TOP>(m, k2) >= j, p3 = top_predict<TOP>(m, k3) >= j;
+        if (p1) hi = q1;
+        else if (p2) { lo = q1 + 1; hi = q2; }
+        else if (p3) { lo = q2 + 1; hi = q3; }
+        else lo = q3 + 1;
       }
     }
     while (lo < hi) {
@@ -1258,8 +1249,10 @@ template <class T, int TOP>
 void launch_bounds_impl(const Launch& L, const T* keys, u64 n, const TopModel* d_top, u64 N, u64* d_S, BuildAux* d_aux,
                    bool allow_search) {
   if (allow_search && top_is_monotone_by_construction(TOP)) {
-    k_bounds_search<T, TOP><<<(unsigned)((N + 1 + BOUNDS_THREADS - 1) / BOUNDS_THREADS), BOUNDS_THREADS, 0, L.stream>>>(
-        keys, n, d_top, N, d_S);
+    static const int arity = [] { const char* e = getenv("RMI_DEV_BOUNDS_ARITY"); return e ? atoi(e) : 2; }();
+    const unsigned sgrid = (unsigned)((N + 1 + BOUNDS_THREADS - 1) / BOUNDS_THREADS);
+    if (arity == 4) k_bounds_search<T, TOP, 4><<<sgrid, BOUNDS_THREADS, 0, L.stream>>>(keys, n, d_top, N, d_S);
+    else k_bounds_search<T, TOP, 2><<<sgrid, BOUNDS_THREADS, 0, L.stream>>>(keys, n, d_top, N, d_S);
     count_launch();
     k_split<T, TOP><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux, 1);
     count_launch();

@@ -12,7 +12,8 @@ Data path per build:
                      robust_linear sums; normal / lognormal mean, then variance; cubic L1
                      comparison), MIN of 4 x i64 (cubic: the two interior points of the spline)
     all-reduce MIN   (N+1) x u64        leaf boundaries S
-    send/recv        halo keys          the tail of a rank's last leaf that lives on the next rank(s)
+    (halo keys — the tail of a rank's last leaf that lives on the next rank(s) — are fetched once
+     per data set, not per build: the keys are immutable)
     all-reduce SUM   N x (ppm+2) x 8 B  leaf parameters, error bounds, key counts (zero where not owned)
 The orchestration below is engine-agnostic: `CudaShardEngine` drives librmi_b200.so; the
 CPU tests (gloo, world_size 2) plug in a numpy engine to exercise exactly this host logic.
@@ -154,7 +155,7 @@ class ShardedTrainingData:
         self.halo_capacity = capacity
         self.engine.end()
         self.engine = CudaShardEngine(self)
-        for attr in ("_min_cap",):
+        for attr in ("_min_cap", "_halo_have"):
             if hasattr(self, attr):
                 delattr(self, attr)
 
@@ -303,46 +304,15 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
     if world > 1:
         dist.all_reduce(bufs["S"], op=dist.ReduceOp.MIN, group=group)
     eng.phase(PHASE_SPLIT)
-    # 4. halo: the keys of a rank's last leaf that live on the following rank(s)
-    halo = 0
-    if world > 1:
-        S = bufs["S"]
-        cuts = torch.tensor(bases[1:], dtype=torch.int64, device=dev)
-        pos = torch.searchsorted(S, cuts).clamp_(max=N)
-        v = S[pos].cpu().tolist()
-        moves = plan_halo(bases, v, n_global)
-        need = {}
-        for (dst, src, off, cnt) in moves:
-            need[dst] = need.get(dst, 0) + cnt
-        most = max(need.values(), default=0)
-        if most > _min_halo_capacity(data, group, world, dev):
-            # every rank computes the same `most`, so they all take this branch together
-            if engine is None and hasattr(data, "grow_halo"):
-                data.grow_halo(int(most * 1.25) + 1024)
-                return train_sharded(data, model_spec, num_leaves, flags, group, counts=counts)
-            raise api.RMIError("a leaf reaches further into the next rank than the halo capacity "
-                               f"({most} keys needed)")
-        # gloo cannot send/recv device memory (one-GPU test boxes): stage through the host there
-        stage = dev.type == "cuda" and dist.get_backend(group) == "gloo"
-        ops, recv_off, landed = [], 0, []
-        for (dst, src, off, cnt) in moves:
-            if dst == rank:
-                view = eng.halo_view(recv_off, cnt)
-                t = torch.empty(cnt, dtype=view.dtype) if stage else view
-                if stage:
-                    landed.append((view, t))
-                ops.append(dist.P2POp(dist.irecv, t, src, group=group))
-                recv_off += cnt
-            elif src == rank:
-                view = eng.local_view(off, cnt)
-                ops.append(dist.P2POp(dist.isend, view.cpu() if stage else view, dst, group=group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for view, t in landed:
-            view.copy_(t)
-        halo = need.get(rank, 0)
-    eng.set_halo(halo)
+    # 4. halo: the keys of a rank's last leaf that live on the following rank(s).  The keys are
+    #    immutable, so the first `halo_capacity` keys behind every slab are fetched ONCE per data set
+    #    (no planning, no host synchronisation, no transfer inside a build); a build whose last leaf
+    #    reaches further reports it through the status word and takes the planned path below.
+    if world > 1 and getattr(data, "_halo_have", None) is None:
+        cap = _min_halo_capacity(data, group, world, dev)
+        moves = plan_halo(bases, [bases[g + 1] + cap - 1 for g in range(world)], n_global)
+        data._halo_have = _exchange_halo(eng, moves, rank, group, dev)
+    eng.set_halo(getattr(data, "_halo_have", 0) or 0)
     # 5. leaves owned by this rank, then everyone gets everything
     eng.phase(PHASE_LEAF)
     if world > 1:
@@ -350,7 +320,49 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
         dist.all_reduce(rec if counts else rec[: N * (ppm + 1)], op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(bufs["status"], op=dist.ReduceOp.MAX, group=group)
     eng.phase(PHASE_STATS)
-    return eng.finish(int(flags) | (api.FLAG_LEAF_COUNTS if counts else 0))
+    try:
+        return eng.finish(int(flags) | (api.FLAG_LEAF_COUNTS if counts else 0))
+    except api.RMIPanic as e:
+        if world <= 1 or "halo" not in str(e):
+            raise
+    # A leaf reaches past the prefetched halo (heavy skew).  The status word is the MAX over ranks, so
+    # every rank arrives here together: size the halo from the global boundaries S and build again.
+    S = bufs["S"]
+    cuts = torch.tensor(bases[1:], dtype=torch.int64, device=dev)
+    pos = torch.searchsorted(S, cuts).clamp_(max=N)
+    v = S[pos].cpu().tolist()
+    need = {}
+    for (dst, src, off, cnt) in plan_halo(bases, v, n_global):
+        need[dst] = need.get(dst, 0) + cnt
+    most = max(need.values(), default=0)
+    if most <= _min_halo_capacity(data, group, world, dev) or not hasattr(data, "grow_halo"):
+        raise api.RMIError(f"a leaf reaches further into the next rank than the halo capacity ({most} keys needed)")
+    data.grow_halo(int(most * 1.25) + 1024)
+    return train_sharded(data, model_spec, num_leaves, flags, group, counts=counts)
+
+
+def _exchange_halo(eng, moves, rank, group, dev) -> int:
+    """Carries out plan_halo's transfers; returns how many halo keys this rank now holds."""
+    # gloo cannot send/recv device memory (one-GPU test boxes): stage through the host there
+    stage = dev.type == "cuda" and dist.get_backend(group) == "gloo"
+    ops, recv_off, landed = [], 0, []
+    for (dst, src, off, cnt) in moves:
+        if dst == rank:
+            view = eng.halo_view(recv_off, cnt)
+            t = torch.empty(cnt, dtype=view.dtype) if stage else view
+            if stage:
+                landed.append((view, t))
+            ops.append(dist.P2POp(dist.irecv, t, src, group=group))
+            recv_off += cnt
+        elif src == rank:
+            view = eng.local_view(off, cnt)
+            ops.append(dist.P2POp(dist.isend, view.cpu() if stage else view, dst, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for view, t in landed:
+        view.copy_(t)
+    return recv_off
 
 
 def _min_halo_capacity(data, group, world, dev):

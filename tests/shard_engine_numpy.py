@@ -318,6 +318,7 @@ class NumpyShardEngine:
         S = [int(x) for x in self.bufs["S"].numpy()]
         N, n, base = self.N, self.n, self.base
         k = self.keys()                                  # local + halo
+        n_have = base + k.size                           # global index one past the last key held here
         ppm = sh._PPM[self.leaf_name]
         params = np.zeros((N, ppm))
         errors = np.zeros(N, dtype=np.int64)
@@ -334,6 +335,9 @@ class NumpyShardEngine:
             lo, hi = S[j], S[j + 1]
             owner = (base <= lo < base + self.n_local) or (lo >= n and info["is_last"])
             if not owner:
+                continue
+            if hi > n_have or (hi < n and hi + 1 > n_have):     # the leaf (or its successor's first key) is not here
+                self.status |= 4096                             # ST_HALO_TOO_SMALL
                 continue
             if self.has_split and j >= self.split_target:
                 half_lo, half_hi, first_leaf = self.split + 1, n, self.split_target
@@ -391,6 +395,8 @@ class NumpyShardEngine:
         pass
 
     def finish(self, flags=0):
+        if int(self.bufs["status"][0]) & 4096:
+            raise api.RMIPanic("a leaf reaches past the halo copied from the next rank")
         if int(self.bufs["status"][0]) != 0:
             raise api.RMIPanic("a rank reported a failure")
         N, n = self.N, self.n
@@ -418,7 +424,15 @@ class NumpyShardedData:
     """Duck-typed ShardedTrainingData for the CPU engine."""
 
     def __init__(self, local_keys: np.ndarray, halo_capacity: int = 4096, group=None):
+        self._keys = local_keys
         self.engine = NumpyShardEngine(local_keys, halo_capacity)
         self.key_type = api.KEY_U64
         self.halo_capacity = halo_capacity
         self.group = group
+
+    def grow_halo(self, capacity: int):
+        self.engine = NumpyShardEngine(self._keys, capacity)
+        self.halo_capacity = capacity
+        for attr in ("_min_cap", "_halo_have"):
+            if hasattr(self, attr):
+                delattr(self, attr)

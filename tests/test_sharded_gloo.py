@@ -44,7 +44,7 @@ def _cuts(n, world, uneven):
     return c
 
 
-def _worker(rank, world, port, kind, n, spec, N, uneven, out_q):
+def _worker(rank, world, port, kind, n, spec, N, uneven, out_q, halo=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -54,7 +54,7 @@ def _worker(rank, world, port, kind, n, spec, N, uneven, out_q):
         from tests.shard_engine_numpy import NumpyShardedData
         keys = _make_keys(kind, n)
         c = _cuts(n, world, uneven)
-        data = NumpyShardedData(keys[c[rank]:c[rank + 1]].copy(), halo_capacity=n)
+        data = NumpyShardedData(keys[c[rank]:c[rank + 1]].copy(), halo_capacity=n if halo is None else halo)
         g = sharded.train_sharded(data, spec, N)
         top = spec.split(",")[0]
         if top in ("linear", "robust_linear", "normal", "lognormal", "cubic"):
@@ -117,6 +117,22 @@ def test_sharded_build_equals_single_process_build(oracle, world, kind, spec, N,
         p.join(timeout=60)
     bad = [r for r in results if r[1] != "ok"]
     assert not bad, bad
+
+
+def test_halo_grows_when_a_leaf_reaches_past_the_prefetched_keys(oracle):
+    """Skewed data, a deliberately tiny halo: the first build reports ST_HALO_TOO_SMALL on every rank, the
+    orchestrator sizes the halo from the global boundaries, re-homes the slab and builds again."""
+    world, kind, n, spec, N = 3, "lognormal", 6000, "linear_spline,linear", 24
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, n, spec, N, False, q, 4)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert not [r for r in results if r[1] != "ok"], results
 
 
 def test_layout_planner_handles_runs_spanning_ranks():
