@@ -9,8 +9,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "librmi_b200.so")
-OBJ_DIR = os.path.join(HERE, "build")
+# RMI_BUILD_TAG=<name> (with RMI_NVCC_DEFS="-DFOO ...") builds an experiment variant next to the
+# default library: lib/librmi_b200_<name>.so, loaded by dev tools through RMI_B200_LIB.
+_TAG = os.environ.get("RMI_BUILD_TAG", "")
+LIB_PATH = os.path.join(LIB_DIR, f"librmi_b200{'_' + _TAG if _TAG else ''}.so")
+OBJ_DIR = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
 
 SOURCES = ["kernels_top.cu", "kernels_leaf.cu", "kernels_shard.cu", "api.cu"]
 HEADERS = ["rust_math.cuh", "models.cuh", "device_util.cuh", "kernels.h",

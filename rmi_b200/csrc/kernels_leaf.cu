@@ -90,9 +90,7 @@ k_bounds(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr
 // keys.  ~28 probes per leaf instead of a pass over all n keys; neighbouring leaves share
 // the upper levels of the search in L1/L2.  Sortedness (and with it monotonicity of the
 // targets) is verified by k_leaf, which visits every consecutive key pair anyway.
-// ARITY 4: every level probes the three quartile points at once (independent loads, one memory
-// latency per level, half as many levels) before the last few keys are bisected.
-template <class T, int TOP, int ARITY>
+template <class T, int TOP>
 __global__ void __launch_bounds__(BOUNDS_THREADS)
 k_bounds_search(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr, u64 N,
                 u64* __restrict__ S) {
@@ -102,18 +100,10 @@ k_bounds_search(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ 
   u64 lo = 0, hi = n;
   if (j == N) lo = n;
   else if (j > 0) {
-    if (ARITY == 4) {
-      while (hi - lo > 8) {
-        const u64 w = hi - lo;
-        const u64 q1 = lo + (w >> 2), q2 = lo + (w >> 1), q3 = lo + (w >> 1) + (w >> 2);
-        const T k1 = keys[q1], k2 = keys[q2], k3 = keys[q3];
-        const bool p1 = top_predict<TOP>(m, k1) >= j, p2 = top_predict<TOP>(m, k2) >= j, p3 = top_predict<TOP>(m, k3) >= j;
-        if (p1) hi = q1;
-        else if (p2) { lo = q1 + 1; hi = q2; }
-        else if (p3) { lo = q2 + 1; hi = q3; }
-        else lo = q3 + 1;
-      }
-    }
+    // (measured alternatives, both dropped: galloping outwards from the interpolated index j*n/N
+    //  — 0.22 ms instead of 0.14 at 200M keys / 2^20 leaves, the divergent gallop loops cost more
+    //  than the saved probes — and a 4-ary search with three independent probes per level — no
+    //  change: the phase is bound by DRAM sectors per boundary, not by levels of latency)
     while (lo < hi) {
       u64 mid = lo + ((hi - lo) >> 1);
       if (top_predict<TOP>(m, keys[mid]) >= j) hi = mid; else lo = mid + 1;
@@ -162,9 +152,6 @@ constexpr int ROW_BYTES = 144;   // 128 B of keys + 16 B pad: rows stay 16-byte 
                                  // a 128-bit shared-load phase hit 8 distinct bank quads
 #ifndef RMI_SSTAGES
 #define RMI_SSTAGES 2
-#endif
-#ifndef RMI_PARTIAL_MODE
-#define RMI_PARTIAL_MODE 2   // 0: per-lane fast/slow split, 1: warp-uniform predicated walk, 2: one variable-bound loop
 #endif
 constexpr int SSTAGES = RMI_SSTAGES;
 constexpr int WARP_STREAM_BYTES = SSTAGES * 32 * ROW_BYTES + 32 * 4 + 32 * 4;
@@ -281,23 +268,6 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
     const I lo_k = skip > cbase ? skip : cbase;
     const I hi_k = rlen < cbase + (I)SW ? rlen : cbase + (I)SW;
     const bool full = lo_k == cbase && hi_k == cbase + (I)SW;
-#if RMI_PARTIAL_MODE == 0
-    if (full) {
-      I idx = a + cbase;
-#pragma unroll 4
-      for (int pp = 0; pp < 8; ++pp) {
-        uint4 v = *reinterpret_cast<const uint4*>(row + pp * 16);
-        T kk[KPP];
-        memcpy(kk, &v, 16);
-#pragma unroll
-        for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(idx + (I)t));
-        idx += (I)KPP;
-      }
-    } else if (lo_k < hi_k) {
-      const int p0 = (int)(lo_k - cbase), p1 = (int)(hi_k - cbase);
-      for (int pos = p0; pos < p1; ++pos) fn(*reinterpret_cast<const T*>(row + pos * (int)sizeof(T)), (I)(a + cbase + (I)pos));
-    }
-#elif RMI_PARTIAL_MODE == 2
     if (__all_sync(FULL, full)) {
       I idx = a + cbase;
 #pragma unroll 4
@@ -318,39 +288,6 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
       for (int pos = p0; pos < p1; ++pos)
         fn(*reinterpret_cast<const T*>(row + pos * (int)sizeof(T)), (I)(a + cbase + (I)pos));
     }
-#else
-    if (__all_sync(FULL, full)) {
-      // every lane has a full chunk: 8 x 128-bit shared loads, no position tests
-      I idx = a + cbase;
-#pragma unroll 4
-      for (int pp = 0; pp < 8; ++pp) {
-        uint4 v = *reinterpret_cast<const uint4*>(row + pp * 16);
-        T kk[KPP];
-        memcpy(kk, &v, 16);
-#pragma unroll
-        for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(idx + (I)t));
-        idx += (I)KPP;
-      }
-    } else {
-      // some lane starts or ends inside this chunk: ONE predicated walk for the whole warp
-      // (a two-path split would make the warp execute both paths for most chunks, because
-      // 32 leaves begin and end at 32 different phases)
-      const int p0 = lo_k < hi_k ? (int)(lo_k - cbase) : SW, p1 = lo_k < hi_k ? (int)(hi_k - cbase) : 0;
-      I idx = a + cbase;
-#pragma unroll 2
-      for (int pp = 0; pp < 8; ++pp) {
-        uint4 v = *reinterpret_cast<const uint4*>(row + pp * 16);
-        T kk[KPP];
-        memcpy(kk, &v, 16);
-#pragma unroll
-        for (int t = 0; t < KPP; ++t) {
-          const int pos = pp * KPP + t;
-          if (pos >= p0 && pos < p1) fn(kk[t], (I)(idx + (I)t));
-        }
-        idx += (I)KPP;
-      }
-    }
-#endif
     __syncwarp();
   }
 }
@@ -1249,10 +1186,8 @@ template <class T, int TOP>
 void launch_bounds_impl(const Launch& L, const T* keys, u64 n, const TopModel* d_top, u64 N, u64* d_S, BuildAux* d_aux,
                    bool allow_search) {
   if (allow_search && top_is_monotone_by_construction(TOP)) {
-    static const int arity = [] { const char* e = getenv("RMI_DEV_BOUNDS_ARITY"); return e ? atoi(e) : 2; }();
-    const unsigned sgrid = (unsigned)((N + 1 + BOUNDS_THREADS - 1) / BOUNDS_THREADS);
-    if (arity == 4) k_bounds_search<T, TOP, 4><<<sgrid, BOUNDS_THREADS, 0, L.stream>>>(keys, n, d_top, N, d_S);
-    else k_bounds_search<T, TOP, 2><<<sgrid, BOUNDS_THREADS, 0, L.stream>>>(keys, n, d_top, N, d_S);
+    k_bounds_search<T, TOP><<<(unsigned)((N + 1 + BOUNDS_THREADS - 1) / BOUNDS_THREADS), BOUNDS_THREADS, 0, L.stream>>>(
+        keys, n, d_top, N, d_S);
     count_launch();
     k_split<T, TOP><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux, 1);
     count_launch();
