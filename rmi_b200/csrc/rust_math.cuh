@@ -34,19 +34,7 @@ __device__ __forceinline__ double rust_fmax(double a, double b) { return fmax(a,
 template <class T> struct Key;
 template <> struct Key<u64> {
   static constexpr bool is_float = false;
-#ifdef RMI_MAGIC_CVT
-  // u64 -> f64 (round to nearest even) without the conversion unit: the two 32-bit halves are
-  // dropped into the mantissas of 2^84 and 2^52, (hi - (2^84 + 2^52)) is exact, and the final
-  // addition rounds once — the same value as cvt.rn.f64.u64, on the fixed-latency FP64 pipe.
-  // (experiment knob, off by default: DESIGN.md section 9)
-  __device__ __forceinline__ static double as_float(u64 k) {
-    const double hi = __hiloint2double(0x45300000, (int)(unsigned)(k >> 32));
-    const double lo = __hiloint2double(0x43300000, (int)(unsigned)k);
-    return __dadd_rn(__dadd_rn(hi, -19342813118337666422669312.0), lo);   // 2^84 + 2^52
-  }
-#else
   __device__ __forceinline__ static double as_float(u64 k) { return __ull2double_rn(k); }
-#endif
   __device__ __forceinline__ static u64 as_int(u64 k) { return k; }
   __device__ __forceinline__ static u64 minus_epsilon(u64 k) { return k - 1ull; }
   __device__ __forceinline__ static u64 plus_epsilon(u64 k) { return k + 1ull; }
