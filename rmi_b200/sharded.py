@@ -126,6 +126,46 @@ def plan_halo(bases: list[int], v: list[int], n_global: int) -> list[tuple[int, 
     return moves
 
 
+_NP_OF_KEY = {api.KEY_U64: np.uint64, api.KEY_U32: np.uint32, api.KEY_F64: np.float64}
+
+
+def key_type_of_path(path: str) -> int:
+    """src/main.rs:122-132: the key type is taken from the file NAME."""
+    import os
+    name = os.path.basename(path)
+    if "uint64" in name:
+        return api.KEY_U64
+    if "uint32" in name:
+        return api.KEY_U32
+    if "f64" in name:
+        return api.KEY_F64
+    raise api.RMIPanic("Data file must contain uint64, uint32, or f64.")
+
+
+def slab_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Rank r's slab of an n-key array: [n*r/world, n*(r+1)/world) — contiguous, disjoint, covering."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def read_slab(path: str, rank: int, world: int, key_type: int | None = None) -> tuple[np.ndarray, int]:
+    """Reads ONLY this rank's slab of a reference-format key file (u64 LE count + packed keys,
+    README.md:26-31 / src/load.rs:132-157) into host memory; returns (keys, total key count).
+    Every rank reads 1/world of the file, so a node's ranks load the data set in parallel."""
+    kt = key_type_of_path(path) if key_type is None else key_type
+    dt = np.dtype(_NP_OF_KEY[kt]).newbyteorder("<")
+    with open(path, "rb") as f:
+        head = f.read(8)
+        if len(head) != 8:
+            raise api.RMIPanic(f"Unable to read the key count of {path}")
+        n = int(np.frombuffer(head, dtype="<u8")[0])
+        lo, hi = slab_bounds(n, rank, world)
+        f.seek(8 + lo * dt.itemsize)
+        keys = np.fromfile(f, dtype=dt, count=hi - lo)
+    if keys.size != hi - lo:
+        raise api.RMIPanic(f"{path} is shorter than its header says ({n} keys)")
+    return keys.astype(_NP_OF_KEY[kt], copy=False), n
+
+
 class ShardedTrainingData:
     """This rank's slab of a globally sorted key array, in device memory with room behind it
     for halo keys.  `keys` must be a 1-D torch tensor on the rank's device (int64 storage for
@@ -145,6 +185,21 @@ class ShardedTrainingData:
         self.n_local = n_local
         self.halo_capacity = self.buf.numel() - n_local
         self.engine = CudaShardEngine(self)
+
+    @classmethod
+    def from_file(cls, path: str, device: torch.device, key_type: int | None = None, halo_capacity: int = 1 << 20,
+                  group=None) -> "ShardedTrainingData":
+        """The loader of a range-partitioned build: this rank's slab of the key file -> pinned host
+        memory -> its GPU (src/load.rs:132-157 for one slab)."""
+        rank, world = _world(group)
+        kt = key_type_of_path(path) if key_type is None else key_type
+        keys, _ = read_slab(path, rank, world, kt)
+        host = torch.from_numpy(keys.view(np.int64) if kt == api.KEY_U64 else (keys.view(np.int32) if kt == api.KEY_U32 else keys))
+        if torch.cuda.is_available():
+            host = host.pin_memory()
+        dev_keys = torch.empty(host.numel() + halo_capacity, dtype=host.dtype, device=device)
+        dev_keys[: host.numel()].copy_(host, non_blocking=False)
+        return cls(dev_keys, host.numel(), kt, halo_capacity, group)
 
     def grow_halo(self, capacity: int):
         """Re-home the slab in a buffer with room for `capacity` halo keys (a leaf reached further

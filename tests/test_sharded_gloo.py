@@ -156,3 +156,30 @@ def test_halo_planner():
     moves = sharded.plan_halo([0, 10, 12, 20], [13, 15, 20], 20)
     assert moves == [(0, 1, 0, 2), (0, 2, 0, 2), (1, 2, 0, 4)]
     assert sharded.plan_halo([0, 10], [10], 10) == []
+
+
+def test_slab_reader_partitions_a_key_file(tmp_path):
+    """read_slab: every rank reads only its contiguous slab; the slabs tile the file in order."""
+    import struct
+    from rmi_b200 import api, sharded
+    for suffix, keys in (("uint64", datasets.uniform_u64(10_007, seed=61)), ("uint32", datasets.uniform_u32(5_003, seed=62)),
+                         ("f64", datasets.uniform_f64(4_001, seed=63))):
+        path = str(tmp_path / f"keys_{suffix}")
+        with open(path, "wb") as f:
+            f.write(struct.pack("<Q", keys.size))
+            f.write(keys.tobytes())
+        for world in (1, 2, 3, 8):
+            parts = [sharded.read_slab(path, r, world) for r in range(world)]
+            assert all(n == keys.size for _, n in parts)
+            assert [p.size for p, _ in parts] == [b - a for a, b in (sharded.slab_bounds(keys.size, r, world) for r in range(world))]
+            assert np.array_equal(np.concatenate([p for p, _ in parts]), keys)
+            assert parts[0][0].dtype == keys.dtype
+    assert sharded.key_type_of_path("/x/wiki_ts_200M_uint64") == api.KEY_U64
+    with pytest.raises(api.RMIPanic):
+        sharded.key_type_of_path("/x/keys.bin")
+    short = str(tmp_path / "short_uint64")
+    with open(short, "wb") as f:
+        f.write(struct.pack("<Q", 100))
+        f.write(b"\0" * 80)
+    with pytest.raises(api.RMIPanic):
+        sharded.read_slab(short, 0, 1)
