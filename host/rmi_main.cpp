@@ -28,6 +28,7 @@
 #include "../include/rmi_b200.h"
 #include "codegen.hpp"
 #include "optimizer.hpp"
+#include "param_grid.hpp"
 
 using namespace rmihost;
 
@@ -36,65 +37,6 @@ namespace {
 [[noreturn]] void die(const std::string& msg) {
   std::fprintf(stderr, "rmi: %s\n", msg.c_str());
   std::exit(101);   // the exit status of a Rust panic
-}
-
-// ---- a JSON reader just large enough for --param-grid files (objects, arrays, strings, numbers, bools, null)
-struct JVal {
-  enum T { Null, Bool, Num, Str, Arr, Obj } t = Null;
-  bool b = false; double num = 0; std::string s;
-  std::vector<JVal> a;
-  std::vector<std::pair<std::string, JVal>> o;
-  const JVal* get(const std::string& k) const { for (auto& kv : o) if (kv.first == k) return &kv.second; return nullptr; }
-};
-struct JParser {
-  const std::string& src; size_t i = 0;
-  explicit JParser(const std::string& s) : src(s) {}
-  void ws() { while (i < src.size() && std::isspace((unsigned char)src[i])) ++i; }
-  JVal parse() {
-    ws();
-    if (i >= src.size()) die("param grid: unexpected end of JSON");
-    JVal v; char c = src[i];
-    if (c == '{') {
-      v.t = JVal::Obj; ++i; ws();
-      if (src[i] == '}') { ++i; return v; }
-      for (;;) {
-        ws(); JVal k = parse(); if (k.t != JVal::Str) die("param grid: object key must be a string");
-        ws(); if (src[i++] != ':') die("param grid: ':' expected");
-        v.o.push_back({k.s, parse()}); ws();
-        if (src[i] == ',') { ++i; continue; }
-        if (src[i] == '}') { ++i; break; }
-        die("param grid: ',' or '}' expected");
-      }
-    } else if (c == '[') {
-      v.t = JVal::Arr; ++i; ws();
-      if (src[i] == ']') { ++i; return v; }
-      for (;;) {
-        v.a.push_back(parse()); ws();
-        if (src[i] == ',') { ++i; continue; }
-        if (src[i] == ']') { ++i; break; }
-        die("param grid: ',' or ']' expected");
-      }
-    } else if (c == '"') {
-      v.t = JVal::Str; ++i;
-      while (i < src.size() && src[i] != '"') { if (src[i] == '\\' && i + 1 < src.size()) ++i; v.s += src[i++]; }
-      ++i;
-    } else if (!src.compare(i, 4, "true")) { v.t = JVal::Bool; v.b = true; i += 4; }
-    else if (!src.compare(i, 5, "false")) { v.t = JVal::Bool; i += 5; }
-    else if (!src.compare(i, 4, "null")) { i += 4; }
-    else { v.t = JVal::Num; char* e; v.num = std::strtod(src.c_str() + i, &e); i = e - src.c_str(); }
-    return v;
-  }
-};
-
-std::string json_num(double v) {
-  char buf[64];
-  auto r = std::to_chars(buf, buf + sizeof buf, v);
-  return std::string(buf, r.ptr);
-}
-std::string json_str(const std::string& s) {
-  std::string o = "\"";
-  for (char c : s) { if (c == '"' || c == '\\') o += '\\'; o += c; }
-  return o + "\"";
 }
 
 struct Args {
@@ -219,36 +161,26 @@ int main(int argc, char** argv) {
     std::ifstream in(a.opt["--param-grid"]);
     if (!in) die("could not read the parameter grid file");
     std::stringstream ss; ss << in.rdbuf();
-    std::string text = ss.str();
-    JVal root = JParser(text).parse();
-    const JVal* configs = root.get("configs");
-    if (!configs || configs->t != JVal::Arr) die("Configs must have an array as its value");
+    std::vector<GridEntry> grid;
+    try { grid = parse_param_grid(ss.str()); } catch (std::exception& e) { die(e.what()); }
     std::ofstream out(a.opt["--param-grid"] + "_results");
     if (!out) die("Could not write results file");
-    out << "{\"results\":[";
-    bool first = true;
-    for (auto& el : configs->a) {
-      const JVal* l = el.get("layers"); const JVal* b = el.get("branching factor"); const JVal* nsv = el.get("namespace");
-      if (!l || l->t != JVal::Str || !b || b->t != JVal::Num) die("called `Option::unwrap()` on a `None` value (param grid entry)");
+    std::vector<GridResult> results;
+    for (auto& g : grid) {   // one GPU executes builds back to back: the grid is walked in order
       rmi_result* r = nullptr;
-      train_one(l->s, (uint64_t)b->num, &r);
-      uint64_t size_bs = rmi_size(*r, true);
-      if (!first) out << ",";
-      first = false;
-      // NB "average error %" is computed from the MAX error in the reference (main.rs:211)
-      out << "{\"layers\":" << json_str(l->s) << ",\"branching factor\":" << (uint64_t)b->num << ",\"average error\":"
-          << json_num(r->model_avg_error) << ",\"average error %\":" << json_num((double)r->model_max_error / (double)num_rows * 100.0)
-          << ",\"average l2 error\":" << json_num(r->model_avg_l2_error) << ",\"average log2 error\":" << json_num(r->model_avg_log2_error)
-          << ",\"max error\":" << r->model_max_error << ",\"max error %\":" << json_num((double)r->model_max_error / (double)num_rows * 100.0)
-          << ",\"max log2 error\":" << json_num(r->model_max_log2_error) << ",\"size binary search\":" << size_bs << ",\"namespace\":"
-          << (nsv && nsv->t == JVal::Str ? json_str(nsv->s) : std::string("null")) << "}";
-      if (nsv && nsv->t == JVal::Str) {
-        try { output_rmi(nsv->s, *r, data_dir, code_kt, true, a.has("--zero-build-time") ? 0 : r->build_time_ns); }
+      train_one(g.layers, g.branching_factor, &r);
+      GridResult gr;
+      gr.entry = g;
+      gr.avg_error = r->model_avg_error; gr.avg_l2 = r->model_avg_l2_error; gr.avg_log2 = r->model_avg_log2_error;
+      gr.max_log2 = r->model_max_log2_error; gr.max_error = r->model_max_error; gr.size_bs = rmi_size(*r, true);
+      results.push_back(gr);
+      if (g.has_namespace) {
+        try { output_rmi(g.ns, *r, data_dir, code_kt, true, a.has("--zero-build-time") ? 0 : r->build_time_ns); }
         catch (std::exception& e) { die(e.what()); }
       }
       rmi_result_free(r);
     }
-    out << "]}";
+    out << grid_results_json(results, num_rows);
   } else if (have_ns) {   // main.rs:263-333
     const std::string ns = a.pos[1];
     rmi_result* r = nullptr;

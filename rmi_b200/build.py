@@ -68,7 +68,7 @@ def build_cli(force: bool = False) -> str:
     """The `rmi` command-line front end (host/rmi_main.cpp) linked against librmi_b200.so."""
     lib = build_library()
     root = os.path.dirname(HERE)
-    srcs = [os.path.join(root, "host", f) for f in ("rmi_main.cpp", "codegen.hpp", "optimizer.hpp", "cache_fix.hpp")]
+    srcs = [os.path.join(root, "host", f) for f in ("rmi_main.cpp", "codegen.hpp", "optimizer.hpp", "cache_fix.hpp", "param_grid.hpp")]
     os.makedirs(os.path.dirname(CLI_PATH), exist_ok=True)
     if force or _stale(CLI_PATH, srcs + [lib, os.path.join(root, "include", "rmi_b200.h")]):
         cmd = ["g++", "-std=c++17", "-O2", "-Wall", srcs[0], "-o", CLI_PATH, "-L", LIB_DIR, "-lrmi_b200",
