@@ -379,8 +379,8 @@ def main():
                       "l2": "inputs (1.6 GB) larger than L2, no flush needed",
                       "parallelism": "1 GPU" if world == 1 else
                       f"range-partitioned over {world} GPUs: one global RMI with {N} leaves over {n * world} keys; "
-                      "all-reduce of top-model sums (64 B), leaf boundaries ((N+1)*8 B) and leaf records (N*32 B), "
-                      "halo send/recv between neighbours",
+                      "per build: all-reduce of the top-model sums (64 B), of the leaf boundaries ((N+1)*8 B) and of the leaf "
+                      "records (N*24 B); halo keys between neighbours are fetched once per data set",
                       "timing": "CUDA events around K synchronous builds, max over ranks",
                       "roofline_note": "dominant kernel = the fused leaf fit + forward pass (k_leaf); on one GPU it runs as 4 launch "
                                        "slices per build (their results cross PCIe while the next slice computes): achieved = "
