@@ -31,7 +31,17 @@ namespace rmi {
 namespace {
 
 constexpr int BOUNDS_THREADS = 256;
-constexpr int LEAF_THREADS = 128;
+// Compile-time experiment knobs (defaults = the measured best; variants are built next to the default
+// library with RMI_BUILD_TAG / RMI_NVCC_DEFS, rmi_b200/build.py, and timed by tools/gpu_variants.sh).
+#ifndef RMI_LEAF_THREADS
+#define RMI_LEAF_THREADS 128
+#endif
+#ifdef RMI_LEAF_MIN_BLOCKS
+#define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS, RMI_LEAF_MIN_BLOCKS)
+#else
+#define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS)
+#endif
+constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
 constexpr int RCP_TABLE = 512;
 
 __device__ __forceinline__ void set_status(BuildAux* aux, unsigned bit) { atomicOr(&aux->status, bit); }
@@ -830,7 +840,7 @@ constexpr size_t leaf_smem_bytes() {
 }
 
 template <class T, class I, int LEAF, bool DUPS>
-__global__ void __launch_bounds__(LEAF_THREADS)
+__global__ void RMI_LEAF_BOUNDS
 k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restrict__ S, BuildAux* aux,
        double* __restrict__ params, u64* __restrict__ errors, u64* __restrict__ counts,
        const u32* __restrict__ long_list, int mode_word, u32 block_offset, u32 total_blocks) {

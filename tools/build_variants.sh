@@ -1,0 +1,19 @@
+#!/bin/bash
+# Builds experiment variants of librmi_b200.so next to the default library (CPU only: nvcc cross-compiles).
+# Each variant is the same source with other compile-time knobs; tools/gpu_variants.sh times them on a GPU box.
+#   tools/build_variants.sh            # all variants below
+#   tools/build_variants.sh s3 t64     # a subset
+declare -A DEFS=(
+  [s3]="-DRMI_SSTAGES=3"                 # three copy stages in the row ring instead of two
+  [t64]="-DRMI_LEAF_THREADS=64"          # 64-lane blocks: finer tail, more blocks per SM
+  [t256]="-DRMI_LEAF_THREADS=256"        # 256-lane blocks: fewer reciprocal-table initialisations
+  [s3t64]="-DRMI_SSTAGES=3 -DRMI_LEAF_THREADS=64"
+)
+names=("$@")
+[ ${#names[@]} -eq 0 ] && names=("${!DEFS[@]}")
+for n in "${names[@]}"; do
+  echo "== variant $n: ${DEFS[$n]}"
+  RMI_BUILD_TAG=$n RMI_NVCC_DEFS="${DEFS[$n]}" python rmi_b200/build.py | tail -1 || exit 1
+done
+python rmi_b200/build.py | tail -1     # relink the CLI against the default library
+ls -la rmi_b200/lib/
