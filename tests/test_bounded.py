@@ -113,3 +113,51 @@ def test_cli_bounded_end_to_end_on_gpu(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     out = build_and_check(work, keys)
     assert out.startswith("ok") and int(out.split()[2]) <= 8
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_host_cache_fix_randomised_against_python(tool, tmp_path, seed):
+    """Small random key sets of very different shapes (clusters, huge gaps, keys up to 2^64 - 1, long runs of
+    equal keys, consecutive integers) and line sizes: the host scan and the Python restatement must emit the
+    same knots, or both must panic."""
+    from oracle import cache_fix as ocf
+    rng = np.random.Generator(np.random.MT19937(1000 + seed))
+    n = int(rng.integers(40, 900))
+    shape = seed % 6
+    if shape == 0:
+        keys = rng.integers(1, 1 << 63, size=n, dtype=np.uint64)
+    elif shape == 1:      # clusters separated by huge gaps
+        centres = rng.integers(1 << 20, 1 << 62, size=5, dtype=np.uint64)
+        keys = (centres[rng.integers(0, 5, size=n)] + rng.integers(0, 1000, size=n, dtype=np.uint64)).astype(np.uint64)
+    elif shape == 2:      # up to the top of the u64 range
+        keys = (np.uint64((1 << 64) - 1) - rng.integers(0, 1 << 40, size=n, dtype=np.uint64)).astype(np.uint64)
+    elif shape == 3:      # long runs of equal keys
+        keys = np.repeat(rng.integers(1, 1 << 50, size=max(n // 20, 3), dtype=np.uint64), 20)
+    elif shape == 4:      # consecutive integers with a few holes
+        keys = np.arange(5, 5 + n, dtype=np.uint64)
+        keys = np.delete(keys, rng.integers(0, n, size=n // 10))
+    else:                 # tiny keys incl. 1 (key - 1 == 0 == the initial last_key)
+        keys = rng.integers(1, 4 * n, size=n, dtype=np.uint64)
+    keys = np.sort(keys)
+    line = int(rng.choice([1, 2, 3, 8, 16, 37]))
+    try:
+        want = ocf.cache_fix(keys.tolist(), line)
+    except ocf.CacheFixPanic:
+        with pytest.raises(RuntimeError):
+            host_cache_fix(tool, str(tmp_path), keys, line)
+        return
+    got, _ = host_cache_fix(tool, str(tmp_path), keys, line)
+    assert [tuple(map(int, r)) for r in got] == want
+    # the property the spline exists for: interpolating between the knots puts every key in its own line
+    kk, vv = got[:, 0].astype(object), got[:, 1].astype(object)
+    firsts = {}
+    for i, k in enumerate(keys.tolist()):
+        firsts.setdefault(k, i)
+    for k, off in list(firsts.items())[:: max(1, len(firsts) // 200)]:
+        j = int(np.searchsorted(got[:, 0], np.uint64(k), side="left"))
+        if j == 0 or int(kk[j]) == k and j == 0:
+            continue
+        x0, y0, x1, y1 = int(kk[j - 1]), int(vv[j - 1]), int(kk[j]), int(vv[j])
+        t = float(k - x0) / float(x1 - x0)
+        pred = int(ocf._fma(1.0 - t, float(y0), t * float(y1)))
+        assert pred // line == off // line, (k, off, pred, line)
