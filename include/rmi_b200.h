@@ -216,6 +216,19 @@ int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out);
 void rmi_shard_build_destroy(rmi_shard_build* b);
 uint32_t rmi_params_per_model(const char* leaf_model_name);
 
+/* ---- `--bounded` support: rmi_lib::cache_fix (reference rmi_lib/src/cache_fix.rs:106-150) ----------
+ * The error-bounded spline over key -> first-occurrence offset whose interpolation always lands in
+ * the key's line (offset / line_size).  A greedy, strictly serial HOST scan (as in the reference;
+ * SURVEY.md section 8(f)4): no device work.  train_bounded (train/mod.rs:156-184) is then
+ *     knots = rmi_cache_fix(keys);  ds = rmi_dataset_create(knot keys);  rmi_train(ds, ...)
+ * — the knots' offsets are 0, 1, 2, ..., i.e. the knot keys are an ordinary sorted duplicate-free
+ * data set.  host_keys: n sorted u64 keys ("Can only construct a bounded RMI on u64 data",
+ * src/main.rs:285-286).  *out_points is owned by the library: release with rmi_spline_free. */
+typedef struct { uint64_t key, offset; } rmi_spline_point;
+int rmi_cache_fix(const uint64_t* host_keys, uint64_t n, uint64_t line_size, rmi_spline_point** out_points,
+                  uint64_t* out_count);
+void rmi_spline_free(rmi_spline_point* points);
+
 /* Message of the last failure on the calling thread ("" if none). */
 const char* rmi_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */

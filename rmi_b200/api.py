@@ -74,6 +74,8 @@ def load_library():
         L.rmi_train_with_top.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32,
                                          C.POINTER(C.POINTER(_Result))]
         L.rmi_result_free.argtypes = [C.POINTER(_Result)]
+        L.rmi_cache_fix.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.rmi_spline_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -160,6 +162,39 @@ class RMITrainingData:
             self.close()
         except Exception:
             pass
+
+
+def cache_fix(keys: np.ndarray, line_size: int) -> np.ndarray:
+    """rmi_lib::cache_fix (cache_fix.rs:106-150): the error-bounded spline over key -> offset whose
+    interpolation always lands in the key's line.  A serial HOST scan (no GPU).  Returns the knots as a
+    (K, 2) uint64 array of (key, offset)."""
+    keys = np.ascontiguousarray(keys)
+    if keys.dtype != np.uint64:
+        raise RMIPanic("Can only construct a bounded RMI on u64 data.")
+    L = load_library()
+    pts, cnt = C.c_void_p(), C.c_uint64(0)
+    _check(L.rmi_cache_fix(keys.ctypes.data_as(C.c_void_p), keys.size, int(line_size), C.byref(pts), C.byref(cnt)))
+    try:
+        n = int(cnt.value)
+        out = np.frombuffer((C.c_uint64 * (2 * n)).from_address(pts.value), dtype=np.uint64).reshape(n, 2).copy() if n else \
+            np.zeros((0, 2), dtype=np.uint64)
+    finally:
+        L.rmi_spline_free(pts)
+    return out
+
+
+def train_bounded(keys: np.ndarray, model_spec: str, branch_factor: int, line_size: int, device: int = 0, flags: int = 0):
+    """rmi_lib::train_bounded (train/mod.rs:156-184): cache_fix on the host, then the two-layer RMI over the
+    spline's knots on the GPU.  Returns (TrainedRMI with num_data_rows = len(keys), knots) — the pair the
+    reference keeps in TrainedRMI.cache_fix."""
+    knots = cache_fix(keys, line_size)
+    ds = RMITrainingData(np.ascontiguousarray(knots[:, 0]), device=device)
+    try:
+        rmi = train(ds, model_spec, branch_factor, flags)
+    finally:
+        ds.close()
+    rmi.num_data_rows = int(np.asarray(keys).size)
+    return rmi, knots
 
 
 def load_data(path: str, key_type: int = -1, device: int = 0) -> RMITrainingData:

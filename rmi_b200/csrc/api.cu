@@ -18,6 +18,7 @@
 
 #include "../../include/rmi_b200.h"
 #include "kernels.h"
+#include "../../host/cache_fix.hpp"
 
 using namespace rmi;
 
@@ -331,6 +332,24 @@ int rmi_dataset_load_file(const char* path, int key_type_or_negative, int device
   *out = ds;
   return RMI_OK;
 }
+
+int rmi_cache_fix(const uint64_t* host_keys, uint64_t n, uint64_t line_size, rmi_spline_point** out_points,
+                  uint64_t* out_count) {
+  g_last_error.clear();
+  if (!host_keys || !out_points || !out_count) return fail(RMI_ERR_INVALID, "rmi_cache_fix: null argument");
+  try {
+    std::vector<rmihost::SplinePoint> sp = rmihost::cache_fix(host_keys, n, line_size);
+    auto* p = static_cast<rmi_spline_point*>(std::malloc(std::max<size_t>(sp.size(), 1) * sizeof(rmi_spline_point)));
+    if (!p) return fail(RMI_ERR_INVALID, "rmi_cache_fix: out of host memory");
+    for (size_t i = 0; i < sp.size(); ++i) { p[i].key = sp[i].first; p[i].offset = sp[i].second; }
+    *out_points = p;
+    *out_count = sp.size();
+    return RMI_OK;
+  } catch (const std::exception& e) {
+    return fail(RMI_ERR_PANIC, e.what());   // the reference's assert! messages (cache_fix.rs)
+  }
+}
+void rmi_spline_free(rmi_spline_point* points) { std::free(points); }
 
 int rmi_dataset_replicate(const rmi_dataset* src, int device, rmi_dataset** out) {
   g_last_error.clear();

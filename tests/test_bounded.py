@@ -161,3 +161,19 @@ def test_host_cache_fix_randomised_against_python(tool, tmp_path, seed):
         t = float(k - x0) / float(x1 - x0)
         pred = int(ocf._fma(1.0 - t, float(y0), t * float(y1)))
         assert pred // line == off // line, (k, off, pred, line)
+
+
+def test_library_cache_fix_through_the_c_abi():
+    """rmi_cache_fix (include/rmi_b200.h) is host-only: it runs without a GPU and must equal the Python restatement."""
+    import rmi_b200
+    from oracle import cache_fix as ocf
+    keys = datasets.with_duplicates(datasets.uniform_u64(5_000, seed=31), frac=0.2)
+    keys = keys[keys > 0]
+    for line in (1, 8, 32):
+        got = rmi_b200.cache_fix(keys, line)
+        assert got.dtype == np.uint64 and got.shape[1] == 2
+        assert [tuple(map(int, r)) for r in got] == ocf.cache_fix(keys.tolist(), line)
+    with pytest.raises(rmi_b200.RMIPanic, match="fewer items"):
+        rmi_b200.cache_fix(keys[:4], 8)
+    with pytest.raises(rmi_b200.RMIPanic, match="u64"):
+        rmi_b200.cache_fix(keys.astype(np.float64), 8)
