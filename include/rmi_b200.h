@@ -229,6 +229,36 @@ int rmi_cache_fix(const uint64_t* host_keys, uint64_t n, uint64_t line_size, rmi
                   uint64_t* out_count);
 void rmi_spline_free(rmi_spline_point* points);
 
+/* ---- The rest of rmi_lib's public surface (host-side code, no device work of their own) ---------
+ * rmi_lib::rmi_size (codegen.rs:375-394): bytes of the model's parameters (+ 8 per leaf with the
+ * last-layer errors, + 16 per spline knot of a bounded RMI). */
+uint64_t rmi_model_size(const rmi_result* r, int include_errors, uint64_t num_spline_points);
+
+/* rmi_lib::output_rmi (codegen.rs:757-788): writes <out_dir>/<ns>.cpp, <ns>.h, <ns>_data.h and the
+ * parameter blobs <data_dir>/<ns>_L{i}_PARAMETERS, byte for byte in the reference's layouts.
+ * key_type: the KeyType handed to codegen (src/main.rs:122-132: uint32 FILES keep RMI_KEY_U64).
+ * knots != NULL: a `--bounded` RMI (TrainedRMI.cache_fix = (line_size, knots); num_data_rows = the
+ * length of the ORIGINAL data set, train/mod.rs:175-176).  `r` must hold the leaf tables (not
+ * RMI_FLAG_STATS_ONLY). */
+int rmi_output_rmi(const char* ns, const rmi_result* r, const char* data_dir, const char* out_dir, int key_type,
+                   int include_errors, uint64_t build_time_ns, const rmi_spline_point* knots, uint64_t num_knots,
+                   uint64_t line_size, uint64_t num_data_rows);
+
+/* optimizer::find_pareto_efficient_configs (optimizer.rs:233-249): the two-phase search over
+ * (models, branching factor); every candidate is one stats-only build.  `replicas` are
+ * rmi_datasets holding the SAME keys on one or more devices (rmi_dataset_replicate): the
+ * independent builds are spread over them, one host thread per replica.  RMI_OPTIMIZER_PROFILE
+ * (fast | memory | disk) selects the grid as in the reference (optimizer.rs:15-57).  At most
+ * `capacity` entries are written, sorted by average log2 error; *out_count = size of the front. */
+typedef struct {
+  char models[64];
+  uint64_t branching_factor;
+  double average_log2_error, max_log2_error;
+  uint64_t size;
+} rmi_config_stats;
+int rmi_find_pareto_efficient_configs(const rmi_dataset* const* replicas, int num_replicas, uint64_t restrict_to,
+                                      uint32_t flags, rmi_config_stats* out, uint64_t capacity, uint64_t* out_count);
+
 /* Message of the last failure on the calling thread ("" if none). */
 const char* rmi_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */

@@ -44,6 +44,12 @@ class _Result(C.Structure):
     ]
 
 
+class _ConfigStats(C.Structure):
+    """struct rmi_config_stats (optimizer.rs:153-160 RMIStatistics)."""
+    _fields_ = [("models", C.c_char * 64), ("branching_factor", C.c_uint64), ("average_log2_error", C.c_double),
+                ("max_log2_error", C.c_double), ("size", C.c_uint64)]
+
+
 _lib = None
 
 
@@ -76,6 +82,12 @@ def load_library():
         L.rmi_result_free.argtypes = [C.POINTER(_Result)]
         L.rmi_cache_fix.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.rmi_spline_free.argtypes = [C.c_void_p]
+        L.rmi_model_size.restype = C.c_uint64
+        L.rmi_model_size.argtypes = [C.POINTER(_Result), C.c_int, C.c_uint64]
+        L.rmi_output_rmi.argtypes = [C.c_char_p, C.POINTER(_Result), C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_uint64,
+                                     C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
+        L.rmi_find_pareto_efficient_configs.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint64, C.c_uint32,
+                                                        C.POINTER(_ConfigStats), C.c_uint64, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -195,6 +207,62 @@ def train_bounded(keys: np.ndarray, model_spec: str, branch_factor: int, line_si
         ds.close()
     rmi.num_data_rows = int(np.asarray(keys).size)
     return rmi, knots
+
+
+def _result_ptr(rmi):
+    """struct rmi_result* of a TrainedRMI returned by train() (or a ctypes _Result the caller filled in)."""
+    if isinstance(rmi, _Result):
+        return C.pointer(rmi)
+    if rmi._res is None or rmi._res.res is None:
+        raise RMIError("this TrainedRMI does not own a struct rmi_result")
+    return rmi._res.res
+
+
+def rmi_size(rmi, include_errors: bool = True, num_spline_points: int = 0) -> int:
+    """rmi_lib::rmi_size (codegen.rs:375-394)."""
+    return int(load_library().rmi_model_size(_result_ptr(rmi), int(include_errors), int(num_spline_points)))
+
+
+def output_rmi(namespace: str, rmi, data_dir: str, key_type: int = KEY_U64, include_errors: bool = True, out_dir: str = ".",
+               build_time_ns: int | None = None, cache_fix_knots: np.ndarray | None = None, line_size: int = 0,
+               num_data_rows: int = 0) -> None:
+    """rmi_lib::output_rmi (codegen.rs:757-788): <out_dir>/<ns>.cpp/.h/_data.h + <data_dir>/<ns>_L*_PARAMETERS.
+    key_type is the KeyType handed to codegen (uint32 FILES keep KEY_U64, src/main.rs:122-132).
+    cache_fix_knots: the (K, 2) array of a train_bounded() build."""
+    os.makedirs(data_dir, exist_ok=True)
+    ptr = _result_ptr(rmi)
+    if build_time_ns is None:
+        build_time_ns = int(ptr.contents.build_time_ns)
+    knots = None if cache_fix_knots is None else np.ascontiguousarray(cache_fix_knots, dtype=np.uint64)
+    _check(load_library().rmi_output_rmi(
+        namespace.encode(), ptr, data_dir.encode(), out_dir.encode(), int(key_type), int(include_errors), int(build_time_ns),
+        None if knots is None else knots.ctypes.data_as(C.c_void_p), 0 if knots is None else knots.shape[0], int(line_size),
+        int(num_data_rows)))
+
+
+def find_pareto_efficient_configs(replicas, restrict_to: int = 10, flags: int = 0) -> list[dict]:
+    """optimizer::find_pareto_efficient_configs (optimizer.rs:233-249).  `replicas`: one RMITrainingData or a
+    list holding the same keys on several devices (RMITrainingData.replicate); the independent stats-only
+    builds are spread over them."""
+    reps = [replicas] if isinstance(replicas, RMITrainingData) else list(replicas)
+    handles = (C.c_void_p * len(reps))(*[r._h for r in reps])
+    cap = 64
+    out = (_ConfigStats * cap)()
+    cnt = C.c_uint64(0)
+    _check(load_library().rmi_find_pareto_efficient_configs(handles, len(reps), int(restrict_to), int(flags), out, cap, C.byref(cnt)))
+    return [dict(models=out[i].models.decode(), branching_factor=int(out[i].branching_factor),
+                 average_log2_error=float(out[i].average_log2_error), max_log2_error=float(out[i].max_log2_error),
+                 size=int(out[i].size)) for i in range(min(int(cnt.value), cap))]
+
+
+def train_for_size(data: RMITrainingData, max_size: int, flags: int = 0) -> TrainedRMI:
+    """rmi_lib::train_for_size (train/mod.rs:128-154): the first configuration of the (un-narrowed) Pareto
+    front that is smaller than max_size bytes, trained in full."""
+    front = find_pareto_efficient_configs(data, 1000, flags)
+    pick = next((c for c in front if c["size"] < max_size), None)
+    if pick is None:
+        raise RMIPanic(f"Could not find any configurations smaller than {max_size}")
+    return train(data, pick["models"], pick["branching_factor"], flags)
 
 
 def load_data(path: str, key_type: int = -1, device: int = 0) -> RMITrainingData:

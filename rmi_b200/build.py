@@ -17,7 +17,8 @@ OBJ_DIR = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
 
 SOURCES = ["kernels_top.cu", "kernels_leaf.cu", "kernels_shard.cu", "api.cu"]
 HEADERS = ["rust_math.cuh", "models.cuh", "device_util.cuh", "spline.cuh", "kernels.h",
-           os.path.join("..", "..", "include", "rmi_b200.h"), os.path.join("..", "..", "host", "cache_fix.hpp")]
+           os.path.join("..", "..", "include", "rmi_b200.h"), os.path.join("..", "..", "host", "cache_fix.hpp"), os.path.join("..", "..", "host", "codegen.hpp"),
+           os.path.join("..", "..", "host", "optimizer.hpp")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: the reference fuses a multiply-add only where it writes mul_add; everything

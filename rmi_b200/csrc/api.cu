@@ -19,6 +19,8 @@
 #include "../../include/rmi_b200.h"
 #include "kernels.h"
 #include "../../host/cache_fix.hpp"
+#include "../../host/codegen.hpp"
+#include "../../host/optimizer.hpp"
 
 using namespace rmi;
 
@@ -350,6 +352,53 @@ int rmi_cache_fix(const uint64_t* host_keys, uint64_t n, uint64_t line_size, rmi
   }
 }
 void rmi_spline_free(rmi_spline_point* points) { std::free(points); }
+
+uint64_t rmi_model_size(const rmi_result* r, int include_errors, uint64_t num_spline_points) {
+  if (!r) return 0;
+  return rmihost::rmi_size(*r, include_errors != 0, nullptr) + 16 * num_spline_points;
+}
+
+int rmi_output_rmi(const char* ns, const rmi_result* r, const char* data_dir, const char* out_dir, int key_type,
+                   int include_errors, uint64_t build_time_ns, const rmi_spline_point* knots, uint64_t num_knots,
+                   uint64_t line_size, uint64_t num_data_rows) {
+  g_last_error.clear();
+  if (!ns || !r || !data_dir || !out_dir) return fail(RMI_ERR_INVALID, "rmi_output_rmi: null argument");
+  try {
+    std::vector<rmihost::SplinePoint> sp;
+    rmihost::CacheFixInfo cf;
+    if (knots) {
+      sp.reserve(num_knots);
+      for (uint64_t i = 0; i < num_knots; ++i) sp.emplace_back(knots[i].key, knots[i].offset);
+      cf.line_size = line_size; cf.spline = &sp; cf.num_data_rows = num_data_rows;
+    }
+    rmihost::output_rmi(ns, *r, data_dir, key_type, include_errors != 0, build_time_ns, out_dir, knots ? &cf : nullptr);
+    return RMI_OK;
+  } catch (const std::exception& e) {
+    return fail(RMI_ERR_PANIC, e.what());
+  }
+}
+
+int rmi_find_pareto_efficient_configs(const rmi_dataset* const* replicas, int num_replicas, uint64_t restrict_to,
+                                      uint32_t flags, rmi_config_stats* out, uint64_t capacity, uint64_t* out_count) {
+  g_last_error.clear();
+  if (!replicas || num_replicas < 1 || !out_count || (capacity && !out))
+    return fail(RMI_ERR_INVALID, "rmi_find_pareto_efficient_configs: bad argument");
+  try {
+    std::vector<const rmi_dataset*> reps(replicas, replicas + num_replicas);
+    std::vector<rmihost::RMIStatistics> front = rmihost::find_pareto_efficient_configs(reps, (size_t)restrict_to, flags, false);
+    *out_count = front.size();
+    for (size_t i = 0; i < front.size() && i < capacity; ++i) {
+      std::snprintf(out[i].models, sizeof out[i].models, "%s", front[i].models.c_str());
+      out[i].branching_factor = front[i].branching_factor;
+      out[i].average_log2_error = front[i].average_log2_error;
+      out[i].max_log2_error = front[i].max_log2_error;
+      out[i].size = front[i].size;
+    }
+    return RMI_OK;
+  } catch (const std::exception& e) {
+    return fail(RMI_ERR_PANIC, e.what());
+  }
+}
 
 int rmi_dataset_replicate(const rmi_dataset* src, int device, rmi_dataset** out) {
   g_last_error.clear();
