@@ -134,3 +134,38 @@ def test_cli_optimize_on_gpu_one_and_two_replicas(tmp_path):
         outs.append(cfgs)
         assert "Models" in r.stdout and "AvgLg2" in r.stdout
     assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+def test_python_mirrors_of_the_public_api_on_gpu(tmp_path, monkeypatch):
+    """find_pareto_efficient_configs / train_for_size / train_bounded / output_rmi through rmi_b200 (the same
+    library entry points the CLI uses)."""
+    import numpy as np
+    import rmi_b200
+    from tests.test_codegen import build_and_check
+    monkeypatch.setenv("RMI_OPTIMIZER_PROFILE", "fast")
+    keys = datasets.uniform_u64(400_000, seed=12)
+    keys = keys[keys > 0]
+    ds = rmi_b200.RMITrainingData(keys)
+    front = rmi_b200.find_pareto_efficient_configs(ds, 10)
+    assert 2 <= len(front) <= 10
+    errs = [c["average_log2_error"] for c in front]
+    sizes = [c["size"] for c in front]
+    assert errs == sorted(errs) and all(a > b for a, b in zip(sizes, sizes[1:]))
+    two = rmi_b200.find_pareto_efficient_configs([ds, ds.replicate(0)], 10)
+    assert two == front
+    # train_for_size: the most accurate configuration below the bound
+    bound = sizes[len(sizes) // 2] + 1
+    m = rmi_b200.train_for_size(ds, bound)
+    assert rmi_b200.rmi_size(m) < bound
+    with pytest.raises(rmi_b200.RMIPanic, match="smaller than"):
+        rmi_b200.train_for_size(ds, 8)
+    # train_bounded + output_rmi: the reference's cache-fix property on the generated code
+    rmi, knots = rmi_b200.train_bounded(keys, "linear_spline,linear", 1024, 8)
+    assert rmi.num_data_rows == keys.size and rmi.num_rmi_rows == knots.shape[0]
+    work = str(tmp_path)
+    rmi_b200.output_rmi("rmi", rmi, os.path.join(work, "rmi_data"), out_dir=work, build_time_ns=0, cache_fix_knots=knots,
+                        line_size=8, num_data_rows=keys.size)
+    out = build_and_check(work, keys)
+    assert out.startswith("ok") and int(out.split()[2]) <= 8
+    assert f"const size_t RMI_SIZE = {rmi_b200.rmi_size(rmi, num_spline_points=knots.shape[0])};" in open(os.path.join(work, "rmi.h")).read()
