@@ -6,14 +6,13 @@ the knots -> generated code with the spline lookup — against the reference's o
 CPU-only: the RMI over the knots comes from the oracle; the GPU test at the bottom runs the
 `rmi` CLI with --bounded end to end."""
 import os
-import struct
 import subprocess
 
 import numpy as np
 import pytest
 
 from tests import datasets
-from tests.test_codegen import ROOT, build_and_check, dump_model, tool, write_keyfile  # noqa: F401  (tool is a fixture)
+from tests.test_codegen import build_and_check, dump_model, tool, write_keyfile  # noqa: F401  (tool is a fixture)
 
 
 def host_cache_fix(tool_exe, work, keys, line):

@@ -140,7 +140,6 @@ def test_cli_optimize_on_gpu_one_and_two_replicas(tmp_path):
 def test_python_mirrors_of_the_public_api_on_gpu(tmp_path, monkeypatch):
     """find_pareto_efficient_configs / train_for_size / train_bounded / output_rmi through rmi_b200 (the same
     library entry points the CLI uses)."""
-    import numpy as np
     import rmi_b200
     from tests.test_codegen import build_and_check
     monkeypatch.setenv("RMI_OPTIMIZER_PROFILE", "fast")
