@@ -110,17 +110,24 @@ int main(int argc, char** argv) {
   std::vector<const rmi_dataset*> replicas{ds};
   std::vector<rmi_dataset*> owned_replicas;
   if (a.has("--devices") && (a.has("--optimize") || a.has("--max-size"))) {
+    // one worker thread per listed device; a device listed more than once gets more workers on the SAME
+    // resident copy (the data set is immutable and rmi_train is re-entrant), other devices get a replica
     std::stringstream dl(a.opt["--devices"]);
     std::string tok;
+    std::map<int, const rmi_dataset*> on_device{{device, ds}};
     bool first_tok = true;
     while (std::getline(dl, tok, ',')) {
       if (tok.empty()) continue;
       int d = std::atoi(tok.c_str());
-      if (first_tok) { first_tok = false; if (d == device) continue; }
-      rmi_dataset* rep = nullptr;
-      if (rmi_dataset_replicate(ds, d, &rep) != RMI_OK) die(rmi_last_error());
-      owned_replicas.push_back(rep);
-      replicas.push_back(rep);
+      if (first_tok) { first_tok = false; if (d == device) continue; }   // the loaded copy already has its worker
+      auto it = on_device.find(d);
+      if (it == on_device.end()) {
+        rmi_dataset* rep = nullptr;
+        if (rmi_dataset_replicate(ds, d, &rep) != RMI_OK) die(rmi_last_error());
+        owned_replicas.push_back(rep);
+        it = on_device.emplace(d, rep).first;
+      }
+      replicas.push_back(it->second);
     }
   }
   auto free_replicas = [&]() { for (auto* r : owned_replicas) rmi_dataset_destroy(r); owned_replicas.clear(); };
