@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--exact-top", action="store_true", help="RMI_FLAG_TOP_FIT_EXACT (serial top fit)")
     ap.add_argument("--cpu-sample-div", type=int, default=8, help="cpu baseline runs on n/div keys, N/div leaves")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     return ap.parse_args()
 
 
