@@ -8,6 +8,7 @@ declare -A DEFS=(
   [t64]="-DRMI_LEAF_THREADS=64"          # 64-lane blocks: finer tail, more blocks per SM
   [t256]="-DRMI_LEAF_THREADS=256"        # 256-lane blocks: fewer reciprocal-table initialisations
   [s3t64]="-DRMI_SSTAGES=3 -DRMI_LEAF_THREADS=64"
+  [u4]="-DRMI_PARTIAL_UNROLL=4"          # partial-chunk walk unrolled 4x instead of 2x
   [pb]="-DRMI_PIPELINED_BOUNDS"          # leaf-boundary search sliced and overlapped with the leaf kernel's slices
 )
 names=("$@")
