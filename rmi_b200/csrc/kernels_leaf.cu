@@ -45,6 +45,7 @@ constexpr int BOUNDS_THREADS = 256;
 #define RMI_PARTIAL_UNROLL 2   // unroll factor of the one-key-per-iteration walk over partially used chunks (~40% of the keys)
 #endif
 constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
+constexpr int PARTIAL_UNROLL = RMI_PARTIAL_UNROLL;
 constexpr int RCP_TABLE = 512;
 
 __device__ __forceinline__ void set_status(BuildAux* aux, unsigned bit) { atomicOr(&aux->status, bit); }
@@ -297,7 +298,7 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
       // loop (full lanes: all SW keys), so the warp pays max(p1 - p0) iterations once instead
       // of a full-chunk path plus a partial-chunk path
       const int p0 = lo_k < hi_k ? (int)(lo_k - cbase) : 0, p1 = lo_k < hi_k ? (int)(hi_k - cbase) : 0;
-#pragma unroll RMI_PARTIAL_UNROLL
+#pragma unroll PARTIAL_UNROLL
       for (int pos = p0; pos < p1; ++pos)
         fn(*reinterpret_cast<const T*>(row + pos * (int)sizeof(T)), (I)(a + cbase + (I)pos));
     }
