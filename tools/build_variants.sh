@@ -1,4 +1,5 @@
 #!/bin/bash
+set -o pipefail
 # Builds experiment variants of librmi_b200.so next to the default library (CPU only: nvcc cross-compiles).
 # Each variant is the same source with other compile-time knobs; tools/gpu_variants.sh times them on a GPU box.
 #   tools/build_variants.sh            # all variants below
@@ -15,7 +16,8 @@ names=("$@")
 [ ${#names[@]} -eq 0 ] && names=("${!DEFS[@]}")
 for n in "${names[@]}"; do
   echo "== variant $n: ${DEFS[$n]}"
-  RMI_BUILD_TAG=$n RMI_NVCC_DEFS="${DEFS[$n]}" python rmi_b200/build.py | tail -1 || exit 1
+  RMI_BUILD_TAG=$n RMI_NVCC_DEFS="${DEFS[$n]}" python rmi_b200/build.py > /tmp/build_variant_$n.log 2>&1 || { tail -20 /tmp/build_variant_$n.log; echo "variant $n FAILED"; exit 1; }
+  tail -1 /tmp/build_variant_$n.log
 done
-python rmi_b200/build.py | tail -1     # relink the CLI against the default library
+python rmi_b200/build.py > /tmp/build_default.log 2>&1 || { tail -20 /tmp/build_default.log; exit 1; }   # relink the CLI against the default library
 ls -la rmi_b200/lib/
