@@ -246,13 +246,18 @@ def find_pareto_efficient_configs(replicas, restrict_to: int = 10, flags: int = 
     builds are spread over them."""
     reps = [replicas] if isinstance(replicas, RMITrainingData) else list(replicas)
     handles = (C.c_void_p * len(reps))(*[r._h for r in reps])
-    cap = 64
+    # The front can never hold more entries than configurations were measured (84 in phase 1 plus the
+    # phase-2 refinements, optimizer.rs:110-231: a few hundred); 4096 is far above that, and a front that
+    # still does not fit is an error, never a silent truncation (the dropped tail would be the smallest models).
+    cap = max(4096, int(restrict_to) if restrict_to < (1 << 20) else 0)
     out = (_ConfigStats * cap)()
     cnt = C.c_uint64(0)
     _check(load_library().rmi_find_pareto_efficient_configs(handles, len(reps), int(restrict_to), int(flags), out, cap, C.byref(cnt)))
+    if int(cnt.value) > cap:
+        raise RMIError(f"Pareto front has {int(cnt.value)} entries, more than the {cap} this call can return")
     return [dict(models=out[i].models.decode(), branching_factor=int(out[i].branching_factor),
                  average_log2_error=float(out[i].average_log2_error), max_log2_error=float(out[i].max_log2_error),
-                 size=int(out[i].size)) for i in range(min(int(cnt.value), cap))]
+                 size=int(out[i].size)) for i in range(int(cnt.value))]
 
 
 def train_for_size(data: RMITrainingData, max_size: int, flags: int = 0) -> TrainedRMI:
