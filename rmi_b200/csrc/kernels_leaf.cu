@@ -24,7 +24,10 @@
 // bit-identical; parallelism comes from the N independent leaves.
 #include "device_util.cuh"
 #include "kernels.h"
+#include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 namespace rmi {
 
@@ -41,12 +44,11 @@ constexpr int BOUNDS_THREADS = 256;
 #else
 #define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS)
 #endif
-#ifndef RMI_PARTIAL_UNROLL
-#define RMI_PARTIAL_UNROLL 2   // unroll factor of the one-key-per-iteration walk over partially used chunks (~40% of the keys)
-#endif
 constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
-constexpr int PARTIAL_UNROLL = RMI_PARTIAL_UNROLL;
-constexpr int RCP_TABLE = 512;
+#ifndef RMI_RCP_TABLE
+#define RMI_RCP_TABLE 512
+#endif
+constexpr int RCP_TABLE = RMI_RCP_TABLE;   // reciprocals of the counts below this live in shared memory
 
 __device__ __forceinline__ void set_status(BuildAux* aux, unsigned bit) { atomicOr(&aux->status, bit); }
 
@@ -162,13 +164,16 @@ __global__ void k_split(const T* __restrict__ keys, u64 n, const TopModel* __res
 // length, so 8-key and 8-million-key leaves take the same code path, and the keys cross
 // HBM -> L2 -> SM in full lines exactly once per pass.
 // ------------------------------------------------------------------------------------------
-constexpr int ROW_BYTES = 144;   // 128 B of keys + 16 B pad: rows stay 16-byte aligned and the 8 lanes of
-                                 // a 128-bit shared-load phase hit 8 distinct bank quads
+// Layout of one stage: piece-major — the 32 rows' q-th 16-byte pieces are contiguous (512 B), so the
+// 8 lanes of a 128-bit shared-load phase, which read the same piece of 8 neighbouring rows, hit 8
+// distinct bank quads without any padding: 4 KB per stage.
+constexpr int STAGE_BYTES = 32 * 128;
+constexpr int PIECE_STRIDE = 32 * 16;   // bytes between a row's consecutive pieces
 #ifndef RMI_SSTAGES
 #define RMI_SSTAGES 2
 #endif
 constexpr int SSTAGES = RMI_SSTAGES;
-constexpr int WARP_STREAM_BYTES = SSTAGES * 32 * ROW_BYTES + 32 * 4 + 32 * 4;
+constexpr int WARP_STREAM_BYTES = SSTAGES * STAGE_BYTES + 32 * 4 + 32 * 4;
 
 // createpolicy for an L2 eviction priority: 0 evict_normal, 1 evict_first, 2 evict_last.
 __device__ __forceinline__ u64 l2_policy_of(int kind) {
@@ -205,7 +210,7 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
   constexpr int SW = 8 * KPP;                // keys per row per chunk
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  u32* rowg = reinterpret_cast<u32*>(wsm + SSTAGES * 32 * ROW_BYTES);   // first 16-byte piece of each row
+  u32* rowg = reinterpret_cast<u32*>(wsm + SSTAGES * STAGE_BYTES);   // first 16-byte piece of each row
   u32* rownp = rowg + 32;                                                // pieces in each row
   const I a = b & ~(I)(KPP - 1);             // 16-byte aligned start of this lane's stream
   const I skip = b - a;
@@ -234,21 +239,21 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
     np[q] = rp > (u32)piece ? (rp - (u32)piece + 7u) / 8u : 0u;   // chunks in which this piece exists
   }
   const unsigned char* kb = reinterpret_cast<const unsigned char*>(keys);
-  const unsigned st0 = (unsigned)__cvta_generic_to_shared(wsm) + (unsigned)(prow * ROW_BYTES + piece * 16);
+  const unsigned st0 = (unsigned)__cvta_generic_to_shared(wsm) + (unsigned)(piece * PIECE_STRIDE + prow * 16);
   const u32 nchunks = (u32)(((u64)maxlen + SW - 1) / SW);
   // One predicated 16-byte copy per (row, piece) stream: address = chunk base + piece index * 16.
   // Pieces are whole 16-byte units; the one that holds the array's last key may extend past it
   // (the buffer is readable up to the next 16-byte boundary, include/rmi_b200.h), and nothing
   // past a lane's range is ever consumed.
   auto issue = [&](u32 c) {
-    const unsigned st = st0 + (c % SSTAGES) * (32 * ROW_BYTES);
+    const unsigned st = st0 + (c % SSTAGES) * STAGE_BYTES;
     const unsigned char* cb = kb + (u64)c * 128u;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       u64 src;
       asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(src) : "r"(g0[q]), "l"(cb));
       asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %4;\n\t}\n"
-                   ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)), "l"(src), "r"(c), "r"(np[q]), "l"(l2_policy) : "memory");
+                   ::"r"(st + (unsigned)(q * 4 * 16)), "l"(src), "r"(c), "r"(np[q]), "l"(l2_policy) : "memory");
     }
     cp_async_commit();
   };
@@ -277,30 +282,63 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
     if (c + (SSTAGES - 1) < nchunks) issue(c + (SSTAGES - 1)); else cp_async_commit();
     cp_async_wait<SSTAGES - 1>();
     __syncwarp();
-    const unsigned char* row = wsm + (int)(c % SSTAGES) * (32 * ROW_BYTES) + lane * ROW_BYTES;
+    const unsigned char* row = wsm + (int)(c % SSTAGES) * STAGE_BYTES + lane * 16;   // this lane's piece 0; piece q at + q * PIECE_STRIDE
     const I cbase = (I)c * (I)SW;
-    const I lo_k = skip > cbase ? skip : cbase;
-    const I hi_k = rlen < cbase + (I)SW ? rlen : cbase + (I)SW;
-    const bool full = lo_k == cbase && hi_k == cbase + (I)SW;
-    if (__all_sync(FULL, full)) {
+    // A chunk is "full" when every lane still has all SW positions on the high side.  The low side
+    // matters in chunk 0 only (a stream starts at the 16-byte piece that holds index b, so up to
+    // KPP-1 leading positions are not the lane's): there the first piece is walked under a per-lane
+    // predicate and the other seven pieces take the vector path like any later chunk.
+    if (__all_sync(FULL, rlen >= cbase + (I)SW)) {
       I idx = a + cbase;
-#pragma unroll 4
-      for (int pp = 0; pp < 8; ++pp) {
-        uint4 v = *reinterpret_cast<const uint4*>(row + pp * 16);
+      if (c == 0) {
+        uint4 v = *reinterpret_cast<const uint4*>(row);
         T kk[KPP];
         memcpy(kk, &v, 16);
 #pragma unroll
-        for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(idx + (I)t));
+        for (int t = 0; t < KPP; ++t) {
+          if (t == KPP - 1 || (I)t >= skip) fn(kk[t], (I)(idx + (I)t));
+        }
         idx += (I)KPP;
+#pragma unroll
+        for (int pp = 1; pp < 8; ++pp) {
+          v = *reinterpret_cast<const uint4*>(row + pp * PIECE_STRIDE);
+          memcpy(kk, &v, 16);
+#pragma unroll
+          for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(idx + (I)t));
+          idx += (I)KPP;
+        }
+      } else {
+#pragma unroll 4
+        for (int pp = 0; pp < 8; ++pp) {
+          uint4 v = *reinterpret_cast<const uint4*>(row + pp * PIECE_STRIDE);
+          T kk[KPP];
+          memcpy(kk, &v, 16);
+#pragma unroll
+          for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(idx + (I)t));
+          idx += (I)KPP;
+        }
       }
     } else {
-      // some lane starts or ends inside this chunk: every lane walks its own [p0, p1) in ONE
-      // loop (full lanes: all SW keys), so the warp pays max(p1 - p0) iterations once instead
-      // of a full-chunk path plus a partial-chunk path
-      const int p0 = lo_k < hi_k ? (int)(lo_k - cbase) : 0, p1 = lo_k < hi_k ? (int)(hi_k - cbase) : 0;
-#pragma unroll PARTIAL_UNROLL
-      for (int pos = p0; pos < p1; ++pos)
-        fn(*reinterpret_cast<const T*>(row + pos * (int)sizeof(T)), (I)(a + cbase + (I)pos));
+      // some lane ends inside this chunk (or the leaf is shorter than a chunk): every lane walks its
+      // own [p0, p1), whole 16-byte pieces with one 128-bit shared load each, single keys at the ends
+      const I lo_k = (c == 0) ? skip : (I)0;
+      const I rem = rlen > cbase ? (I)(rlen - cbase) : (I)0;
+      int pos = (int)lo_k;
+      const int p1 = rem < (I)SW ? (int)rem : SW;
+      auto key_at = [&](int q) {   // key at position q of this lane's row
+        return *reinterpret_cast<const T*>(row + (q / KPP) * PIECE_STRIDE + (q % KPP) * (int)sizeof(T));
+      };
+      if (c == 0) {
+        for (; pos < p1 && (pos & (KPP - 1)) != 0; ++pos) fn(key_at(pos), (I)(a + cbase + (I)pos));
+      }
+      for (; pos + KPP <= p1; pos += KPP) {
+        uint4 v = *reinterpret_cast<const uint4*>(row + (pos / KPP) * PIECE_STRIDE);
+        T kk[KPP];
+        memcpy(kk, &v, 16);
+#pragma unroll
+        for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(a + cbase + (I)(pos + t)));
+      }
+      for (; pos < p1; ++pos) fn(key_at(pos), (I)(a + cbase + (I)pos));
     }
     __syncwarp();
   }
@@ -349,6 +387,16 @@ template <class T, class I> struct LeafRange {
 // CHECKED = false skips div_by_count's range test (integer keys cannot produce operands
 // outside [2^-900, 2^900], and a zero operand is handled exactly by the fast sequence).
 __device__ __noinline__ double rcp_beyond_table(double nf) { return __drcp_rn(nf); }
+// Reciprocals of the counts RCP_TABLE .. RCP_FAR-1 live in global memory (512 KB, filled once per
+// device; neighbouring lanes ask for neighbouring counts, so a warp's load touches one or two L1
+// sectors): training vectors longer than the shared table — 2^18 leaves on 200M keys, or 2^20
+// leaves on a key set spread over eight GPUs — pay one cached load per item, not a division.
+constexpr unsigned RCP_FAR = 1u << 16;
+__device__ double g_rcp_far[RCP_FAR];
+__global__ void k_init_rcp_far() {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < RCP_FAR) g_rcp_far[i] = i ? __drcp_rn((double)i) : 0.0;
+}
 
 template <bool CHECKED> struct LeafWelford {
   double mean_x, mean_y, c, m2, nf;
@@ -358,22 +406,31 @@ template <bool CHECKED> struct LeafWelford {
     ra = (unsigned)__cvta_generic_to_shared(table);
     ra_end = ra + (unsigned)((RCP_TABLE - 1) * sizeof(double));
   }
+  // 1/(items pushed + 1): shared table, then the global table, then a division.  `ra` keeps counting
+  // past the shared table's end (it is the item count in bytes, relative to the table's start).
+  __device__ __forceinline__ double next_rc() {
+    ra += (unsigned)sizeof(double);
+    double rc;
+    if (ra <= ra_end) {
+      asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
+    } else {
+      const unsigned off = ra - (ra_end - (unsigned)((RCP_TABLE - 1) * sizeof(double)));   // count * 8
+      if (off < RCP_FAR * (unsigned)sizeof(double))
+        rc = __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(g_rcp_far) + off));
+      else
+        rc = rcp_beyond_table(__dadd_rn(nf, 1.0));   // a real call, so it is not if-converted
+    }
+    return rc;
+  }
+  // after a stretch in which `ra` was not advanced (solo mode): later steps divide
+  __device__ __forceinline__ void rc_cursor_off() { ra = ra_end + RCP_FAR * (unsigned)sizeof(double); }
   __device__ __forceinline__ double dv(double a, double rc) const {
     if (CHECKED) return div_by_count(a, nf, rc);
     double q0 = __dmul_rn(a, rc);
     double rem = __fma_rn(-nf, q0, a);
     return __fma_rn(rem, rc, q0);
   }
-  __device__ __forceinline__ void push(double x, double y) {
-    double rc;
-    if (ra < ra_end) {   // 1/n from the shared table
-      ra += (unsigned)sizeof(double);
-      asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
-    } else {
-      rc = rcp_beyond_table(__dadd_rn(nf, 1.0));   // longer than the table: a real call, so it is not if-converted
-    }
-    push_rc(x, y, rc);
-  }
+  __device__ __forceinline__ void push(double x, double y) { push_rc(x, y, next_rc()); }
   // the caller guarantees fewer than RCP_TABLE items in total (no lane of the warp has a longer
   // vector): 1/n always comes from the shared table and the step has no branch
   __device__ __forceinline__ void push_t(double x, double y) {
@@ -398,16 +455,7 @@ template <bool CHECKED> struct LeafWelford {
     double dx2 = __dadd_rn(x, -mean_x);
     m2 = __dadd_rn(m2, __dmul_rn(dx, dx2));
   }
-  __device__ __forceinline__ void push_nd(double x) {
-    double rc;
-    if (ra < ra_end) {
-      ra += (unsigned)sizeof(double);
-      asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
-    } else {
-      rc = rcp_beyond_table(__dadd_rn(nf, 1.0));
-    }
-    push_rc_nd(x, rc);
-  }
+  __device__ __forceinline__ void push_nd(double x) { push_rc_nd(x, next_rc()); }
   __device__ __forceinline__ void push_t_nd(double x) {
     double rc;
     ra += (unsigned)sizeof(double);
@@ -652,7 +700,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
       it.idxd = __shfl_sync(FULL, it.idxd, solo_lane);
       const I s_b = __shfl_sync(FULL, solo_at, solo_lane), s_e = __shfl_sync(FULL, r.ve, solo_lane);
       solo_chain<T, I, CHECKED, DUPS>(keys, s_b, s_e, wsm, w, it);
-      w.ra = w.ra_end;   // the table cursor was not advanced in solo mode: later steps compute 1/n directly
+      w.rc_cursor_off();   // the table cursor was not advanced in solo mode: later steps compute 1/n directly
       if (lane == solo_lane) finalize();
     }
   } else if (LEAF == M_ROBUST_LINEAR) {
@@ -820,6 +868,126 @@ __device__ __forceinline__ I leaf_predict_clamped(const double* f, double x, I n
   if (sizeof(I) == 4) v = (I)__double2uint_rd(p); else v = (I)__double2ull_rd(p);
   if (NANCHECK) v = p != p ? (I)0 : v;
   return v < n ? v : n;
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward pass (two_layer.rs:207-217) + longest run of equal keys (lower_bound_correction.rs:
+// 101-119), warp-cooperative.  For every lane with `mine` set the warp evaluates that lane's
+// leaf model on the leaf's keys [lo, hi) (LOCAL indices) and returns max |pred - offset| and
+// the longest recorded run to that lane.  Must be called by all 32 lanes.
+//   offset of key i = global index of the first key of i's run (FixDupsIter); a leaf's first
+//   key always starts a run (equal keys get equal top predictions, so runs never straddle a leaf
+//   boundary);  a run's length is recorded when the NEXT run starts, hence the data set's final
+//   run never is (g_hi == n).
+// ------------------------------------------------------------------------------------------
+template <class I> __device__ __forceinline__ I warp_max(I v) {
+  if (sizeof(I) == 4) return (I)__reduce_max_sync(0xffffffffu, (unsigned)v);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    I t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  return v;
+}
+
+template <class T, class I, int LEAF, bool DUPS, bool NANCHECK>
+__device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const Shard<T>& sh, unsigned char* wsm, bool mine,
+                                             I lo, I hi, u64 g_hi, const double* f, I& max_err, I& run_max) {
+  constexpr int PPM = leaf_params_per_model(LEAF);
+  constexpr int FWD_DEPTH = 4;   // coalesced 32-key loads in flight per outer step
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const I nI = (I)sh.n_global;
+  const I baseI = (I)sh.base;
+  // per-lane descriptors: {lo, hi} as two u64, then PPM doubles, one 16-byte aligned record per lane
+  constexpr int REC = 16 + ((PPM * 8 + 15) / 16) * 16;
+  unsigned todo = __ballot_sync(FULL, mine);
+  if (todo == 0) return;
+  __syncwarp();
+  {
+    unsigned char* rec = wsm + lane * REC;
+    *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2((u64)lo, (u64)hi);
+#pragma unroll
+    for (int q = 0; q < PPM; ++q) reinterpret_cast<double*>(rec + 16)[q] = f[q];
+    if (DUPS) reinterpret_cast<u64*>(wsm + 32 * REC)[lane] = g_hi;
+  }
+  __syncwarp();
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const unsigned char* rec = wsm + src * REC;
+    const ulonglong2 lh = *reinterpret_cast<const ulonglong2*>(rec);
+    const I c_lo = (I)lh.x, c_hi = (I)lh.y;
+    double cf[PPM];
+#pragma unroll
+    for (int q = 0; q < PPM; ++q) cf[q] = reinterpret_cast<const double*>(rec + 16)[q];
+    I w_err = 0, w_run = 0;
+    I carry_F = (I)(c_lo + baseI);     // offset of the last key seen so far (DUPS)
+    T carry_k = T();
+    for (I b0 = c_lo; b0 < c_hi; b0 += (I)(32 * FWD_DEPTH)) {
+      T kk[FWD_DEPTH];
+#pragma unroll
+      for (int u = 0; u < FWD_DEPTH; ++u) {
+        const I iu = b0 + (I)(u * 32 + lane);
+        kk[u] = iu < c_hi ? __ldcs(keys + iu) : T();   // streaming: this is the last use of the line
+      }
+#pragma unroll
+      for (int u = 0; u < FWD_DEPTH; ++u) {
+        const I s0 = b0 + (I)(u * 32);
+        if (DUPS && s0 >= c_hi) break;   // warp-uniform (without duplicate tracking an all-invalid step is a no-op)
+        const I i = s0 + (I)lane;
+        const bool valid = i < c_hi;
+        const T k = kk[u];
+        const I Fi = (I)(i + baseI);
+        I F = Fi;
+        if (DUPS) {
+          T kp = __shfl_up_sync(FULL, k, 1);
+          if (lane == 0) kp = carry_k;
+          const bool starts = valid && (i == c_lo || k != kp);
+          const unsigned sm = __ballot_sync(FULL, starts);
+          const unsigned vm = __ballot_sync(FULL, valid);
+          if (sm == vm) {
+            // every key of this step starts its own run: the runs that end here have length 1, except
+            // the one that may have come in from the previous step
+            if (valid && i != c_lo) {
+              const I len = lane == 0 ? (I)(Fi - carry_F) : (I)1;
+              w_run = len > w_run ? len : w_run;
+            }
+          } else {
+            const unsigned below = sm & ((2u << lane) - 1u);   // run starts at or below this lane
+            F = below ? (I)(s0 + baseI + (I)(31 - __clz(below))) : carry_F;
+            I Fm1 = __shfl_up_sync(FULL, F, 1);
+            if (lane == 0) Fm1 = carry_F;
+            if (starts && i != c_lo) {   // the run before this key ends here
+              const I len = (I)(Fi - Fm1);
+              w_run = len > w_run ? len : w_run;
+            }
+          }
+          const int lastv = (c_hi - s0) < (I)32 ? (int)(c_hi - s0) - 1 : 31;
+          carry_F = __shfl_sync(FULL, F, lastv);
+          carry_k = __shfl_sync(FULL, k, lastv);
+        }
+        {   // branch-free: an invalid lane evaluates the model on a zero key and discards the result
+          const I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, Key<T>::as_float(k), nI);
+          I e = pred > F ? pred - F : F - pred;
+          e = valid ? e : (I)0;
+          w_err = e > w_err ? e : w_err;
+        }
+      }
+    }
+    w_err = warp_max<I>(w_err);
+    if (DUPS) {
+      w_run = warp_max<I>(w_run);
+      // the leaf's final run is recorded only if another run follows it in the data set
+      const u64 c_ghi = reinterpret_cast<const u64*>(wsm + 32 * REC)[src];
+      if (c_ghi < sh.n_global) {
+        const I len = (I)((I)(c_hi + baseI) - carry_F);
+        w_run = len > w_run ? len : w_run;
+      }
+    }
+    if (lane == src) { max_err = w_err; if (DUPS) run_max = w_run; }
+  }
+  __syncwarp();
 }
 
 constexpr u64 LONG_LEAF_KEYS = 2048;   // leaves longer than this go to the long-leaf kernel (linear leaves)
@@ -996,7 +1164,6 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
 
   double f[4] = {0.0, 0.0, 0.0, 0.0};
   fit_leaf<T, I, LEAF, DUPS>(keys, sh, wsm, r, s_rcp, f, bad, l2_policy_of((mode_word >> 4) & 3));
-  const u64 pol_fwd = l2_policy_of((mode_word >> 6) & 3);
 
   // two_layer.rs:186-197: empty leaves (lower-bound-correction sense) except the last
   const u64 next_idx = g_hi;                                        // lb.next_index(j) = S[j+1]
@@ -1018,126 +1185,18 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
     if (sh.n_local > 0) { prev_key = keys[sh.n_local - 1]; have_prev = true; }
     else if (sh.has_prev) { prev_key = sh.prev_key; have_prev = true; }
   }
+  // The forward pass has no order dependence, so the WARP walks each of its lanes' leaves in turn,
+  // 32 consecutive keys per step straight from global memory (coalesced; the fit pass read the same
+  // lines moments ago, so they come from L2), instead of every lane walking its own leaf through the
+  // row ring a second time.  Owners park their leaf's range and parameters in the warp's shared
+  // memory (the ring is idle now); results return to the owner lane.
   I max_err = 0, run_max = 0;
-  // Leaves longer than LONG_LEAF keys skip the lane-serial walk: their forward pass has no
-  // order dependence, so the whole warp does it afterwards, 32 keys per step, coalesced.
-  constexpr u64 LONG_LEAF = 1024;
-  const bool is_long = live && (g_hi - g_lo) > LONG_LEAF;
-  // worth it only when a few lanes are long (when all 32 are, lane-serial walks are already balanced)
-  const unsigned long_mask = __ballot_sync(0xffffffffu, is_long);   // (all lanes vote: no short-circuit)
-  const bool long_leaf = is_long && __popc(long_mask) <= 4;
-  {
-    T pk = (live && g_lo == 0 && g_hi > 0) ? keys[0] : prev_key;
-    I F = (I)g_lo, run = 0;
-    if (DUPS) {
-      stream_pass<T, I>(keys, pol_fwd, wsm, r.lo, long_leaf ? r.lo : r.hi, [&](T k, I i) {
-        if (k != pk) { run_max = run > run_max ? run : run_max; run = 0; F = (I)(i + baseI); }
-        run += 1;
-        pk = k;
-        I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
-        I e = pred > F ? pred - F : F - pred;
-        max_err = e > max_err ? e : max_err;
-      });
-      if (g_hi < n && run > run_max) run_max = run;
-    } else {
-      // no two keys of the data set are equal: the offset of a key is its index, every run has
-      // length 1 (and the data set's final run is never recorded)
-      stream_pass<T, I>(keys, pol_fwd, wsm, r.lo, long_leaf ? r.lo : r.hi, [&](T k, I i) {
-        I Fi = (I)(i + baseI);
-        I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
-        I e = pred > Fi ? pred - Fi : Fi - pred;
-        max_err = e > max_err ? e : max_err;
-      });
-      const u64 recorded = g_hi < n ? (g_hi - g_lo) : (g_hi > g_lo ? g_hi - g_lo - 1 : 0);
-      run_max = recorded > 0 ? (I)1 : (I)0;
-      (void)pk; (void)F; (void)run;
-    }
-  }
-  {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    unsigned todo = __ballot_sync(FULL, long_leaf);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      // the owner's leaf, parameters and boundary key, broadcast to the warp
-      const u64 c_lo = __shfl_sync(FULL, (u64)r.lo, src), c_hi = __shfl_sync(FULL, (u64)r.hi, src);
-      const u64 c_ghi = __shfl_sync(FULL, g_hi, src);
-      double cf[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) cf[q] = __shfl_sync(FULL, f[q], src);
-      T carry_k = __shfl_sync(FULL, prev_key, src);
-      const bool c_have_prev = __shfl_sync(FULL, (int)have_prev, src) != 0;
-      I carry_F = (I)(c_lo + sh.base);
-      I w_err = 0, w_run = 0;
-      // 8 coalesced batches of 32 keys in flight per outer step (one global-memory latency per
-      // 256 keys instead of per 32)
-      constexpr int DEPTH = 8;
-      for (u64 b0 = c_lo; b0 < c_hi; b0 += 32 * DEPTH) {
-        T kk[DEPTH];
-#pragma unroll
-        for (int u = 0; u < DEPTH; ++u) {
-          const u64 iu = b0 + (u64)(u * 32 + lane);
-          kk[u] = iu < c_hi ? keys[iu] : T();
-        }
-        const u64 inext = b0 + 32 * DEPTH;
-        const T k_after = (DUPS && inext < c_hi) ? keys[inext] : T();   // first key of the next outer step
-#pragma unroll
-        for (int u = 0; u < DEPTH; ++u) {
-          const u64 s0 = b0 + (u64)(u * 32);
-          if (s0 >= c_hi) break;   // warp-uniform
-          const u64 i = s0 + lane;
-          const bool valid = i < c_hi;
-          const T k = kk[u];
-          if (!DUPS) {
-            if (valid) {
-              const I Fi = (I)(i + sh.base);
-              I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, Key<T>::as_float(k), nI);
-              I e = pred > Fi ? pred - Fi : Fi - pred;
-              w_err = e > w_err ? e : w_err;
-            }
-            continue;
-          }
-          T kp = __shfl_up_sync(FULL, k, 1);
-          if (lane == 0) kp = carry_k;
-          // a run starts where the key differs from its predecessor (the leaf's first key always
-          // differs from the key before the leaf; at global index 0 there is no predecessor)
-          const bool starts = valid && (k != kp || (i == c_lo && !c_have_prev));
-          I F = starts ? (I)(i + sh.base) : (I)0;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            I t = __shfl_up_sync(FULL, F, o);
-            if (lane >= o && t > F) F = t;
-          }
-          if (carry_F > F) F = carry_F;
-          if (valid) {
-            I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, Key<T>::as_float(k), nI);
-            I e = pred > F ? pred - F : F - pred;
-            w_err = e > w_err ? e : w_err;
-          }
-          // a run ends at i when the next key differs or the leaf ends; its length counts unless
-          // it is the data set's final run (lower_bound_correction.rs:108-119)
-          T kn = __shfl_down_sync(FULL, k, 1);
-          const T k_next_batch = u + 1 < DEPTH ? __shfl_sync(FULL, kk[u + 1 < DEPTH ? u + 1 : u], 0) : k_after;
-          if (lane == 31) kn = k_next_batch;
-          const bool last_of_leaf = valid && i + 1 == c_hi;
-          const bool ends = valid && (last_of_leaf || kn != k);
-          if (ends && !(last_of_leaf && c_ghi >= n)) {
-            I len = (I)(i + sh.base) - F + 1;
-            w_run = len > w_run ? len : w_run;
-          }
-          const int lastv = (c_hi - s0) < 32 ? (int)(c_hi - s0) - 1 : 31;
-          carry_F = __shfl_sync(FULL, F, lastv);
-          carry_k = __shfl_sync(FULL, k, lastv);
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        I t = __shfl_xor_sync(FULL, w_err, o); w_err = t > w_err ? t : w_err;
-        t = __shfl_xor_sync(FULL, w_run, o); w_run = t > w_run ? t : w_run;
-      }
-      if (lane == src) { max_err = w_err; if (DUPS) run_max = w_run; }
-    }
+  coop_forward<T, I, LEAF, DUPS, NANCHECK>(keys, sh, wsm, live && r.hi > r.lo, r.lo, r.hi, g_hi, f, max_err, run_max);
+  if (!DUPS) {
+    // no two keys of the data set are equal: every run has length 1 (and the data set's final run
+    // is never recorded, lower_bound_correction.rs:108-119)
+    const u64 recorded = g_hi < n ? (g_hi - g_lo) : (g_hi > g_lo ? g_hi - g_lo - 1 : 0);
+    run_max = recorded > 0 ? (I)1 : (I)0;
   }
   if (bad) set_status(aux, bad);
   if (!live) return;
@@ -1298,6 +1357,20 @@ void search_bounds_range(int top_kind, cudaStream_t st, const T* keys, u64 n, co
 }
 #endif
 
+// g_rcp_far is per device; filled once, synchronously, before the first leaf kernel on that device.
+void ensure_rcp_far() {
+  static std::mutex mu;
+  static std::vector<char> done;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)done.size() <= dev) done.resize(dev + 1, 0);
+  if (done[dev]) return;
+  k_init_rcp_far<<<RCP_FAR / 256, 256>>>();
+  count_launch();
+  if (cudaDeviceSynchronize() == cudaSuccess) done[dev] = 1;
+}
+
 template <class T, class I, int LEAF, bool DUPS>
 void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N, const u64* d_S, BuildAux* d_aux,
                       double* d_params, u64* d_errors, u64* d_counts) {
@@ -1312,7 +1385,17 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
     if (e && e[0] && e[1]) { fit = (e[0] - '0') & 3; fwd = (e[1] - '0') & 3; }
     return (fit << 4) | (fwd << 6);
   }();
+  ensure_rcp_far();
   cudaFuncSetAttribute(k_leaf<T, I, LEAF, DUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, LONG_LEAF_SMEM);
+  static const bool print_occ = getenv("RMI_DEV_PRINT_OCC") != nullptr;
+  if (print_occ) {
+    int nb = 0;
+    cudaFuncAttributes fa;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_leaf<T, I, LEAF, DUPS>, LEAF_THREADS, smem);
+    cudaFuncGetAttributes(&fa, k_leaf<T, I, LEAF, DUPS>);
+    fprintf(stderr, "[rmi_b200] k_leaf: %d threads/block, %zu B dynamic smem, %d registers -> %d blocks/SM\n", LEAF_THREADS, smem,
+            fa.numRegs, nb);
+  }
   const bool fork = LEAF == M_LINEAR && L.side && L.ev_fork && L.ev_join && L.d_long && N < 0xffffffffull;
   if (fork) {
     // Long leaves (the two end leaves of a regression top model collect every key it places

@@ -7,17 +7,20 @@ set -o pipefail
 declare -A DEFS=(
   [s3]="-DRMI_SSTAGES=3"                 # three copy stages in the row ring instead of two
   [t64]="-DRMI_LEAF_THREADS=64"          # 64-lane blocks: finer tail, more blocks per SM
-  [t256]="-DRMI_LEAF_THREADS=256"        # 256-lane blocks: fewer reciprocal-table initialisations
-  [s3t64]="-DRMI_SSTAGES=3 -DRMI_LEAF_THREADS=64"
-  [u4]="-DRMI_PARTIAL_UNROLL=4"          # partial-chunk walk unrolled 4x instead of 2x
+  [t256]="-DRMI_LEAF_THREADS=256 -DRMI_LEAF_MIN_BLOCKS=3 -DRMI_RCP_TABLE=384"   # 256-lane blocks, 3 per SM (24 warps)
+  [b6]="-DRMI_LEAF_MIN_BLOCKS=6 -DRMI_RCP_TABLE=384"   # 6 blocks of 128 lanes per SM (needs <= 80 registers, 37 KB of shared memory each)
   [pb]="-DRMI_PIPELINED_BOUNDS"          # leaf-boundary search sliced and overlapped with the leaf kernel's slices
 )
 names=("$@")
 [ ${#names[@]} -eq 0 ] && names=("${!DEFS[@]}")
+pids=()
 for n in "${names[@]}"; do
   echo "== variant $n: ${DEFS[$n]}"
-  RMI_BUILD_TAG=$n RMI_NVCC_DEFS="${DEFS[$n]}" python rmi_b200/build.py > /tmp/build_variant_$n.log 2>&1 || { tail -20 /tmp/build_variant_$n.log; echo "variant $n FAILED"; exit 1; }
-  tail -1 /tmp/build_variant_$n.log
+  ( RMI_BUILD_TAG=$n RMI_NVCC_DEFS="${DEFS[$n]}" python rmi_b200/build.py > /tmp/build_variant_$n.log 2>&1 || { tail -20 /tmp/build_variant_$n.log; echo "variant $n FAILED"; exit 1; } ) &
+  pids+=($!)
 done
+rc=0
+for p in "${pids[@]}"; do wait $p || rc=1; done
+[ $rc -ne 0 ] && exit 1
 python rmi_b200/build.py > /tmp/build_default.log 2>&1 || { tail -20 /tmp/build_default.log; exit 1; }   # relink the CLI against the default library
 ls -la rmi_b200/lib/
