@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 namespace rmi {
@@ -39,10 +40,12 @@ constexpr int BOUNDS_THREADS = 256;
 #ifndef RMI_LEAF_THREADS
 #define RMI_LEAF_THREADS 128
 #endif
+// Resident blocks per SM the compiler must allow for: 24 warps (80 registers) for the duplicate-free linear
+// leaf — the kernel of the headline build, which fits — and 20 warps (96 registers) for everything else.
 #ifdef RMI_LEAF_MIN_BLOCKS
 #define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS, RMI_LEAF_MIN_BLOCKS)
 #else
-#define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS)
+#define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS, ((LEAF == M_LINEAR && !DUPS) ? 768 : 640) / RMI_LEAF_THREADS)
 #endif
 constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
 #ifndef RMI_RCP_TABLE
@@ -202,6 +205,13 @@ template <int N_> __device__ __forceinline__ void cp_async_wait() {
 // to go and every other lane is done; it then reports that lane and the index it stopped at
 // (*solo_lane = -1 if the pass ran to completion), so that the caller can finish the long
 // leaf with solo_pass(), where the whole warp serves the one remaining chain.
+// item functors that split an item into prep() (conversion) and step() (the dependent chain) declare a Prepared type
+template <class F> struct has_prep {
+  template <class U> static char test(typename U::Prepared*);
+  template <class U> static long test(...);
+  static constexpr bool value = sizeof(test<F>(nullptr)) == sizeof(char);
+};
+
 constexpr int SOLO_MIN = 384;
 template <class T, class I, class Fn, bool SOLO = false>
 __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_policy, unsigned char* wsm, I b, I e,
@@ -308,14 +318,45 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
           idx += (I)KPP;
         }
       } else {
-#pragma unroll 4
-        for (int pp = 0; pp < 8; ++pp) {
-          uint4 v = *reinterpret_cast<const uint4*>(row + pp * PIECE_STRIDE);
-          T kk[KPP];
-          memcpy(kk, &v, 16);
+        typedef typename std::remove_reference<Fn>::type FnT;
+        if constexpr (has_prep<FnT>::value) {
+          // software pipeline over the 8 pieces: piece pp+2 is being loaded and piece pp+1 converted while
+          // piece pp's dependent chains run
+          typename FnT::Prepared pa[KPP], pb[KPP];
+          uint4 v1 = *reinterpret_cast<const uint4*>(row + PIECE_STRIDE);
+          {
+            uint4 v0 = *reinterpret_cast<const uint4*>(row);
+            T kk[KPP];
+            memcpy(kk, &v0, 16);
 #pragma unroll
-          for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(idx + (I)t));
-          idx += (I)KPP;
+            for (int t = 0; t < KPP; ++t) pa[t] = fn.prep(kk[t]);
+          }
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) {
+            uint4 v2 = v1;
+            if (pp + 2 < 8) v2 = *reinterpret_cast<const uint4*>(row + (pp + 2) * PIECE_STRIDE);
+            if (pp + 1 < 8) {
+              T kk[KPP];
+              memcpy(kk, &v1, 16);
+#pragma unroll
+              for (int t = 0; t < KPP; ++t) pb[t] = fn.prep(kk[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < KPP; ++t) fn.step(pa[t]);
+#pragma unroll
+            for (int t = 0; t < KPP; ++t) pa[t] = pb[t];
+            v1 = v2;
+          }
+        } else {
+#pragma unroll 4
+          for (int pp = 0; pp < 8; ++pp) {
+            uint4 v = *reinterpret_cast<const uint4*>(row + pp * PIECE_STRIDE);
+            T kk[KPP];
+            memcpy(kk, &v, 16);
+#pragma unroll
+            for (int t = 0; t < KPP; ++t) fn(kk[t], (I)(idx + (I)t));
+            idx += (I)KPP;
+          }
         }
       }
     } else {
@@ -433,12 +474,22 @@ template <bool CHECKED> struct LeafWelford {
   __device__ __forceinline__ void push(double x, double y) { push_rc(x, y, next_rc()); }
   // the caller guarantees fewer than RCP_TABLE items in total (no lane of the warp has a longer
   // vector): 1/n always comes from the shared table and the step has no branch
-  __device__ __forceinline__ void push_t(double x, double y) {
-    double rc;
-    ra += (unsigned)sizeof(double);
-    asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
-    push_rc(x, y, rc);
+  // The reciprocal is loaded ONE STEP AHEAD (rc_next): a shared-memory load issued in the step that
+  // consumes it stalls the dependent chain for the load's whole latency (ncu: the short-scoreboard
+  // stall on the first multiply was the largest single stall of the fit loop).  table_begin() must be
+  // called once before the first push_t / push_t_nd; the look-ahead reads one entry past the last
+  // count used, which `all_short` (L + 2 < RCP_TABLE) keeps inside the table.
+  double rc_next;
+  __device__ __forceinline__ void table_begin() {
+    asm("ld.shared.f64 %0, [%1+8];" : "=d"(rc_next) : "r"(ra));
   }
+  __device__ __forceinline__ double table_rc() {
+    const double rc = rc_next;
+    ra += (unsigned)sizeof(double);
+    asm("ld.shared.f64 %0, [%1+8];" : "=d"(rc_next) : "r"(ra));
+    return rc;
+  }
+  __device__ __forceinline__ void push_t(double x, double y) { push_rc(x, y, table_rc()); }
   // Items whose y are CONSECUTIVE integers y0, y0+1, ... (a data set without equal keys): the
   // reference's mean_y recurrence is then exact at every step — dy = k/2, dy/k = 0.5, mean_y =
   // y0 + (k-1)/2, y - mean_y' = (k-1)/2, all representable — so the y chain collapses to one
@@ -456,12 +507,7 @@ template <bool CHECKED> struct LeafWelford {
     m2 = __dadd_rn(m2, __dmul_rn(dx, dx2));
   }
   __device__ __forceinline__ void push_nd(double x) { push_rc_nd(x, next_rc()); }
-  __device__ __forceinline__ void push_t_nd(double x) {
-    double rc;
-    ra += (unsigned)sizeof(double);
-    asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
-    push_rc_nd(x, rc);
-  }
+  __device__ __forceinline__ void push_t_nd(double x) { push_rc_nd(x, table_rc()); }
   __device__ __forceinline__ void nd_finish(double y0) {
     mean_y = nf > 0.0 ? __dadd_rn(y0, __dadd_rn(hy, -0.5)) : 0.0;
   }
@@ -611,6 +657,24 @@ __device__ __forceinline__ void solo_chain(const T* __restrict__ keys, I s_b, I 
   __syncwarp();
 }
 
+// Item functors of the hot fit loops.  A functor with prep()/step() lets stream_pass() convert the keys
+// of the NEXT 16-byte piece (prep: int -> double on the XU pipe, ~20 cycles) while the dependent chain of the
+// current piece runs (step), instead of starting every key's chain with its own conversion.
+template <class T, bool CHECKED> struct FitStepND {
+  LeafWelford<CHECKED>& w;
+  typedef double Prepared;
+  __device__ __forceinline__ Prepared prep(T k) const { return Key<T>::as_float(k); }
+  __device__ __forceinline__ void step(Prepared x) { w.push_t_nd(x); }
+  template <class I> __device__ __forceinline__ void operator()(T k, I) { step(prep(k)); }
+};
+template <class T, bool CHECKED, bool DUPS> struct FitStepDups {
+  LeafWelford<CHECKED>& w;
+  ItemTracker<T, DUPS>& it;
+  struct Prepared { double x; T k; };
+  __device__ __forceinline__ Prepared prep(T k) const { Prepared p; p.x = Key<T>::as_float(k); p.k = k; return p; }
+  __device__ __forceinline__ void step(const Prepared& p) { w.push_t(p.x, it.next(p.k)); }
+  template <class I> __device__ __forceinline__ void operator()(T k, I) { step(prep(k)); }
+};
 // train_model(layer2, vector) for every leaf model type, as warp-synchronous stream passes.
 // f receives Model::params().  Every lane of the warp must call this (with vs == ve if it has
 // no leaf or an empty vector).
@@ -661,13 +725,14 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     };
     if (ND) w.nd_init();
     if (LEAF == M_LINEAR && all_short) {
+      w.table_begin();
       if (ND) {
-        auto item_nd = [&](T k, I) { w.push_t_nd(Key<T>::as_float(k)); };
+        FitStepND<T, CHECKED> item_nd{w};
         if (r.p_remote) item_nd(r.pkey, (I)0);
         stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item_nd);
         nd_materialise(r.ve);
       } else {
-        auto item_t = [&](T k, I) { w.push_t(Key<T>::as_float(k), it.next(k)); };
+        FitStepDups<T, CHECKED, DUPS> item_t{w, it};
         if (r.p_remote) item_t(r.pkey, (I)0);
         stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item_t);
       }
@@ -892,15 +957,21 @@ template <class I> __device__ __forceinline__ I warp_max(I v) {
 
 template <class T, class I, int LEAF, bool DUPS, bool NANCHECK>
 __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const Shard<T>& sh, unsigned char* wsm, bool mine,
-                                             I lo, I hi, u64 g_hi, const double* f, I& max_err, I& run_max) {
+                                             I lo, I hi, const double* f, I& max_err, I& run_max) {
+  // The leaves of a warp's lanes are consecutive, so their key ranges tile one contiguous span
+  // (interrupted only where a lane has no leaf of its own: another rank's, a long leaf built elsewhere).
+  // The warp walks every such SEGMENT as a flat stream, 32 consecutive keys per step whatever leaf they
+  // belong to: the loads of the step FWD_DEPTH ahead are issued before a step is evaluated (the keys come
+  // from L2 / HBM, the latency is that of a miss), and a step that straddles a leaf boundary is evaluated
+  // once per leaf it touches.  Per-leaf maxima are reduced when the stream leaves the leaf.
   constexpr int PPM = leaf_params_per_model(LEAF);
-  constexpr int FWD_DEPTH = 4;   // coalesced 32-key loads in flight per outer step
+  constexpr int FWD_DEPTH = 8;
+  constexpr int REC = 16 + ((PPM * 8 + 15) / 16) * 16;   // {lo, hi} + parameters, 16-byte aligned
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const unsigned le_mask = (2u << lane) - 1u;            // lanes at or below this one
   const I nI = (I)sh.n_global;
   const I baseI = (I)sh.base;
-  // per-lane descriptors: {lo, hi} as two u64, then PPM doubles, one 16-byte aligned record per lane
-  constexpr int REC = 16 + ((PPM * 8 + 15) / 16) * 16;
   unsigned todo = __ballot_sync(FULL, mine);
   if (todo == 0) return;
   __syncwarp();
@@ -909,83 +980,125 @@ __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const S
     *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2((u64)lo, (u64)hi);
 #pragma unroll
     for (int q = 0; q < PPM; ++q) reinterpret_cast<double*>(rec + 16)[q] = f[q];
-    if (DUPS) reinterpret_cast<u64*>(wsm + 32 * REC)[lane] = g_hi;
+  }
+  // a lane's leaf continues the segment of the previous lane that has one iff it starts where that one ends
+  unsigned seg_starts;
+  {
+    const unsigned lower = todo & (le_mask >> 1);        // lanes with a leaf strictly below this one
+    const int prev = lower ? 31 - __clz(lower) : lane;
+    const I prev_hi = __shfl_sync(FULL, hi, prev);
+    seg_starts = __ballot_sync(FULL, mine && (lower == 0 || prev_hi != lo));
   }
   __syncwarp();
   while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const unsigned char* rec = wsm + src * REC;
-    const ulonglong2 lh = *reinterpret_cast<const ulonglong2*>(rec);
-    const I c_lo = (I)lh.x, c_hi = (I)lh.y;
+    int q = __ffs(todo) - 1;                             // first leaf of the segment
+    // last leaf of the segment: the one before the next segment start (or the last leaf at all)
+    const unsigned later_starts = seg_starts & ~((2u << q) - 1u);
+    const unsigned seg_mask = later_starts ? (todo & ((1u << (__ffs(later_starts) - 1)) - 1u)) : todo;
+    const int q_last = 31 - __clz(seg_mask);
+    todo &= ~seg_mask;
+    unsigned left = seg_mask & ~(1u << q);               // leaves of the segment after the current one
+    const I seg_lo = (I)reinterpret_cast<const ulonglong2*>(wsm + q * REC)->x;
+    const I seg_hi = (I)reinterpret_cast<const ulonglong2*>(wsm + q_last * REC)->y;
+    I hi_q = (I)reinterpret_cast<const ulonglong2*>(wsm + q * REC)->y;
     double cf[PPM];
 #pragma unroll
-    for (int q = 0; q < PPM; ++q) cf[q] = reinterpret_cast<const double*>(rec + 16)[q];
+    for (int t = 0; t < PPM; ++t) cf[t] = reinterpret_cast<const double*>(wsm + q * REC + 16)[t];
     I w_err = 0, w_run = 0;
-    I carry_F = (I)(c_lo + baseI);     // offset of the last key seen so far (DUPS)
+    I carry_F = (I)(seg_lo + baseI);
     T carry_k = T();
-    for (I b0 = c_lo; b0 < c_hi; b0 += (I)(32 * FWD_DEPTH)) {
-      T kk[FWD_DEPTH];
+    auto leave_leaf = [&]() {   // the stream has passed leaf q: hand its maxima to the owner, move to the next leaf
+      const I r_err = warp_max<I>(w_err);
+      I r_run = 0;
+      if (DUPS) r_run = warp_max<I>(w_run);
+      if (lane == q) { max_err = r_err; if (DUPS) run_max = r_run; }
+      w_err = 0; w_run = 0;
+      if (left) {
+        q = __ffs(left) - 1;
+        left &= left - 1;
+        hi_q = (I)reinterpret_cast<const ulonglong2*>(wsm + q * REC)->y;
 #pragma unroll
-      for (int u = 0; u < FWD_DEPTH; ++u) {
-        const I iu = b0 + (I)(u * 32 + lane);
-        kk[u] = iu < c_hi ? __ldcs(keys + iu) : T();   // streaming: this is the last use of the line
+        for (int t = 0; t < PPM; ++t) cf[t] = reinterpret_cast<const double*>(wsm + q * REC + 16)[t];
       }
+    };
+    T kk[FWD_DEPTH];
+#pragma unroll
+    for (int u = 0; u < FWD_DEPTH; ++u) {
+      const I iu = seg_lo + (I)(u * 32 + lane);
+      kk[u] = (iu < seg_hi && iu >= seg_lo) ? __ldcs(keys + iu) : T();     // streaming: the line's last use
+    }
+    I pos = seg_lo;
+    // look-ahead loads are unconditional: the index is clamped to the last readable key instead of predicated
+    // (a predicated load costs a branch per step; a clamped one past the segment's end is simply not used)
+    I inext = (I)(seg_lo + (I)(FWD_DEPTH * 32 + lane));
+    const I last_readable = (I)(sh.n_avail - 1);
+    I Fi = (I)(seg_lo + (I)lane + baseI);                 // global index of this lane's key in the current step
+    bool done = false;
+    while (!done) {
 #pragma unroll
       for (int u = 0; u < FWD_DEPTH; ++u) {
-        const I s0 = b0 + (I)(u * 32);
-        if (DUPS && s0 >= c_hi) break;   // warp-uniform (without duplicate tracking an all-invalid step is a no-op)
-        const I i = s0 + (I)lane;
-        const bool valid = i < c_hi;
         const T k = kk[u];
-        const I Fi = (I)(i + baseI);
-        I F = Fi;
+        kk[u] = __ldcs(keys + (inext < last_readable ? inext : last_readable));
+        inext += 32;
+        const double x = Key<T>::as_float(k);
+        if (!DUPS && (I)(hi_q - pos) >= (I)32) {
+          // the whole step lies inside leaf q (the common case: 5 of 6 steps at 190 keys per leaf)
+          const I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, x, nI);
+          const I e = pred > Fi ? pred - Fi : Fi - pred;
+          w_err = e > w_err ? e : w_err;
+          pos += 32;
+          Fi += 32;
+          continue;
+        }
+        if (pos >= seg_hi) { done = true; break; }        // warp-uniform
+        const I i = pos + (I)lane;
+        const I step_end = (seg_hi - pos) > (I)32 ? (I)(pos + 32) : seg_hi;
+        const bool valid = i < step_end;
+        I F = Fi, len = 0;
+        bool pend = valid, pend_run = false;
         if (DUPS) {
           T kp = __shfl_up_sync(FULL, k, 1);
           if (lane == 0) kp = carry_k;
-          const bool starts = valid && (i == c_lo || k != kp);
+          const bool starts = valid && (i == seg_lo || k != kp);   // a segment's (and every leaf's) first key starts a run
           const unsigned sm = __ballot_sync(FULL, starts);
-          const unsigned vm = __ballot_sync(FULL, valid);
-          if (sm == vm) {
-            // every key of this step starts its own run: the runs that end here have length 1, except
-            // the one that may have come in from the previous step
-            if (valid && i != c_lo) {
-              const I len = lane == 0 ? (I)(Fi - carry_F) : (I)1;
-              w_run = len > w_run ? len : w_run;
-            }
-          } else {
-            const unsigned below = sm & ((2u << lane) - 1u);   // run starts at or below this lane
-            F = below ? (I)(s0 + baseI + (I)(31 - __clz(below))) : carry_F;
-            I Fm1 = __shfl_up_sync(FULL, F, 1);
-            if (lane == 0) Fm1 = carry_F;
-            if (starts && i != c_lo) {   // the run before this key ends here
-              const I len = (I)(Fi - Fm1);
-              w_run = len > w_run ? len : w_run;
-            }
-          }
-          const int lastv = (c_hi - s0) < (I)32 ? (int)(c_hi - s0) - 1 : 31;
+          const unsigned below = sm & le_mask;
+          F = below ? (I)(pos + baseI + (I)(31 - __clz(below))) : carry_F;
+          I Fm1 = __shfl_up_sync(FULL, F, 1);
+          if (lane == 0) Fm1 = carry_F;
+          // the run BEFORE a run start ends here; its length belongs to the leaf of the key before this one
+          pend_run = starts && i != seg_lo;
+          len = (I)(Fi - Fm1);
+          const int lastv = (int)(step_end - pos) - 1;
           carry_F = __shfl_sync(FULL, F, lastv);
           carry_k = __shfl_sync(FULL, k, lastv);
         }
-        {   // branch-free: an invalid lane evaluates the model on a zero key and discards the result
-          const I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, Key<T>::as_float(k), nI);
+        for (;;) {
+          const I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, x, nI);
           I e = pred > F ? pred - F : F - pred;
-          e = valid ? e : (I)0;
+          const bool take = pend && i < hi_q;
+          e = take ? e : (I)0;
           w_err = e > w_err ? e : w_err;
+          pend = pend && !take;
+          if (DUPS) {
+            const bool take_run = pend_run && i <= hi_q;
+            const I l = take_run ? len : (I)0;
+            w_run = l > w_run ? l : w_run;
+            pend_run = pend_run && !take_run;
+          }
+          if (hi_q >= step_end) break;                    // warp-uniform: leaf q covers the rest of the step
+          leave_leaf();
         }
+        pos = step_end;
+        Fi += 32;
       }
     }
-    w_err = warp_max<I>(w_err);
-    if (DUPS) {
-      w_run = warp_max<I>(w_run);
-      // the leaf's final run is recorded only if another run follows it in the data set
-      const u64 c_ghi = reinterpret_cast<const u64*>(wsm + 32 * REC)[src];
-      if (c_ghi < sh.n_global) {
-        const I len = (I)((I)(c_hi + baseI) - carry_F);
-        w_run = len > w_run ? len : w_run;
-      }
+    // the segment's last leaf: its final run counts only if another run follows it in the data set
+    if (DUPS && (u64)seg_hi + sh.base < sh.n_global) {
+      const I l = (I)((I)(seg_hi + baseI) - carry_F);
+      w_run = l > w_run ? l : w_run;
     }
-    if (lane == src) { max_err = w_err; if (DUPS) run_max = w_run; }
+    left = 0;
+    leave_leaf();
   }
   __syncwarp();
 }
@@ -1191,7 +1304,7 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   // row ring a second time.  Owners park their leaf's range and parameters in the warp's shared
   // memory (the ring is idle now); results return to the owner lane.
   I max_err = 0, run_max = 0;
-  coop_forward<T, I, LEAF, DUPS, NANCHECK>(keys, sh, wsm, live && r.hi > r.lo, r.lo, r.hi, g_hi, f, max_err, run_max);
+  coop_forward<T, I, LEAF, DUPS, NANCHECK>(keys, sh, wsm, live && r.hi > r.lo, r.lo, r.hi, f, max_err, run_max);
   if (!DUPS) {
     // no two keys of the data set are equal: every run has length 1 (and the data set's final run
     // is never recorded, lower_bound_correction.rs:108-119)
@@ -1496,7 +1609,7 @@ template <class T, int LEAF>
 void launch_leaf(const Launch& L, const T* keys, const Shard<T>& sh, u64 N, const u64* d_S, BuildAux* d_aux,
                  double* d_params, u64* d_errors, u64* d_counts) {
   constexpr bool SPECIALISED = LEAF == M_LINEAR || LEAF == M_LINEAR_SPLINE || LEAF == M_CUBIC;
-  if (sh.n_global < 0xfffffff0ull) {   // 32-bit indices
+  if (sh.n_global < 0xfffffc00ull) {   // 32-bit indices (with room for the forward pass's look-ahead: no index arithmetic wraps)
     if (SPECIALISED && sh.no_dups)
       launch_leaf_inst<T, u32, SPECIALISED ? LEAF : M_LINEAR, false>(L, keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts);
     else

@@ -107,6 +107,49 @@ def test_fast_top_fit_within_tolerance_then_exact_downstream(rmi, oracle, top, b
     parity.assert_same_rmi(g, o)
 
 
+@pytest.mark.parametrize("dname", list(DATA))
+@pytest.mark.parametrize("top", ["loglinear", "normal", "lognormal"])
+@pytest.mark.parametrize("bf", [100, 4096])
+def test_log_and_normal_tops_single_gpu(rmi, oracle, top, bf, dname):
+    """loglinear (linear.rs:61-72, :169-180), normal and lognormal (normal.rs:28-76, :89-92, :163-167) as TOP
+    models on the single-GPU kernels (k_slr_partial<MODE 1>, k_normal_*), followed by the streaming
+    boundary pass these non-monotone-by-construction tops take.  Fast flow: coefficients within 1e-9 of the
+    oracle's serial sums, then — with the GPU's coefficients injected into the oracle — everything downstream
+    bit-identical.  Where the reference panics (two_layer.rs:50: the model is not monotone on the data, or a
+    split at an end) the GPU path must panic too."""
+    spec = f"{top},linear"
+    keys = data(dname)
+    try:
+        o_ref = oracle.train(keys, spec, bf)
+    except oracle.OraclePanic as e_ref:
+        # with tolerance-level coefficients the GPU run lands on the same side in every case below
+        with pytest.raises(rmi.RMIPanic):
+            rmi.train(dataset(rmi, dname), spec, bf)
+        pytest.skip(f"reference panics here and so does the GPU path: {e_ref}")
+    g = rmi.train(dataset(rmi, dname), spec, bf)
+    parity.assert_top_equal(g, o_ref, exact=False, N=bf)
+    try:
+        o = oracle.train(keys, spec, bf, l0_override=g.l0_fparams)
+    except oracle.OraclePanic as e:
+        pytest.fail(f"oracle panics on the GPU's own top coefficients: {e}")
+    if top == "lognormal" and not np.array_equal(g.l1_counts, o.l1_counts):
+        # the top prediction goes through ln(x) for every key: a last-bit difference between the device's
+        # and libm's ln can move single keys across a leaf boundary; the leaves it does not touch are identical
+        same = g.l1_counts == o.l1_counts
+        assert same.mean() > 0.99, f"{(~same).sum()} of {bf} leaves differ"
+        return
+    parity.assert_same_rmi(g, o)
+
+
+@pytest.mark.parametrize("dname", ["uniform_u64", "uniform_u32", "lognormal_u64"])
+@pytest.mark.parametrize("top", ["radix22", "radix26"])
+def test_large_radix_tables_bit_exact(rmi, oracle, top, dname):
+    """radix22 is in the optimizer's default profile (optimizer.rs:110-151); radix26 is the next template size.
+    16 MiB / 256 MiB hint tables (radix.rs:90-134), bit-exact."""
+    g, o = run_both(rmi, oracle, dname, f"{top},linear", 1024)
+    parity.assert_same_rmi(g, o)
+
+
 @pytest.mark.parametrize("dname", ["uniform_u64", "lognormal_u64", "dups_u64", "uniform_f64"])
 @pytest.mark.parametrize("leaf", ["cubic", "robust_linear", "normal"])
 def test_other_leaf_models_given_top(rmi, oracle, leaf, dname):

@@ -6,9 +6,8 @@ set -o pipefail
 #   tools/build_variants.sh s3 t64     # a subset
 declare -A DEFS=(
   [s3]="-DRMI_SSTAGES=3"                 # three copy stages in the row ring instead of two
-  [t64]="-DRMI_LEAF_THREADS=64"          # 64-lane blocks: finer tail, more blocks per SM
-  [t256]="-DRMI_LEAF_THREADS=256 -DRMI_LEAF_MIN_BLOCKS=3 -DRMI_RCP_TABLE=384"   # 256-lane blocks, 3 per SM (24 warps)
-  [b6]="-DRMI_LEAF_MIN_BLOCKS=6 -DRMI_RCP_TABLE=384"   # 6 blocks of 128 lanes per SM (needs <= 80 registers, 37 KB of shared memory each)
+  [b5]="-DRMI_LEAF_MIN_BLOCKS=5"         # 5 blocks of 128 lanes per SM for every instantiation (96 registers)
+  [b4]="-DRMI_LEAF_MIN_BLOCKS=4"         # 4 blocks per SM (128 registers): fewer leaves in flight between the two reads of a key
   [pb]="-DRMI_PIPELINED_BOUNDS"          # leaf-boundary search sliced and overlapped with the leaf kernel's slices
 )
 names=("$@")
