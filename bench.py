@@ -10,17 +10,25 @@ A "step" is one complete two-layer build (rmi_lib::train) of the workload
 top-model fit, leaf boundaries, per-leaf fits, forward/error pass, lower-bound widening,
 statistics, and the copy of all leaf parameters and error bounds back to the host.
 
-value       keys/s with the key array already resident in HBM (all ranks' keys / max-over-ranks time)
-e2e         the same build through the C ABI from a PINNED HOST buffer: H2D copy of the keys +
-            build + results on the host, every step
-roofline    the dominant kernel (fused leaf fit + forward/error pass): algorithmic bytes per
-            launch / its CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
+value        keys/s with the key array already resident in HBM (all ranks' keys / max-over-ranks time)
+e2e          the same build through the C ABI from a PINNED HOST buffer: H2D copy of the keys +
+             build + results on the host, every step
+roofline     the dominant kernel (fused leaf fit + forward/error pass): algorithmic bytes per
+             launch / its CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
 cpu_baseline the CPU oracle (a C++ port of the reference algorithm; the Rust reference cannot be
-            built offline) timed on a bounded sample of the same workload on this box's cores
+             built offline) timed on this box's cores: ONE build of the FULL workload (about 10 s)
+parity       (outside the timed regions) the build that was timed is compared with the oracle:
+             N = 1: top coefficients' true relative error, leaves whose bound differs from the serial
+             top fit's, and bit-exact equality of every leaf record given the same top coefficients;
+             N > 1: every rank's result hashes equal, and equal to a single-GPU build of the gathered keys
+extra_configs  BASELINE.json configs[2], [3] (cubic,linear 262144; radix,linear 524288 on uint32), the
+             skewed / duplicate-heavy variants of the headline data set, the bit-exact top-fit mode, and at
+             N > 1 the strong-scaling point (200M keys in total over the N GPUs)
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -45,10 +53,19 @@ def parse_args():
     ap.add_argument("--leaves", type=int, default=1 << 20)
     ap.add_argument("--spec", default="linear,linear")
     ap.add_argument("--exact-top", action="store_true", help="RMI_FLAG_TOP_FIT_EXACT (serial top fit)")
-    ap.add_argument("--cpu-sample-div", type=int, default=8, help="cpu baseline runs on n/div keys, N/div leaves")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle legs (cpu_baseline, parity)")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra_configs")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--extra-steps", type=int, default=5)
     return ap.parse_args()
+
+
+def workload_config(args, world):
+    """What both arms are asked to build — identical in the two arms' JSON lines."""
+    n = int(args.keys)
+    return {"workload": f"{args.spec} {args.leaves} on {n} synthetic sorted uint64 per GPU",
+            "spec": args.spec, "leaves": args.leaves, "keys_per_gpu": n, "key_type": "uint64", "n_gpus": world,
+            "distribution": "uniform over [0, 2^63), sorted, duplicates kept (none occur at this density)"}
 
 
 class ClockSampler:
@@ -112,7 +129,7 @@ def measured_hbm_peak():
 
 
 def ncu_traffic_per_launch():
-    """dram read+write bytes of the dominant kernel from the committed ncu --set full capture."""
+    """dram read+write bytes of the dominant kernel from the committed ncu --set full capture (1 GPU)."""
     p = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     try:
         with open(p) as f:
@@ -121,27 +138,12 @@ def ncu_traffic_per_launch():
         return None
 
 
-def sample_for_cpu(keys_np, div):
-    return keys_np[::div].copy()
-
-
-def time_oracle(keys_np, spec, leaves, threads=2):
+def time_oracle(keys_np, spec, leaves, threads=2, l0=None):
     import oracle
     t0 = time.perf_counter()
-    r = oracle.train(keys_np, spec, leaves, threads=threads)
+    r = oracle.train(keys_np, spec, leaves, threads=threads, l0_override=l0)
     dt = time.perf_counter() - t0
-    r.close()
-    return dt
-
-
-def time_oracle_concurrent(keys_np, spec, leaves, workers):
-    """`workers` independent builds at once, 2 threads each — how the reference occupies a many-core host
-    (optimizer.rs:224 par_iter over configurations); returns aggregate keys/s.  ctypes releases the GIL."""
-    from concurrent.futures import ThreadPoolExecutor
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=workers) as ex:
-        list(ex.map(lambda _: time_oracle(keys_np, spec, leaves), range(workers)))
-    return workers * keys_np.size / (time.perf_counter() - t0)
+    return dt, r
 
 
 def host_keys_numpy(n, seed):
@@ -154,30 +156,32 @@ def host_keys_numpy(n, seed):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port, <= 2 threads as
-    rayon::join gives the reference, two_layer.rs:161-169) on a bounded sample."""
+    """--impl reference: the reference's CPU algorithm (C++ oracle port, <= 2 threads as rayon::join gives the
+    reference, two_layer.rs:161-169).  Every step is ONE build of the full single-GPU workload (200M keys, 2^20
+    leaves: about 10 s); under torchrun (N > 1) rank 0 alone runs it, on the same 200M-key build — 1/N of the
+    N-GPU job's keys — because a CPU build of N x 200M keys would not fit the time limit (keys/s of this
+    linear-time path does not depend on the size)."""
     if rank != 0:
         return
     import oracle
     oracle.build()
-    n_full = int(args.keys)
-    n_s = max(n_full // args.cpu_sample_div, 1000)
-    leaves_s = max(args.leaves // args.cpu_sample_div, 2)
-    keys = host_keys_numpy(n_s, 42)
+    n = int(args.keys)
+    keys = host_keys_numpy(n, 42)
     for _ in range(args.warmup):
-        time_oracle(keys, args.spec, leaves_s)
+        time_oracle(keys, args.spec, args.leaves)
     t = []
     for _ in range(args.steps):
-        t.append(time_oracle(keys, args.spec, leaves_s))
+        t.append(time_oracle(keys, args.spec, args.leaves)[0])
     tot = sum(t)
-    val = n_s * args.steps / tot
-    sample = f"{n_s} uniform uint64 keys, {args.spec} {leaves_s} (1/{args.cpu_sample_div} of the workload, same keys per leaf)"
+    val = n * args.steps / tot
+    sample = (f"every step = one build of {n} uniform uint64 keys (numpy MT19937(42), sorted), {args.spec} {args.leaves}: "
+              + ("the full workload" if world == 1 else f"one GPU's share (1/{world}) of the {world}-GPU job's keys"))
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "keys/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{args.spec} {args.leaves} on {n_full} synthetic sorted uint64 per GPU",
-                      "note": "Rust reference cannot be built offline (no cargo); this is the C++ oracle port of "
-                              "rmi_lib::train, single build uses <= 2 threads like the reference"},
+           "config": workload_config(args, world),
+           "notes": "Rust reference cannot be built offline (no cargo); this is the C++ oracle port of rmi_lib::train; a "
+                    "single build uses <= 2 threads like the reference",
            "cpu_baseline": {"value": val, "unit": "keys/s", "cores": 2, "kind": "port", "sample": sample,
                             "host_cores": os.cpu_count()},
            "e2e": {"value": val, "unit": "keys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -205,6 +209,15 @@ def quiet_stdout():
         os.dup2(2, 1)
 
 
+def result_digest(r):
+    h = hashlib.sha256()
+    h.update(r.l0_fparams.tobytes())
+    h.update(r.l1_params.tobytes())
+    h.update(r.last_layer_max_l1s.tobytes())
+    h.update(repr((r.model_max_error, r.model_max_error_idx, r.model_avg_error)).encode())
+    return h.hexdigest()
+
+
 def main():
     quiet_stdout()
     args = parse_args()
@@ -229,87 +242,97 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    from rmi_b200 import sharded
 
     n = int(args.keys)
     N = args.leaves
-    flags = rmi_b200.FLAG_TOP_FIT_EXACT if args.exact_top else 0
-    # ---- synthetic workload: sorted uniform uint64 keys; rank r draws from the r-th slice of
-    # the key space so that the concatenation over ranks is globally sorted -------------------
-    g = torch.Generator(device=dev)
-    g.manual_seed(42 + rank)
-    width = ((1 << 63) - 1) // world
-    k = torch.randint(0, width, (n,), dtype=torch.int64, device=dev, generator=g) + rank * width
-    k, _ = torch.sort(k)
-    torch.cuda.synchronize()
-    ppm = 2
+    top_flag = rmi_b200.FLAG_TOP_FIT_EXACT if args.exact_top else 0
     key_bytes = 8
-    if world == 1:
-        ds = rmi_b200.RMITrainingData.from_device(k.data_ptr(), n, rmi_b200.KEY_U64, local_rank, keep_alive=k)
-
-        def build():
-            return rmi_b200.train(ds, args.spec, N, flags, counts=False)
-    else:
-        # range-partitioned build: ONE global RMI with N leaves over all ranks' keys
-        # (rank r holds the r-th slab of the globally sorted array); weak scaling in keys.
-        from rmi_b200 import sharded
-        sdata = sharded.ShardedTrainingData(k, n, rmi_b200.KEY_U64, halo_capacity=1 << 20)
-
-        def build():
-            return sharded.train_sharded(sdata, args.spec, N, flags, counts=False)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gen_uniform(count, seed, lo_frac, hi_frac, dtype=torch.int64):
+        """sorted uniform keys over the slice [lo_frac, hi_frac) of the key space, on the device"""
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        top = (1 << 63) - 1 if dtype == torch.int64 else (1 << 31) - 1
+        lo, hi = int(top * lo_frac), int(top * hi_frac)
+        k = torch.randint(lo, max(hi, lo + 1), (count,), dtype=dtype, device=dev, generator=g)
+        k, _ = torch.sort(k)
+        return k
+
+    def make_builder(keys_t, count, key_type, spec, leaves, flags, root_only=True):
+        """returns (build(), keep_alive): one complete build of `spec` on this job's GPUs"""
+        if world == 1:
+            ds = rmi_b200.RMITrainingData.from_device(keys_t.data_ptr(), count, key_type, local_rank, keep_alive=keys_t)
+            return (lambda: rmi_b200.train(ds, spec, leaves, flags, counts=False)), ds
+        sd = sharded.ShardedTrainingData(keys_t, count, key_type, halo_capacity=1 << 20)
+        fl = flags | (rmi_b200.FLAG_SHARD_ROOT_ONLY if root_only else 0)
+        return (lambda: sharded.train_sharded(sd, spec, leaves, fl, counts=False)), sd
+
+    def timed(build, steps, warmup=2):
+        """(ms per step, max over ranks; last result; summed phase ns; summed device ns)"""
+        res = None
+        for _ in range(warmup):
+            res = build()
+        phase = np.zeros(4)
+        dev_ns = 0.0
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            res = build()      # synchronous: returns with results on the host
+            phase += np.array(res.phase_device_ns, dtype=np.float64)
+            dev_ns += res.device_time_ns
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, res, phase / steps, dev_ns / steps
+
+    # ---- synthetic workload: sorted uniform uint64 keys; rank r draws from the r-th slice of the key space so
+    # that the concatenation over ranks is globally sorted ------------------------------------------------------------
+    k = gen_uniform(n, 42 + rank, rank / world, (rank + 1) / world)
+    torch.cuda.synchronize()
+    ppm = 2
+    build, keep = make_builder(k, n, rmi_b200.KEY_U64, args.spec, N, top_flag)
+
     clocks = ClockSampler(local_rank)
-    # ---- warm-up --------------------------------------------------------------------------
     res = None
     for _ in range(max(args.warmup, 3)):
         res = build()
     if rank == 0:
         clocks.start()
-    # ---- timed region: K resident builds ---------------------------------------------------
+    # ---- timed region: K resident builds ------------------------------------------------------------------------
     launches0 = rmi_b200.kernel_launch_count()
-    phase = np.zeros(4)
-    dev_ns = 0.0
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = build()      # synchronous: returns with results on the host
-        phase += np.array(res.phase_device_ns, dtype=np.float64)
-        dev_ns += res.device_time_ns
-    e1.record()
-    barrier()
-    wall = time.perf_counter() - t0
-    ev_ms = e0.elapsed_time(e1)
+    t_wall0 = time.perf_counter()
+    ms_per_step, res, phase_ms, dev_ns = timed(build, args.steps, warmup=0)
+    wall = time.perf_counter() - t_wall0
     launches = rmi_b200.kernel_launch_count() - launches0
-    t_rank = torch.tensor([ev_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_rank, op=dist.ReduceOp.MAX)
-    ms_total = float(t_rank.item())
-    ms_per_step = ms_total / args.steps
+    phase_ms = phase_ms / 1e6
     value = (n * world) / (ms_per_step / 1e3)
 
-    # ---- e2e: pinned host keys -> H2D -> build -> results on host, every step ----------------
+    # ---- e2e: pinned host keys -> H2D -> build -> results on host, every step -----------------------------------
     host = torch.empty(n, dtype=torch.int64, pin_memory=True)
     host.copy_(k)
     torch.cuda.synchronize()
     host_np = host.numpy().view(np.uint64)
+
     def e2e_step():
         if world == 1:
             d2 = rmi_b200.RMITrainingData(host_np, device=local_rank)   # cudaMemcpy H2D from pinned memory
-            r2 = rmi_b200.train(d2, args.spec, N, flags, counts=False)
+            r2 = rmi_b200.train(d2, args.spec, N, top_flag, counts=False)
             d2.close()
         else:
-            from rmi_b200 import sharded
             kd = torch.empty(n + (1 << 20), dtype=torch.int64, device=dev)
             kd[:n].copy_(host, non_blocking=False)                       # H2D from pinned memory
-            sd = sharded.ShardedTrainingData(kd, n, rmi_b200.KEY_U64, halo_capacity=1 << 20)
-            r2 = sharded.train_sharded(sd, args.spec, N, flags, counts=False)
+            sd2 = sharded.ShardedTrainingData(kd, n, rmi_b200.KEY_U64, halo_capacity=1 << 20)
+            r2 = sharded.train_sharded(sd2, args.spec, N, top_flag | rmi_b200.FLAG_SHARD_ROOT_ONLY, counts=False)
         return r2
 
     e2e_step()
@@ -328,70 +351,162 @@ def main():
     e2e_val = (n * world) / (e2e_ms / 1e3)
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- parity of what was timed (outside the timed regions) ---------------------------------------------------
+    parity = {}
+    cpu = None
+    if world > 1:
+        # (1) every rank's copy of the result must be identical
+        full_build, _k2 = make_builder(k, n, rmi_b200.KEY_U64, args.spec, N, top_flag, root_only=False)
+        g_all = full_build()
+        digests = [None] * world
+        dist.all_gather_object(digests, result_digest(g_all))
+        parity["ranks_agree"] = len(set(digests)) == 1
+        # (2) ... and equal to ONE GPU's build of the concatenated key array with the same top coefficients
+        gathered = [torch.empty(n, dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(k, gathered, dst=0)
+        if rank == 0:
+            allk = torch.cat(gathered)
+            del gathered
+            ds1 = rmi_b200.RMITrainingData.from_device(allk.data_ptr(), allk.numel(), rmi_b200.KEY_U64, local_rank, keep_alive=allk)
+            g1 = rmi_b200.train(ds1, args.spec, N, 0, l0_params=g_all.l0_fparams, counts=False)
+            same = (np.array_equal(g1.l1_params.view(np.uint64), g_all.l1_params.view(np.uint64))
+                    and np.array_equal(g1.last_layer_max_l1s, g_all.last_layer_max_l1s)
+                    and g1.model_max_error == g_all.model_max_error and g1.model_max_error_idx == g_all.model_max_error_idx
+                    and g1.model_avg_error == g_all.model_avg_error)
+            parity["equals_single_gpu_build_of_all_keys"] = bool(same)
+            parity["checked_keys"] = int(allk.numel())
+            parity["parity_check"] = "ok" if (same and parity["ranks_agree"]) else "MISMATCH"
+            del allk, ds1
+        barrier()
+    elif not args.no_cpu_baseline:
+        import oracle
+        from tests import parity as tparity
+        oracle.build()
+        g = rmi_b200.train(keep, args.spec, N, top_flag, counts=True)
+        dt, o_ref = time_oracle(host_np, args.spec, N)              # the reference's own (serial) top fit: the CPU baseline
+        cpu = {"value": n / dt, "unit": "keys/s", "cores": 2, "kind": "port",
+               "sample": f"ONE build of the full workload ({n} keys, {args.spec} {N}) on 2 threads (the reference's rayon::join)",
+               "host_cores": os.cpu_count(), "seconds": dt}
+        names = {2: ["alpha", "beta"], 4: ["a", "b", "c", "d"], 3: ["mean", "stdev", "scale"]}.get(len(o_ref.l0.fp), [])
+        parity["top_fit_rel_err"] = dict(zip(names, tparity.coef_rel_err(g.l0_fparams, o_ref.l0.fp)))
+        parity["leaves_differing_vs_serial_fit"] = int((g.last_layer_max_l1s != o_ref.l1_errors).sum())
+        parity["max_error_serial_fit_vs_this"] = [int(o_ref.max_error), int(g.model_max_error)]
+        _, o = time_oracle(host_np, args.spec, N, l0=g.l0_fparams)  # same top coefficients: everything else must be bit-exact
+        try:
+            tparity.assert_same_rmi(g, o)
+            parity["parity_check"] = "ok"
+        except AssertionError as e:
+            parity["parity_check"] = "MISMATCH: " + str(e)[:300]
+        parity["parity_check_what"] = ("every leaf parameter, error bound, key count and the summary statistics bit-identical to the "
+                                       "oracle run with this build's top coefficients")
+        del o, o_ref
+
+    # ---- extra configurations ---------------------------------------------------------------------------------
+    extras = {}
+    peak, peak_src = measured_hbm_peak()
+    if not args.no_extras:
+        def extra(name, keys_t, count, key_type, spec, leaves, kb, flags=0, steps=None):
+            try:
+                b2, keep2 = make_builder(keys_t, count, key_type, spec, leaves, flags)
+                ms, r, ph, dns = timed(b2, steps or args.extra_steps)
+                nbytes = 2 * count * world * kb + leaves * (8 * rmi_b200.api.load_library().rmi_params_per_model(spec.split(",")[1].encode()) + 8)
+                extras[name] = {"value": count * world / (ms / 1e3), "unit": "keys/s", "ms_per_step": ms,
+                                "phases_ms": [float(x) / 1e6 for x in ph], "device_ms": dns / 1e6,
+                                "whole_build_frac_of_hbm_peak": nbytes / world / (ms / 1e3) / 1e9 / peak,
+                                "max_error": int(r.model_max_error)}
+            except rmi_b200.RMIError as e:
+                extras[name] = {"error": str(e)[:200]}
+
+        # BASELINE.json configs[2]: cubic,linear 262144 on the same keys (at every N)
+        extra("cubic,linear 262144", k, n, rmi_b200.KEY_U64, "cubic,linear", 262144, 8)
+        if world == 1:
+            # configs[3]: radix,linear 524288 on 200M uint32
+            k32 = gen_uniform(n, 7, 0.0, 1.0, dtype=torch.int32)
+            extra("radix,linear 524288 (uint32)", k32, n, rmi_b200.KEY_U32, "radix,linear", 524288, 4)
+            del k32
+            # the headline build on less friendly data: lognormal skew, 5% duplicated keys
+            g = torch.Generator(device=dev)
+            g.manual_seed(3)
+            kl = torch.exp(torch.randn(n, dtype=torch.float64, device=dev, generator=g) * 2.0) * float(1 << 40)
+            kl = torch.sort(torch.round(kl).to(torch.int64))[0]
+            extra("linear,linear 1048576, lognormal(sigma=2) keys", kl, n, rmi_b200.KEY_U64, args.spec, N, 8)
+            del kl
+            kd = k.clone()
+            g.manual_seed(5)
+            m = torch.rand(n, device=dev, generator=g) < 0.05
+            m[0] = False
+            idx = torch.nonzero(m).squeeze(1)
+            kd[idx] = kd[idx - 1]
+            kd = torch.sort(kd)[0]
+            extra("linear,linear 1048576, 5% duplicated keys", kd, n, rmi_b200.KEY_U64, args.spec, N, 8)
+            del kd, m, idx
+            # bit-exact top fit (RMI_FLAG_TOP_FIT_EXACT): the reference's serial recurrence
+            extra("linear,linear 1048576, exact (serial) top fit", k, n, rmi_b200.KEY_U64, args.spec, N, 8,
+                  flags=rmi_b200.FLAG_TOP_FIT_EXACT, steps=1)
+            if "linear,linear 1048576, exact (serial) top fit" in extras:
+                parity["exact_top_ms_per_step"] = extras["linear,linear 1048576, exact (serial) top fit"].get("ms_per_step")
+        else:
+            # strong scaling: BASELINE's 200M keys IN TOTAL over the N GPUs
+            ns = n // world
+            ks = gen_uniform(ns, 4242 + rank, rank / world, (rank + 1) / world)
+            extra(f"strong scaling: {args.spec} {N} on {ns * world} keys in total", ks, ns, rmi_b200.KEY_U64, args.spec, N, 8,
+                  steps=args.steps)
+            del ks
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel ----------------------------------------------------
-    phase_ms = phase / args.steps / 1e6
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------------
     names = ["top_fit", "leaf_bounds", "leaf_fit_error(k_leaf)", "statistics"]
     dom = int(np.argmax(phase_ms))
-    peak, peak_src = measured_hbm_peak()
     out_bytes = N * (8 * ppm + 8)     # leaf parameters + error bounds copied to the host every step
     kern_bytes = {0: n * key_bytes, 1: n * key_bytes + (N + 1) * 8, 2: n * key_bytes + (N + 1) * 8 + out_bytes,
                   3: N * 16}[dom]
     achieved = kern_bytes / (phase_ms[dom] / 1e3) / 1e9
     build_bytes = 2 * n * key_bytes + N * (8 * ppm + 8)
-    tr = ncu_traffic_per_launch()
+    tr = ncu_traffic_per_launch() if world == 1 else None
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                "traffic_source": (tr or {}).get("source") if tr else "not captured at this N (ncu is a 1-GPU tool here)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": kern_bytes,
                 "kernel_ms": float(phase_ms[dom]),
                 "phases_ms": {nm: float(v) for nm, v in zip(names, phase_ms)},
-                "whole_build": {"algorithmic_bytes": build_bytes, "device_ms": dev_ns / args.steps / 1e6,
-                                "achieved": build_bytes / (dev_ns / args.steps / 1e9) / 1e9,
-                                "frac": build_bytes / (dev_ns / args.steps / 1e9) / 1e9 / peak}}
+                "whole_build": {"algorithmic_bytes": build_bytes, "ms_per_step": ms_per_step,
+                                "achieved": build_bytes / (ms_per_step / 1e3) / 1e9,
+                                "frac": build_bytes / (ms_per_step / 1e3) / 1e9 / peak,
+                                "note": "against the driver-timed ms_per_step (launch gaps, collectives and the result copy included)"}}
 
-    # ---- CPU baseline on a bounded sample ------------------------------------------------------
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        import oracle
-        oracle.build()
-        ks = sample_for_cpu(host_np, args.cpu_sample_div)
-        leaves_s = max(N // args.cpu_sample_div, 2)
-        dt = min(time_oracle(ks, args.spec, leaves_s) for _ in range(2))
-        cpu = {"value": ks.size / dt, "unit": "keys/s", "cores": 2, "kind": "port",
-               "sample": f"every {args.cpu_sample_div}th key: {ks.size} keys, {args.spec} {leaves_s} "
-                         f"(same keys per leaf), best of 2", "host_cores": os.cpu_count(), "seconds": dt}
-        # one build cannot use more than 2 threads (two_layer.rs:161-169); a many-core host is only filled by
-        # independent builds, as in the reference's --optimize sweep: aggregate throughput of W such builds
-        workers = max(1, min((os.cpu_count() or 2) // 2, 32))
-        cpu["many_builds_at_once"] = {"value": time_oracle_concurrent(ks, args.spec, leaves_s, workers), "unit": "keys/s",
-                                      "builds": workers, "cores": 2 * workers}
-
+    cfg = workload_config(args, world)
     out = {"metric": METRIC, "value": value, "unit": "keys/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{args.spec} {N} on {n} synthetic sorted uint64 per GPU",
-                      "top_fit": "exact-serial" if args.exact_top else "parallel (coefficients within 1e-9 of the reference)",
-                      "keys_per_gpu": n, "leaves": N, "key_type": "uint64",
-                      "l2": "inputs (1.6 GB) larger than L2, no flush needed",
-                      "parallelism": "1 GPU" if world == 1 else
-                      f"range-partitioned over {world} GPUs: one global RMI with {N} leaves over {n * world} keys; "
-                      "per build: all-reduce of the top-model sums (64 B), of the leaf boundaries ((N+1)*8 B) and of the leaf "
-                      "records (N*24 B); halo keys between neighbours are fetched once per data set",
-                      "timing": "CUDA events around K synchronous builds, max over ranks",
-                      "roofline_note": "dominant kernel = the fused leaf fit + forward pass (k_leaf); on one GPU it runs as 4 launch "
-                                       "slices per build (their results cross PCIe while the next slice computes): achieved = "
-                                       "algorithmic bytes of all slices / the leaf phase's device time, traffic = ncu DRAM bytes "
-                                       "summed over the slices of one build (profiles/dominant_kernel_traffic.json)",
-                      "wall_ms_per_step": 1e3 * wall / args.steps},
+           "config": cfg,
+           "details": {
+               "generator": "torch.randint(seed 42 + rank) on the device over the rank's slice of [0, 2^63), torch.sort "
+                            "(SURVEY 8(d) names mt19937_64(42)()>>1: same distribution, other stream; the reference arm draws "
+                            "its keys with numpy MT19937(42))",
+               "top_fit": "exact-serial" if args.exact_top else "parallel (coefficients within 1e-9 of the reference)",
+               "l2": "inputs (1.6 GB per GPU) larger than L2, no flush needed",
+               "parallelism": "1 GPU" if world == 1 else
+               f"range-partitioned over {world} GPUs: ONE RMI with {N} leaves over {n * world} keys; per build, all on one stream in "
+               "one library call (rmi_shard_train): all-reduce of the top-model sums (64 B) and of the leaf boundaries ((N+1)*8 B), "
+               "all-gather of the leaf records by ownership range (N*24 B), all-gather of the per-rank statistics; the leaf tables "
+               "are copied to the host on rank 0; halo keys between neighbours are fetched once per data set",
+               "timing": "CUDA events around K synchronous builds, max over ranks",
+               "roofline_note": "dominant kernel = the fused leaf fit + forward pass (k_leaf); on one GPU it runs as 4 launch slices "
+                                "per build (their results cross PCIe while the next slice computes): achieved = algorithmic bytes of "
+                                "all slices / the leaf phase's device time; traffic = ncu DRAM bytes summed over the slices of one "
+                                "build, from the committed capture profiles/dominant_kernel_traffic.json (N = 1 only)",
+               "wall_ms_per_step": 1e3 * wall / args.steps},
            "clocks": clk,
-           "e2e": {"value": e2e_val, "unit": "keys/s", "h2d_bytes_per_step": n * key_bytes,
+           "e2e": {"value": e2e_val, "unit": "keys/s", "h2d_bytes_per_step": n * key_bytes * world,
                    "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms},
            "gpu_launches": int(launches),
-           "roofline": roofline, "cpu_baseline": cpu}
+           "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "extra_configs": extras}
+    if "parity_check" in parity:
+        out["parity_check"] = parity["parity_check"]
     emit(out)
     if dist is not None:
         dist.destroy_process_group()

@@ -60,8 +60,10 @@ enum {
                                    reference, seconds at 200 M keys.  Default is the parallel fit
                                    (tree reduction, coefficients equal within 1e-9 relative). */
   RMI_FLAG_NO_ERRORS = 4u,      /* reserved for --no-errors (main.rs:84-86); errors are still computed */
-  RMI_FLAG_LEAF_COUNTS = 8u     /* also return l1_counts (keys per leaf as the error pass counts them,
+  RMI_FLAG_LEAF_COUNTS = 8u,    /* also return l1_counts (keys per leaf as the error pass counts them,
                                    two_layer.rs:207-217); not part of TrainedRMI, used by parity checks */
+  RMI_FLAG_SHARD_ROOT_ONLY = 16u /* rmi_shard_train: only rank 0 receives the leaf tables in host memory (every rank still
+                                   holds them on its device and gets the top model and the statistics) */
 };
 
 /* A device-resident sorted key set.  Replaces src/load.rs:132-157 load_data + the mmap
@@ -215,6 +217,28 @@ int rmi_shard_set_halo(rmi_shard_build* b, uint64_t halo_keys);
 int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out);
 void rmi_shard_build_destroy(rmi_shard_build* b);
 uint32_t rmi_params_per_model(const char* leaf_model_name);
+
+/* The same build in ONE call: all phases and every collective are enqueued on the build's CUDA stream by the
+ * library itself (NCCL, bound at run time from libnccl.so.2), with no host round trip between the first kernel
+ * and the result copy except one 8 x (world+1)-byte read of the leaf-ownership ranges that overlaps the leaf kernel.
+ *     top model      all-reduce SUM of 8 doubles / MIN of 4 x i64 (rmi_shard_top_rounds)
+ *     boundaries     all-reduce MIN of (N+1) u64
+ *     leaf records   all-gather by ownership range: rank r owns the contiguous leaf range whose first key index
+ *                    S[j] lies in its slab and broadcasts exactly that range (north_star: "a single NCCL allgather
+ *                    of leaf parameters"); nothing is zero-filled or summed
+ *     statistics     each rank reduces the leaves it owns, all-gather of one 40-byte partial per rank
+ *     status         all-gather of every rank's status word, OR-ed on the host (a halo that is too small, or a
+ *                    panic on any rank, fails the call on EVERY rank with the same message)
+ * Setup per communicator: rank 0 calls rmi_shard_comm_unique_id and ships the 128 bytes to the other ranks by any
+ * means (rmi_b200/sharded.py: torch.distributed broadcast); every rank then calls rmi_shard_comm_create (collective).
+ * Setup per build object: rmi_shard_set_partition (global index of every rank's first key, world+1 entries) and, as
+ * before, rmi_shard_set_halo.  The host-driven rmi_shard_phase flow above remains (CPU tests drive it over gloo). */
+typedef struct rmi_shard_comm rmi_shard_comm;
+int rmi_shard_comm_unique_id(void* out_id128);
+int rmi_shard_comm_create(const void* id128, int world, int rank, int device, rmi_shard_comm** out);
+void rmi_shard_comm_destroy(rmi_shard_comm* c);
+int rmi_shard_set_partition(rmi_shard_build* b, const uint64_t* bases, int world, int rank);
+int rmi_shard_train(rmi_shard_build* b, rmi_shard_comm* c, uint32_t flags, rmi_result** out);
 
 /* ---- `--bounded` support: rmi_lib::cache_fix (reference rmi_lib/src/cache_fix.rs:106-150) ----------
  * The error-bounded spline over key -> first-occurrence offset whose interpolation always lands in

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "lib", "librmi_b200.so")
 
 KEY_U64, KEY_U32, KEY_F64 = 0, 1, 2
-FLAG_STATS_ONLY, FLAG_TOP_FIT_EXACT, FLAG_LEAF_COUNTS = 1, 2, 8
+FLAG_STATS_ONLY, FLAG_TOP_FIT_EXACT, FLAG_LEAF_COUNTS, FLAG_SHARD_ROOT_ONLY = 1, 2, 8, 16
 _NP_OF_KEY = {KEY_U64: np.uint64, KEY_U32: np.uint32, KEY_F64: np.float64}
 MODEL_NAMES = ["linear", "robust_linear", "linear_spline", "cubic", "loglinear", "normal", "lognormal", "radix",
                "radix_table", "bradix", "histogram"]

@@ -18,6 +18,7 @@
 
 #include "../../include/rmi_b200.h"
 #include "kernels.h"
+#include "nccl_dl.h"
 #include "../../host/cache_fix.hpp"
 #include "../../host/codegen.hpp"
 #include "../../host/optimizer.hpp"
@@ -806,6 +807,23 @@ struct rmi_shard_build {
   cudaEvent_t ev_begin[RMI_NUM_PHASES] = {};
   cudaEvent_t ev_end[RMI_NUM_PHASES] = {};
   bool ran[RMI_NUM_PHASES] = {};
+  // rmi_shard_train: the partition of the key array over the ranks and the exchange scratch
+  int world = 0, rank = -1, r_last = 0;
+  std::vector<uint64_t> bases;          // world + 1
+  u64* d_bases = nullptr;               // world + 1
+  u64* d_off = nullptr;                 // world + 1: first leaf owned by every rank
+  u64* h_off = nullptr;                 // pinned mirror
+  void* d_parts = nullptr;              // world x statistics partials
+  unsigned* d_flags_mine = nullptr;     // {status, could_not_replace != 0}
+  unsigned* d_flags_all = nullptr;      // world x 2
+  unsigned* h_flags_all = nullptr;      // pinned mirror
+  bool gather_mode = false;             // rmi_shard_train: owners broadcast their leaf ranges, nothing is zero-filled
+  cudaEvent_t ev_off = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_leaf0 = nullptr, ev_leaf1 = nullptr;
+};
+
+struct rmi_shard_comm {
+  ncclComm_t comm = nullptr;
+  int world = 0, rank = 0, device = 0;
 };
 
 namespace {
@@ -899,9 +917,11 @@ template <class T> int shard_phase_typed(rmi_shard_build* b, int phase) {
       shard_split<T>(L, keys, sh, b->top->kind, b->d_top, b->N, (const u64*)b->buf.S, b->d_aux);
       break;
     case RMI_PHASE_LEAF:
-      cudaMemsetAsync(b->buf.params, 0, sizeof(double) * b->N * ppm, b->st);
-      cudaMemsetAsync(b->buf.errors, 0, sizeof(u64) * b->N, b->st);
-      cudaMemsetAsync(b->buf.counts, 0, sizeof(u64) * b->N, b->st);
+      if (!b->gather_mode) {   // host-driven flow: the leaf records are combined by an all-reduce SUM of zero-filled arrays
+        cudaMemsetAsync(b->buf.params, 0, sizeof(double) * b->N * ppm, b->st);
+        cudaMemsetAsync(b->buf.errors, 0, sizeof(u64) * b->N, b->st);
+        cudaMemsetAsync(b->buf.counts, 0, sizeof(u64) * b->N, b->st);
+      }
       fit_leaves<T>(L, keys, sh, b->leaf->kind, b->N, (const u64*)b->buf.S, b->d_aux, (double*)b->buf.params,
                     (u64*)b->buf.errors, (u64*)b->buf.counts);
       shard_copy_status(L, b->d_aux, (unsigned*)b->buf.status);
@@ -1012,37 +1032,23 @@ int rmi_shard_set_halo(rmi_shard_build* b, uint64_t halo_keys) {
   return RMI_OK;
 }
 
-int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
-  if (!b || !out) return fail(RMI_ERR_INVALID, "rmi_shard_finish: null argument");
-  CUDA_TRY(cudaSetDevice(b->ds->device));
+}  // extern "C"
+
+// Fills the public result from the scalars / tables already copied into `box` (after the stream has been
+// synchronised).  st_all: OR of every rank's status word; cnr: some rank could not replace an empty leaf.
+static int shard_fill_result(rmi_shard_build* b, ResultBox* box, uint32_t flags, unsigned st_all, bool cnr, bool have_leaves,
+                             const uint64_t* total_device_ns, rmi_result** out) {
   const uint64_t N = b->N, n = b->info.n_global;
   const int ppm = leaf_params_per_model(b->leaf->kind);
-  const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0;
-  auto box = new ResultBox();
-  bool host_ok = box->scalars.resize(sizeof(BuildAux) + sizeof(TopModel));
+  const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0 || !have_leaves;
   const bool want_counts = !stats_only && (flags & RMI_FLAG_LEAF_COUNTS) != 0;
-  if (!stats_only) host_ok = host_ok && box->l1_params.resize((size_t)N * ppm) && box->l1_errors.resize(N);
-  if (want_counts) host_ok = host_ok && box->l1_counts.resize(N);
-  if (!host_ok) { delete box; return fail(RMI_ERR_CUDA, "pinned host allocation for the results failed"); }
   BuildAux& h_aux = *reinterpret_cast<BuildAux*>(box->scalars.data());
   TopModel& h_top = *reinterpret_cast<TopModel*>(box->scalars.data() + sizeof(BuildAux));
-  unsigned h_status = 0;
-  cudaMemcpyAsync(&h_aux, b->d_aux, sizeof(BuildAux), cudaMemcpyDeviceToHost, b->st);
-  cudaMemcpyAsync(&h_top, b->d_top, sizeof(TopModel), cudaMemcpyDeviceToHost, b->st);
-  if (!stats_only) {
-    cudaMemcpyAsync(box->l1_params.data(), b->buf.params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, b->st);
-    cudaMemcpyAsync(box->l1_errors.data(), b->buf.errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, b->st);
-    if (want_counts) cudaMemcpyAsync(box->l1_counts.data(), b->buf.counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, b->st);
-  }
-  cudaError_t e = cudaStreamSynchronize(b->st);
-  if (e == cudaSuccess) e = cudaMemcpy(&h_status, b->buf.status, sizeof(unsigned), cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess) { delete box; return fail(RMI_ERR_CUDA, std::string("rmi_shard_finish: ") + cudaGetErrorString(e)); }
-  unsigned st_all = b->host_status | h_aux.status | h_status;   // buffers.status holds the MAX over ranks
   if (st_all) {
-    delete box;
-    std::string msg = status_text(b->host_status | h_aux.status);
-    if (msg.empty()) msg = "another rank reported a failure";
+    std::string msg = status_text((b->host_status | h_aux.status | st_all) & ~ST_HALO_TOO_SMALL);
     if (st_all & ST_HALO_TOO_SMALL) msg += (msg.empty() ? "" : "; ") + std::string("a leaf reaches past the halo copied from the next rank");
+    if (msg.empty()) msg = "another rank reported a failure";
+    delete box;
     return fail(RMI_ERR_PANIC, msg);
   }
   rmi_result& R = box->pub;
@@ -1075,10 +1081,242 @@ int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
       }
     }
   }
-  R.could_not_replace = 0;   // per-rank counters are not reduced; the warning condition is local
+  if (total_device_ns) R.device_time_ns = *total_device_ns;   // whole build on the stream, collectives included
+  R.could_not_replace = cnr ? 1 : 0;   // two_layer.rs:199-203: ANY leaf, on any rank
   R.build_time_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - b->t_start).count();
   *out = &box->pub;
   return RMI_OK;
+}
+
+extern "C" {
+
+int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
+  if (!b || !out) return fail(RMI_ERR_INVALID, "rmi_shard_finish: null argument");
+  CUDA_TRY(cudaSetDevice(b->ds->device));
+  const uint64_t N = b->N;
+  const int ppm = leaf_params_per_model(b->leaf->kind);
+  const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0;
+  auto box = new ResultBox();
+  bool host_ok = box->scalars.resize(sizeof(BuildAux) + sizeof(TopModel));
+  const bool want_counts = !stats_only && (flags & RMI_FLAG_LEAF_COUNTS) != 0;
+  if (!stats_only) host_ok = host_ok && box->l1_params.resize((size_t)N * ppm) && box->l1_errors.resize(N);
+  if (want_counts) host_ok = host_ok && box->l1_counts.resize(N);
+  if (!host_ok) { delete box; return fail(RMI_ERR_CUDA, "pinned host allocation for the results failed"); }
+  BuildAux& h_aux = *reinterpret_cast<BuildAux*>(box->scalars.data());
+  TopModel& h_top = *reinterpret_cast<TopModel*>(box->scalars.data() + sizeof(BuildAux));
+  unsigned h_status = 0;
+  cudaMemcpyAsync(&h_aux, b->d_aux, sizeof(BuildAux), cudaMemcpyDeviceToHost, b->st);
+  cudaMemcpyAsync(&h_top, b->d_top, sizeof(TopModel), cudaMemcpyDeviceToHost, b->st);
+  if (!stats_only) {
+    cudaMemcpyAsync(box->l1_params.data(), b->buf.params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, b->st);
+    cudaMemcpyAsync(box->l1_errors.data(), b->buf.errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, b->st);
+    if (want_counts) cudaMemcpyAsync(box->l1_counts.data(), b->buf.counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, b->st);
+  }
+  cudaError_t e = cudaStreamSynchronize(b->st);
+  if (e == cudaSuccess) e = cudaMemcpy(&h_status, b->buf.status, sizeof(unsigned), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { delete box; return fail(RMI_ERR_CUDA, std::string("rmi_shard_finish: ") + cudaGetErrorString(e)); }
+  // host-driven flow: buffers.status holds whatever the caller combined over the ranks (sharded.py: a bitwise OR)
+  unsigned st_all = b->host_status | h_aux.status | h_status;
+  return shard_fill_result(b, box, flags, st_all, h_aux.could_not_replace != 0, true, nullptr, out);
+}
+
+// ---- the whole range-partitioned build in one call, collectives issued on the build's stream ----------
+#define NCCL_TRY(expr)                                                                                          \
+  do {                                                                                                          \
+    ncclResult_t _r = (expr);                                                                                   \
+    if (_r != ncclSuccess) return fail(RMI_ERR_CUDA, std::string(#expr) + ": " + nccl_api().GetErrorString(_r)); \
+  } while (0)
+
+int rmi_shard_comm_unique_id(void* out_id128) {
+  g_last_error.clear();
+  if (!out_id128) return fail(RMI_ERR_INVALID, "rmi_shard_comm_unique_id: null argument");
+  const NcclApi& nc = nccl_api();
+  if (!nc.ok) return fail(RMI_ERR_UNSUPPORTED, nc.error);
+  ncclUniqueId id;
+  NCCL_TRY(nc.GetUniqueId(&id));
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out_id128, &id, sizeof(id));
+  return RMI_OK;
+}
+
+int rmi_shard_comm_create(const void* id128, int world, int rank, int device, rmi_shard_comm** out) {
+  g_last_error.clear();
+  if (!id128 || !out || world < 1 || world > 63 || rank < 0 || rank >= world)
+    return fail(RMI_ERR_INVALID, "rmi_shard_comm_create: bad argument (1 <= world <= 63)");
+  const NcclApi& nc = nccl_api();
+  if (!nc.ok) return fail(RMI_ERR_UNSUPPORTED, nc.error);
+  CUDA_TRY(cudaSetDevice(device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  auto* c = new rmi_shard_comm();
+  c->world = world; c->rank = rank; c->device = device;
+  ncclResult_t r = nc.CommInitRank(&c->comm, world, id, rank);
+  if (r != ncclSuccess) { delete c; return fail(RMI_ERR_CUDA, std::string("ncclCommInitRank: ") + nc.GetErrorString(r)); }
+  *out = c;
+  return RMI_OK;
+}
+
+void rmi_shard_comm_destroy(rmi_shard_comm* c) {
+  if (!c) return;
+  if (c->comm && nccl_api().ok) nccl_api().CommDestroy(c->comm);
+  delete c;
+}
+
+int rmi_shard_set_partition(rmi_shard_build* b, const uint64_t* bases, int world, int rank) {
+  g_last_error.clear();
+  if (!b || !bases || world < 1 || world > 63 || rank < 0 || rank >= world)
+    return fail(RMI_ERR_INVALID, "rmi_shard_set_partition: bad argument (1 <= world <= 63)");
+  if (bases[rank] != b->info.base || bases[world] != b->info.n_global)
+    return fail(RMI_ERR_INVALID, "rmi_shard_set_partition: bases do not agree with this rank's rmi_shard_info");
+  CUDA_TRY(cudaSetDevice(b->ds->device));
+  b->bases.assign(bases, bases + world + 1);
+  b->world = world; b->rank = rank;
+  b->r_last = 0;
+  for (int r = 0; r < world; ++r) if (bases[r + 1] > bases[r]) b->r_last = r;
+  const size_t pb = stats_partial_bytes();
+  for (void* p : {(void*)b->d_bases, (void*)b->d_off, b->d_parts, (void*)b->d_flags_mine, (void*)b->d_flags_all}) cudaFree(p);
+  if (b->h_off) cudaFreeHost(b->h_off);
+  if (b->h_flags_all) cudaFreeHost(b->h_flags_all);
+  b->d_bases = b->d_off = nullptr; b->d_parts = nullptr; b->d_flags_mine = b->d_flags_all = nullptr; b->h_off = nullptr; b->h_flags_all = nullptr;
+  bool ok = cudaMalloc((void**)&b->d_bases, sizeof(u64) * (world + 1)) == cudaSuccess &&
+            cudaMalloc((void**)&b->d_off, sizeof(u64) * (world + 1)) == cudaSuccess &&
+            cudaMalloc(&b->d_parts, pb * world) == cudaSuccess &&
+            cudaMalloc((void**)&b->d_flags_mine, 2 * sizeof(unsigned)) == cudaSuccess &&
+            cudaMalloc((void**)&b->d_flags_all, 2 * sizeof(unsigned) * world) == cudaSuccess &&
+            cudaMallocHost((void**)&b->h_off, sizeof(u64) * (world + 1)) == cudaSuccess &&
+            cudaMallocHost((void**)&b->h_flags_all, 2 * sizeof(unsigned) * world) == cudaSuccess;
+  for (cudaEvent_t* e : {&b->ev_off, &b->ev_leaf0, &b->ev_leaf1})
+    if (!*e) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+  for (cudaEvent_t* e : {&b->ev_t0, &b->ev_t1}) if (!*e) ok = ok && cudaEventCreate(e) == cudaSuccess;
+  if (ok) ok = cudaMemcpy(b->d_bases, bases, sizeof(u64) * (world + 1), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) return fail(RMI_ERR_CUDA, "rmi_shard_set_partition: allocation failed");
+  return RMI_OK;
+}
+
+}  // extern "C"
+
+template <class T>
+static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t flags, rmi_result** out) {
+  const NcclApi& nc = nccl_api();
+  const uint64_t N = b->N;
+  const int ppm = leaf_params_per_model(b->leaf->kind);
+  const int W = b->world, rank = b->rank;
+  const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0;
+  const bool want_counts = !stats_only && (flags & RMI_FLAG_LEAF_COUNTS) != 0;
+  const bool leaves_to_host = !stats_only && (rank == 0 || (flags & RMI_FLAG_SHARD_ROOT_ONLY) == 0);
+  cudaStream_t st = b->st;
+  ncclComm_t comm = c->comm;
+  Launch L{st, b->num_sms};
+  double* sums = (double*)b->buf.sums;
+  // pinned host memory for the results first (nothing below waits for the host except the owner offsets)
+  auto box = new ResultBox();
+  bool host_ok = box->scalars.resize(sizeof(BuildAux) + sizeof(TopModel));
+  if (leaves_to_host) host_ok = host_ok && box->l1_params.resize((size_t)N * ppm) && box->l1_errors.resize(N);
+  if (leaves_to_host && want_counts) host_ok = host_ok && box->l1_counts.resize(N);
+  if (!host_ok) { delete box; return fail(RMI_ERR_CUDA, "pinned host allocation for the results failed"); }
+  b->gather_mode = true;
+  int rc = RMI_OK;
+  auto phase = [&](int ph) { if (rc == RMI_OK) rc = shard_phase_typed<T>(b, ph); };
+  auto nccl = [&](ncclResult_t r, const char* what) {
+    if (rc == RMI_OK && r != ncclSuccess) rc = fail(RMI_ERR_CUDA, std::string(what) + ": " + nc.GetErrorString(r));
+  };
+  cudaEventRecord(b->ev_t0, st);
+  // ---- top model: local part, 0-2 tiny all-reduces, closed form (identical on every rank) -----------------
+  phase(RMI_PHASE_TOP_LOCAL);
+  const int rounds = rmi_shard_top_rounds(b->top->name);
+  if (W > 1 && rc == RMI_OK) {
+    if (rounds == 1 || rounds == 2) nccl(nc.AllReduce(sums, sums, 8, ncclFloat64, ncclSum, comm, st), "ncclAllReduce(top sums)");
+    if (rounds == 3) nccl(nc.AllReduce(sums + 8, sums + 8, 4, ncclInt64, ncclMin, comm, st), "ncclAllReduce(cubic interior points)");
+  }
+  if (rounds >= 2) {
+    phase(RMI_PHASE_TOP_MID);
+    if (W > 1 && rc == RMI_OK) nccl(nc.AllReduce(sums, sums, 8, ncclFloat64, ncclSum, comm, st), "ncclAllReduce(top sums, round 2)");
+  }
+  phase(RMI_PHASE_TOP_FINISH);
+  // ---- leaf boundaries: local lower bounds -> all-reduce MIN; split; who owns which leaves -----------------
+  phase(RMI_PHASE_BOUNDS);
+  if (W > 1 && rc == RMI_OK) nccl(nc.AllReduce(b->buf.S, b->buf.S, N + 1, ncclUint64, ncclMin, comm, st), "ncclAllReduce(leaf boundaries)");
+  phase(RMI_PHASE_SPLIT);
+  if (rc == RMI_OK) {
+    shard_owner_offsets(L, (const u64*)b->buf.S, N, b->d_bases, W, b->r_last, b->d_off);
+    cudaMemcpyAsync(b->h_off, b->d_off, sizeof(u64) * (W + 1), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(b->ev_off, st);
+  }
+  // ---- leaves owned by this rank (the host learns the ownership ranges while this runs) ----------------------
+  phase(RMI_PHASE_LEAF);
+  if (rc == RMI_OK) {
+    shard_copy_flags(L, b->d_aux, b->d_flags_mine);
+    // statistics of the owned leaves (needs only local results), gathered below
+    leaf_statistics_owned(L, b->info.n_global, N, (const u64*)b->buf.errors, (const u64*)b->buf.counts, b->d_off, rank, W,
+                          (char*)b->d_parts + stats_partial_bytes() * rank, b->d_stats);
+    cudaError_t e = cudaEventSynchronize(b->ev_off);
+    if (e != cudaSuccess) rc = fail(RMI_ERR_CUDA, std::string("rmi_shard_train: ") + cudaGetErrorString(e));
+  }
+  // ---- every owner publishes its leaf range: an all-gather with per-rank counts (grouped broadcasts) ----------
+  if (rc == RMI_OK && W > 1) {
+    nccl(nc.GroupStart(), "ncclGroupStart");
+    for (int r = 0; r < W && rc == RMI_OK; ++r) {
+      const uint64_t j0 = b->h_off[r], cnt = b->h_off[r + 1] - b->h_off[r];
+      if (cnt == 0) continue;
+      double* pp = (double*)b->buf.params + j0 * ppm;
+      u64* pe = (u64*)b->buf.errors + j0;
+      nccl(nc.Broadcast(pp, pp, cnt * ppm, ncclFloat64, r, comm, st), "ncclBroadcast(leaf parameters)");
+      nccl(nc.Broadcast(pe, pe, cnt, ncclUint64, r, comm, st), "ncclBroadcast(leaf error bounds)");
+      if (want_counts) {
+        u64* pc = (u64*)b->buf.counts + j0;
+        nccl(nc.Broadcast(pc, pc, cnt, ncclUint64, r, comm, st), "ncclBroadcast(leaf key counts)");
+      }
+    }
+    nccl(nc.AllGather(b->d_flags_mine, b->d_flags_all, 2, ncclUint32, comm, st), "ncclAllGather(status)");
+    nccl(nc.AllGather((char*)b->d_parts + stats_partial_bytes() * rank, b->d_parts, stats_partial_bytes(), ncclChar, comm, st),
+         "ncclAllGather(statistics)");
+    nccl(nc.GroupEnd(), "ncclGroupEnd");
+  } else if (rc == RMI_OK) {
+    cudaMemcpyAsync(b->d_flags_all, b->d_flags_mine, 2 * sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
+  }
+  if (rc == RMI_OK) {
+    if (b->ran[RMI_PHASE_STATS] == false) { cudaEventRecord(b->ev_begin[RMI_PHASE_STATS], st); b->ran[RMI_PHASE_STATS] = true; }
+    leaf_statistics_merge(L, b->d_parts, W, b->d_aux);
+    cudaEventRecord(b->ev_end[RMI_PHASE_STATS], st);
+  }
+  cudaEventRecord(b->ev_t1, st);
+  if (rc != RMI_OK) { cudaStreamSynchronize(st); delete box; return rc; }
+  // ---- results to the host ------------------------------------------------------------------------------------
+  BuildAux& h_aux = *reinterpret_cast<BuildAux*>(box->scalars.data());
+  TopModel& h_top = *reinterpret_cast<TopModel*>(box->scalars.data() + sizeof(BuildAux));
+  cudaMemcpyAsync(&h_aux, b->d_aux, sizeof(BuildAux), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(&h_top, b->d_top, sizeof(TopModel), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(b->h_flags_all, b->d_flags_all, 2 * sizeof(unsigned) * W, cudaMemcpyDeviceToHost, st);
+  if (leaves_to_host) {
+    cudaMemcpyAsync(box->l1_params.data(), b->buf.params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(box->l1_errors.data(), b->buf.errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
+    if (want_counts) cudaMemcpyAsync(box->l1_counts.data(), b->buf.counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { delete box; return fail(RMI_ERR_CUDA, std::string("rmi_shard_train: ") + cudaGetErrorString(e)); }
+  unsigned st_all = b->host_status;
+  bool cnr = false;
+  for (int r = 0; r < W; ++r) { st_all |= b->h_flags_all[2 * r]; cnr = cnr || b->h_flags_all[2 * r + 1] != 0; }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, b->ev_t0, b->ev_t1);
+  const uint64_t total_ns = (uint64_t)((double)ms * 1e6);
+  return shard_fill_result(b, box, flags, st_all, cnr, leaves_to_host, &total_ns, out);
+}
+
+extern "C" {
+
+int rmi_shard_train(rmi_shard_build* b, rmi_shard_comm* c, uint32_t flags, rmi_result** out) {
+  g_last_error.clear();
+  if (!b || !c || !out) return fail(RMI_ERR_INVALID, "rmi_shard_train: null argument");
+  if (b->world != c->world || b->rank != c->rank || b->world < 1)
+    return fail(RMI_ERR_INVALID, "rmi_shard_train: call rmi_shard_set_partition with the communicator's world size and rank first");
+  if (!nccl_api().ok) return fail(RMI_ERR_UNSUPPORTED, nccl_api().error);
+  CUDA_TRY(cudaSetDevice(b->ds->device));
+  switch (b->ds->key_type) {
+    case RMI_KEY_U64: return shard_train_typed<u64>(b, c, flags, out);
+    case RMI_KEY_U32: return shard_train_typed<u32>(b, c, flags, out);
+    default: return shard_train_typed<double>(b, c, flags, out);
+  }
 }
 
 void rmi_shard_build_destroy(rmi_shard_build* b) {
@@ -1089,6 +1327,10 @@ void rmi_shard_build_destroy(rmi_shard_build* b) {
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->side) cudaStreamDestroy(b->side);
   cudaFree(b->d_long);
+  cudaFree(b->d_bases); cudaFree(b->d_off); cudaFree(b->d_parts); cudaFree(b->d_flags_mine); cudaFree(b->d_flags_all);
+  if (b->h_off) cudaFreeHost(b->h_off);
+  if (b->h_flags_all) cudaFreeHost(b->h_flags_all);
+  for (cudaEvent_t e : {b->ev_off, b->ev_t0, b->ev_t1, b->ev_leaf0, b->ev_leaf1}) if (e) cudaEventDestroy(e);
   delete b;
 }
 

@@ -144,6 +144,17 @@ void leaf_statistics(const Launch& L, u64 n, u64 num_leaves, const u64* d_errors
                      BuildAux* d_aux, void* scratch);
 size_t stats_scratch_bytes(u64 num_leaves);
 
+// ---- cross-rank pieces of a range-partitioned build (kernels_leaf.cu) --------------------------
+// d_off[r] = first leaf owned by rank r, d_off[world] = N (d_bases: global index of every rank's first key,
+// world + 1 entries; r_last: last rank that holds keys).  One tiny kernel, no host involvement.
+void shard_owner_offsets(const Launch& L, const u64* d_S, u64 N, const u64* d_bases, int world, int r_last, u64* d_off);
+// Summary statistics of the leaves this rank owns, as one partial record (stats_partial_bytes()) at d_part_out;
+// after an all-gather of the partials, leaf_statistics_merge() finishes them into d_aux on every rank.
+size_t stats_partial_bytes();
+void leaf_statistics_owned(const Launch& L, u64 n, u64 N, const u64* d_errors, const u64* d_counts, const u64* d_off, int rank,
+                           int world, void* d_part_out, void* scratch);
+void leaf_statistics_merge(const Launch& L, const void* d_parts, int world, BuildAux* d_aux);
+
 // ---- range-partitioned build phases (kernels_shard.cu) ---------------------------------------
 size_t shard_scratch_bytes();
 template <class T>
@@ -162,5 +173,7 @@ template <class T>
 void shard_split(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N,
                  const u64* d_S, BuildAux* d_aux);
 void shard_copy_status(const Launch& L, const BuildAux* d_aux, unsigned* d_out);
+// {status word, could_not_replace != 0} of this rank, for the cross-rank gather (two_layer.rs:199-203 warns if ANY leaf could not be replaced)
+void shard_copy_flags(const Launch& L, const BuildAux* d_aux, unsigned* d_out2);
 
 }  // namespace rmi

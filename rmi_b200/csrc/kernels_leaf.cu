@@ -48,6 +48,9 @@ constexpr int BOUNDS_THREADS = 256;
 #define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS, ((LEAF == M_LINEAR && !DUPS) ? 768 : 640) / RMI_LEAF_THREADS)
 #endif
 constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
+#ifndef RMI_FWD_DEPTH
+#define RMI_FWD_DEPTH 8   // 32-key loads in flight per warp in the forward pass
+#endif
 #ifndef RMI_RCP_TABLE
 #define RMI_RCP_TABLE 512
 #endif
@@ -965,7 +968,7 @@ __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const S
   // from L2 / HBM, the latency is that of a miss), and a step that straddles a leaf boundary is evaluated
   // once per leaf it touches.  Per-leaf maxima are reduced when the stream leaves the leaf.
   constexpr int PPM = leaf_params_per_model(LEAF);
-  constexpr int FWD_DEPTH = 8;
+  constexpr int FWD_DEPTH = RMI_FWD_DEPTH;
   constexpr int REC = 16 + ((PPM * 8 + 15) / 16) * 16;   // {lo, hi} + parameters, 16-byte aligned
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -1007,6 +1010,7 @@ __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const S
     I w_err = 0, w_run = 0;
     I carry_F = (I)(seg_lo + baseI);
     T carry_k = T();
+    const I last_readable = (I)(sh.n_avail - 1);
     auto leave_leaf = [&]() {   // the stream has passed leaf q: hand its maxima to the owner, move to the next leaf
       const I r_err = warp_max<I>(w_err);
       I r_run = 0;
@@ -1021,24 +1025,28 @@ __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const S
         for (int t = 0; t < PPM; ++t) cf[t] = reinterpret_cast<const double*>(wsm + q * REC + 16)[t];
       }
     };
-    T kk[FWD_DEPTH];
+    // FWD_DEPTH + 1 register slots: the step that consumes slot u refills the slot the PREVIOUS step consumed, so a
+    // load never targets the register it is just reading (with FWD_DEPTH slots the compiler loads into a temporary
+    // and copies it — and the copy waits for the load: measured, it serialised every step on the load latency)
+    constexpr int FWD_SLOTS = FWD_DEPTH + 1;
+    T kk[FWD_SLOTS];
 #pragma unroll
     for (int u = 0; u < FWD_DEPTH; ++u) {
       const I iu = seg_lo + (I)(u * 32 + lane);
-      kk[u] = (iu < seg_hi && iu >= seg_lo) ? __ldcs(keys + iu) : T();     // streaming: the line's last use
+      kk[u] = __ldcs(keys + (iu < last_readable ? iu : last_readable));     // streaming: the line's last use
     }
+    kk[FWD_DEPTH] = T();
     I pos = seg_lo;
     // look-ahead loads are unconditional: the index is clamped to the last readable key instead of predicated
     // (a predicated load costs a branch per step; a clamped one past the segment's end is simply not used)
     I inext = (I)(seg_lo + (I)(FWD_DEPTH * 32 + lane));
-    const I last_readable = (I)(sh.n_avail - 1);
     I Fi = (I)(seg_lo + (I)lane + baseI);                 // global index of this lane's key in the current step
     bool done = false;
     while (!done) {
 #pragma unroll
-      for (int u = 0; u < FWD_DEPTH; ++u) {
+      for (int u = 0; u < FWD_SLOTS; ++u) {
         const T k = kk[u];
-        kk[u] = __ldcs(keys + (inext < last_readable ? inext : last_readable));
+        kk[(u + FWD_DEPTH) % FWD_SLOTS] = __ldcs(keys + (inext < last_readable ? inext : last_readable));
         inext += 32;
         const double x = Key<T>::as_float(k);
         if (!DUPS && (I)(hi_q - pos) >= (I)32) {
@@ -1190,8 +1198,6 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_rcp = reinterpret_cast<double*>(smem_raw);
   unsigned char* wsm = smem_raw + (size_t)RCP_TABLE * sizeof(double) + (size_t)(threadIdx.x >> 5) * WARP_STREAM_BYTES;
-  for (int c = threadIdx.x; c < RCP_TABLE; c += blockDim.x) s_rcp[c] = c ? __drcp_rn((double)c) : 0.0;
-  __syncthreads();
   // Leaf groups are handed out from both ends of the leaf range: with a regression top model
   // the first and the last leaf collect every key the model places below 0 / above N-1 and are
   // by far the longest serial chains, so they must start first, not last.
@@ -1223,6 +1229,11 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   // owner of leaf j: the rank whose slab holds index S[j]; S[j] == n (trailing empty leaves)
   // belongs to the last rank
   bool live = j < N && ((g_lo >= sh.base && g_lo < sh.base + sh.n_local) || (g_lo >= n && sh.is_last));
+  // a block none of whose leaves belongs to this rank (range-partitioned builds launch the whole leaf range
+  // on every rank) leaves before the reciprocal table is built
+  if (!__syncthreads_or(live ? 1 : 0)) { if (bad) set_status(aux, bad); return; }
+  for (int c = threadIdx.x; c < RCP_TABLE; c += blockDim.x) s_rcp[c] = c ? __drcp_rn((double)c) : 0.0;
+  __syncthreads();
 #ifdef RMI_PIPELINED_BOUNDS
   if (long_mode == 0 && long_active && live && (g_hi - g_lo) > LONG_LEAF_KEYS) {   // built by the long-leaf kernel IF it is listed
     bool listed = false;
@@ -1304,7 +1315,35 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   // row ring a second time.  Owners park their leaf's range and parameters in the warp's shared
   // memory (the ring is idle now); results return to the owner lane.
   I max_err = 0, run_max = 0;
+#ifdef RMI_LANE_SERIAL_FORWARD
+  // (experiment variant: round 1's forward pass — every lane walks its own leaf through the copy ring a second time)
+  {
+    const u64 pol_fwd = l2_policy_of((mode_word >> 6) & 3);
+    T pk = (live && g_lo == 0 && g_hi > 0) ? keys[0] : prev_key;
+    I F = (I)g_lo, run = 0;
+    if (DUPS) {
+      stream_pass<T, I>(keys, pol_fwd, wsm, r.lo, r.hi, [&](T k, I i) {
+        if (k != pk) { run_max = run > run_max ? run : run_max; run = 0; F = (I)(i + baseI); }
+        run += 1;
+        pk = k;
+        I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
+        I e = pred > F ? pred - F : F - pred;
+        max_err = e > max_err ? e : max_err;
+      });
+      if (g_hi < n && run > run_max) run_max = run;
+    } else {
+      stream_pass<T, I>(keys, pol_fwd, wsm, r.lo, r.hi, [&](T k, I i) {
+        I Fi = (I)(i + baseI);
+        I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
+        I e = pred > Fi ? pred - Fi : Fi - pred;
+        max_err = e > max_err ? e : max_err;
+      });
+      (void)pk; (void)F; (void)run;
+    }
+  }
+#else
   coop_forward<T, I, LEAF, DUPS, NANCHECK>(keys, sh, wsm, live && r.hi > r.lo, r.lo, r.hi, f, max_err, run_max);
+#endif
   if (!DUPS) {
     // no two keys of the data set are equal: every run has length 1 (and the data set's final run
     // is never recorded, lower_bound_correction.rs:108-119)
@@ -1425,6 +1464,110 @@ k_stats_finish(const StatsPartial* __restrict__ parts, int nblocks, BuildAux* au
   if (threadIdx.x == 0) {
     aux->max_error = me; aux->max_error_idx = mi; aux->sum_n_err = r_ne; aux->sum_l2 = r_l2; aux->sum_log2 = r_lg;
   }
+}
+
+// Range-partitioned builds: every rank reduces the leaves it OWNS (leaf range [off[rank], off[rank+1]),
+// read from device memory so that the host need not know it) to one StatsPartial; the partials of all
+// ranks are gathered and merged by k_stats_finish.  Same tree shape on every rank and in every run.
+__global__ void __launch_bounds__(STATS_THREADS)
+k_stats_partial_range(u64 n, const u64* __restrict__ off, int rank, const u64* __restrict__ errors,
+                      const u64* __restrict__ counts, StatsPartial* __restrict__ out) {
+  __shared__ double smd[32];
+  __shared__ u64 smu[32];
+  __shared__ u64 sme[32], smi[32];
+  const u64 j0 = off[rank], j1 = off[rank + 1];
+  double nf = __ull2double_rn(n);
+  u64 me = 0, mi = 0, sne = 0;
+  double l2 = 0.0, lg = 0.0;
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 j = j0 + (u64)blockIdx.x * blockDim.x + threadIdx.x; j < j1; j += stride) {
+    u64 e = errors[j], c = counts[j];
+    stats_merge(me, mi, e, j);
+    u64 ne = c * e;
+    sne += ne;
+    double v = __ull2double_rn(ne);
+    l2 += __ddiv_rn(__dmul_rn(v, v), nf);
+    lg += __dmul_rn(__ull2double_rn(c), log2(__ull2double_rn(2ull * e + 2ull)));
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    u64 oe = __shfl_down_sync(0xffffffffu, me, o), oi = __shfl_down_sync(0xffffffffu, mi, o);
+    stats_merge(me, mi, oe, oi);
+  }
+  if (lane == 0) { sme[w] = me; smi[w] = mi; }
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    me = lane < nw ? sme[lane] : 0; mi = lane < nw ? smi[lane] : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      u64 oe = __shfl_down_sync(0xffffffffu, me, o), oi = __shfl_down_sync(0xffffffffu, mi, o);
+      stats_merge(me, mi, oe, oi);
+    }
+  }
+  u64 r_ne = block_sum_u64(sne, smu);
+  double r_l2 = block_sum(l2, smd), r_lg = block_sum(lg, smd);
+  if (threadIdx.x == 0) {
+    StatsPartial p;
+    p.max_err = me; p.max_idx = mi; p.sum_ne = r_ne; p.l2 = r_l2; p.lg = r_lg;
+    out[blockIdx.x] = p;
+  }
+}
+// merges `nblocks` partials into ONE partial (*out) instead of into BuildAux
+__global__ void __launch_bounds__(STATS_THREADS)
+k_stats_merge(const StatsPartial* __restrict__ parts, int nblocks, StatsPartial* __restrict__ out) {
+  __shared__ double smd[32];
+  __shared__ u64 smu[32];
+  __shared__ u64 sme[32], smi[32];
+  u64 me = 0, mi = 0, sne = 0;
+  double l2 = 0.0, lg = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    stats_merge(me, mi, parts[b].max_err, parts[b].max_idx);
+    sne += parts[b].sum_ne;
+    l2 += parts[b].l2;
+    lg += parts[b].lg;
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 16; o > 0; o >>= 1) {
+    u64 oe = __shfl_down_sync(0xffffffffu, me, o), oi = __shfl_down_sync(0xffffffffu, mi, o);
+    stats_merge(me, mi, oe, oi);
+  }
+  if (lane == 0) { sme[w] = me; smi[w] = mi; }
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    me = lane < nw ? sme[lane] : 0; mi = lane < nw ? smi[lane] : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      u64 oe = __shfl_down_sync(0xffffffffu, me, o), oi = __shfl_down_sync(0xffffffffu, mi, o);
+      stats_merge(me, mi, oe, oi);
+    }
+  }
+  u64 r_ne = block_sum_u64(sne, smu);
+  double r_l2 = block_sum(l2, smd), r_lg = block_sum(lg, smd);
+  if (threadIdx.x == 0) {
+    StatsPartial p;
+    p.max_err = me; p.max_idx = mi; p.sum_ne = r_ne; p.l2 = r_l2; p.lg = r_lg;
+    *out = p;
+  }
+}
+
+// off[r] = first leaf owned by rank r (the rule k_leaf applies: the rank whose slab holds index S[j];
+// trailing leaves with S[j] == n belong to the last rank that holds keys), off[world] = N.
+__global__ void k_owner_offsets(const u64* __restrict__ S, u64 N, const u64* __restrict__ bases, int world, int r_last,
+                                u64* __restrict__ off) {
+  int r = threadIdx.x;
+  if (r > world) return;
+  u64 v;
+  if (r == world || r > r_last) v = N;
+  else {
+    const u64 b = bases[r];
+    u64 lo = 0, hi = N;               // first j in [0, N) with S[j] >= b
+    while (lo < hi) {
+      u64 mid = lo + ((hi - lo) >> 1);
+      if (S[mid] >= b) hi = mid; else lo = mid + 1;
+    }
+    v = lo;
+  }
+  off[r] = v;
 }
 
 int grid_cap(u64 n, int threads, int cap) {
@@ -1727,6 +1870,28 @@ void leaf_statistics(const Launch& L, u64 n, u64 N, const u64* d_errors, const u
   k_stats_partial<<<g, STATS_THREADS, 0, L.stream>>>(n, N, d_errors, d_counts, (StatsPartial*)scratch);
   count_launch();
   k_stats_finish<<<1, STATS_THREADS, 0, L.stream>>>((const StatsPartial*)scratch, g, d_aux);
+  count_launch();
+}
+
+size_t stats_partial_bytes() { return sizeof(StatsPartial); }
+
+void shard_owner_offsets(const Launch& L, const u64* d_S, u64 N, const u64* d_bases, int world, int r_last, u64* d_off) {
+  k_owner_offsets<<<1, 64, 0, L.stream>>>(d_S, N, d_bases, world, r_last, d_off);   // world < 64 (checked by the caller)
+  count_launch();
+}
+
+void leaf_statistics_owned(const Launch& L, u64 n, u64 N, const u64* d_errors, const u64* d_counts, const u64* d_off, int rank,
+                           int world, void* d_part_out, void* scratch) {
+  // the owned range is about N / world leaves; the grid is sized for that (a few idle blocks do no harm)
+  int g = grid_cap((N + (u64)world - 1) / (u64)world, STATS_THREADS, STATS_MAX_BLOCKS);
+  k_stats_partial_range<<<g, STATS_THREADS, 0, L.stream>>>(n, d_off, rank, d_errors, d_counts, (StatsPartial*)scratch);
+  count_launch();
+  k_stats_merge<<<1, STATS_THREADS, 0, L.stream>>>((const StatsPartial*)scratch, g, (StatsPartial*)d_part_out);
+  count_launch();
+}
+
+void leaf_statistics_merge(const Launch& L, const void* d_parts, int world, BuildAux* d_aux) {
+  k_stats_finish<<<1, STATS_THREADS, 0, L.stream>>>((const StatsPartial*)d_parts, world, d_aux);
   count_launch();
 }
 

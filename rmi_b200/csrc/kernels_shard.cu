@@ -462,6 +462,10 @@ __global__ void k_copy_status(const BuildAux* __restrict__ aux, unsigned* __rest
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = aux->status;
 }
 
+__global__ void k_copy_flags(const BuildAux* __restrict__ aux, unsigned* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = aux->status; out[1] = aux->could_not_replace ? 1u : 0u; }
+}
+
 int sh_grid(u64 n, int num_sms) {
   u64 blocks = (n + SH_THREADS - 1) / SH_THREADS;
   u64 cap = (u64)num_sms * 8;
@@ -604,6 +608,11 @@ void shard_split(const Launch& L, const T* keys, const Shard<T>& sh, int kind, c
 
 void shard_copy_status(const Launch& L, const BuildAux* d_aux, unsigned* d_out) {
   k_copy_status<<<1, 32, 0, L.stream>>>(d_aux, d_out);
+  count_launch();
+}
+
+void shard_copy_flags(const Launch& L, const BuildAux* d_aux, unsigned* d_out2) {
+  k_copy_flags<<<1, 32, 0, L.stream>>>(d_aux, d_out2);
   count_launch();
 }
 

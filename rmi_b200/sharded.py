@@ -228,6 +228,11 @@ class CudaShardEngine:
         L.rmi_shard_set_halo.argtypes = [C.c_void_p, C.c_uint64]
         L.rmi_shard_finish.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(api._Result))]
         L.rmi_shard_build_destroy.argtypes = [C.c_void_p]
+        L.rmi_shard_comm_unique_id.argtypes = [C.c_void_p]
+        L.rmi_shard_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rmi_shard_comm_destroy.argtypes = [C.c_void_p]
+        L.rmi_shard_set_partition.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int]
+        L.rmi_shard_train.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(api._Result))]
         self.device = data.buf.device
         self.ds = api.RMITrainingData.from_device(data.buf.data_ptr(), data.n_local, data.key_type,
                                                   self.device.index or 0, keep_alive=data.buf)
@@ -269,6 +274,16 @@ class CudaShardEngine:
     def local_view(self, offset: int, count: int) -> torch.Tensor:
         return self.data.buf[offset: offset + count]
 
+    def set_partition(self, bases: list[int], world: int, rank: int):
+        arr = (C.c_uint64 * (world + 1))(*bases)
+        api._check(self.lib.rmi_shard_set_partition(self._build, arr, world, rank))
+
+    def train(self, comm, flags: int = 0):
+        """The whole build in one library call: phases and NCCL collectives on the build's stream (rmi_shard_train)."""
+        res = C.POINTER(api._Result)()
+        api._check(self.lib.rmi_shard_train(self._build, comm, int(flags), C.byref(res)))
+        return api.result_from_pointer(res, self._spec)
+
     def finish(self, flags: int = 0):
         res = C.POINTER(api._Result)()
         api._check(self.lib.rmi_shard_finish(self._build, int(flags), C.byref(res)))
@@ -292,8 +307,51 @@ def _world(group):
     return 0, 1
 
 
-def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=None, engine=None, counts: bool = True):
-    """rmi_lib::train on a range-partitioned key array; returns the full TrainedRMI on every rank."""
+_native_comms = {}
+
+
+def native_comm(group, device: torch.device, single_rank_ok: bool = False):
+    """The library's own NCCL communicator for `group` (rmi_shard_comm_*): rank 0 draws the unique id, the
+    128 bytes travel through torch.distributed, every rank joins.  Cached per (group, device).  Returns None
+    when the group does not run over NCCL (gloo tests; a single rank unless single_rank_ok — a one-rank
+    communicator is how the one-call path is exercised on a one-GPU box) or NCCL cannot be loaded."""
+    rank, world = _world(group)
+    if device.type != "cuda" or (world > 1 and dist.get_backend(group) != "nccl") or (world <= 1 and not single_rank_ok):
+        return None
+    key = (id(group) if group is not None else 0, device.index or 0, world)
+    if key in _native_comms:
+        return _native_comms[key]
+    lib = api.load_library()
+    lib.rmi_shard_comm_unique_id.argtypes = [C.c_void_p]
+    lib.rmi_shard_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    buf = (C.c_uint8 * 128)()
+    ok = 1
+    if rank == 0:
+        ok = 1 if lib.rmi_shard_comm_unique_id(buf) == 0 else 0
+    if world > 1:
+        t = torch.tensor(list(buf) + [ok], dtype=torch.uint8, device=device)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        vals = t.cpu().tolist()
+    else:
+        vals = list(buf) + [ok]
+    comm = None
+    if vals[128] == 1:
+        ident = (C.c_uint8 * 128)(*vals[:128])
+        h = C.c_void_p()
+        api._check(lib.rmi_shard_comm_create(ident, world, rank, device.index or 0, C.byref(h)))
+        comm = h
+    _native_comms[key] = comm
+    return comm
+
+
+def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=None, engine=None, counts: bool = True,
+                  native: bool | None = None):
+    """rmi_lib::train on a range-partitioned key array; returns the full TrainedRMI on every rank.
+
+    native=None (default): with the CUDA engine over an NCCL group the whole build is ONE library call
+    (rmi_shard_train: kernels and collectives on one stream, leaf records exchanged as an all-gather by
+    ownership range); otherwise — gloo, the numpy engine of the CPU tests, native=False — the phases are
+    sequenced here and the collectives go through torch.distributed."""
     eng = engine if engine is not None else data.engine
     group = group if group is not None else getattr(data, "group", None)
     rank, world = _world(group)
@@ -336,6 +394,26 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
         data._bufs = bufs
     eng.begin(info, model_spec, N, bufs)
 
+    comm = None
+    if native is not False and isinstance(eng, CudaShardEngine):
+        comm = native_comm(group, dev, single_rank_ok=native is True)
+        if native is True and comm is None:
+            raise api.RMIError("native=True needs an NCCL process group (or a single rank) and a loadable libnccl.so.2")
+    if comm is not None:
+        # halo keys are fetched once per data set (see step 4 below), then the whole build is one call
+        if getattr(data, "_halo_have", None) is None:
+            cap = _min_halo_capacity(data, group, world, dev)
+            moves = plan_halo(bases, [bases[g + 1] + cap - 1 for g in range(world)], n_global)
+            data._halo_have = _exchange_halo(eng, moves, rank, group, dev)
+        eng.set_halo(data._halo_have or 0)
+        eng.set_partition(bases, world, rank)
+        try:
+            return eng.train(comm, int(flags) | (api.FLAG_LEAF_COUNTS if counts else 0))
+        except api.RMIPanic as e:
+            if "halo" not in str(e):
+                raise
+        return _retry_with_larger_halo(data, bufs, bases, n_global, N, model_spec, num_leaves, flags, group, world, dev, counts, native)
+
     # 2. top model: local part -> tiny all-reduce(s) -> closed form (identical on every rank)
     def top_collective(kind):
         if world <= 1:
@@ -372,14 +450,25 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
     if world > 1:
         rec = bufs["records"]
         dist.all_reduce(rec if counts else rec[: N * (ppm + 1)], op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(bufs["status"], op=dist.ReduceOp.MAX, group=group)
+        # the status word is a BIT MASK (kernels.h StatusBit): combine by OR, not MAX, so that every rank sees every
+        # rank's bits and all of them take the same decision below (retry with a larger halo / raise)
+        st_all = [torch.empty_like(bufs["status"]) for _ in range(world)]
+        dist.all_gather(st_all, bufs["status"], group=group)
+        acc = st_all[0].clone()
+        for t in st_all[1:]:
+            acc |= t
+        bufs["status"].copy_(acc)
     eng.phase(PHASE_STATS)
     try:
         return eng.finish(int(flags) | (api.FLAG_LEAF_COUNTS if counts else 0))
     except api.RMIPanic as e:
         if world <= 1 or "halo" not in str(e):
             raise
-    # A leaf reaches past the prefetched halo (heavy skew).  The status word is the MAX over ranks, so
+    return _retry_with_larger_halo(data, bufs, bases, n_global, N, model_spec, num_leaves, flags, group, world, dev, counts, native)
+
+
+def _retry_with_larger_halo(data, bufs, bases, n_global, N, model_spec, num_leaves, flags, group, world, dev, counts, native):
+    # A leaf reaches past the prefetched halo (heavy skew).  The status word is the OR over ranks, so
     # every rank arrives here together: size the halo from the global boundaries S and build again.
     S = bufs["S"]
     cuts = torch.tensor(bases[1:], dtype=torch.int64, device=dev)
@@ -392,7 +481,7 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
     if most <= _min_halo_capacity(data, group, world, dev) or not hasattr(data, "grow_halo"):
         raise api.RMIError(f"a leaf reaches further into the next rank than the halo capacity ({most} keys needed)")
     data.grow_halo(int(most * 1.25) + 1024)
-    return train_sharded(data, model_spec, num_leaves, flags, group, counts=counts)
+    return train_sharded(data, model_spec, num_leaves, flags, group, counts=counts, native=native)
 
 
 def _exchange_halo(eng, moves, rank, group, dev) -> int:

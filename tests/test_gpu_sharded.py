@@ -68,6 +68,15 @@ def _worker(rank, world, port, kind, n, spec, N, backend, q):
         g2 = sharded.train_sharded(data, spec, N)
         assert np.array_equal(parity.bits(g2.l1_params), parity.bits(g.l1_params))
         assert np.array_equal(g2.last_layer_max_l1s, g.last_layer_max_l1s)
+        if backend == "nccl":
+            # over NCCL the default is the one-call path (rmi_shard_train: collectives issued by the library, leaf
+            # records all-gathered by ownership range); the host-sequenced path must give the same bits
+            g3 = sharded.train_sharded(data, spec, N, native=False)
+            assert np.array_equal(parity.bits(g3.l0_fparams), parity.bits(g.l0_fparams))
+            assert np.array_equal(parity.bits(g3.l1_params), parity.bits(g.l1_params))
+            assert np.array_equal(g3.last_layer_max_l1s, g.last_layer_max_l1s)
+            assert np.array_equal(g3.l1_counts, g.l1_counts)
+            assert g3.model_max_error == g.model_max_error and g3.model_avg_error == g.model_avg_error
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         import traceback
@@ -103,6 +112,35 @@ def test_sharded_cuda_build_equals_oracle(oracle, world, kind, spec, N):
         p.join(timeout=60)
     bad = [r for r in results if r[1] != "ok"]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("spec,N", [("linear,linear", 4096), ("radix,linear", 2048), ("cubic,linear", 1000),
+                                    ("linear_spline,cubic", 512), ("normal,linear", 256)])
+def test_one_call_path_single_rank(oracle, spec, N):
+    """rmi_shard_train (every phase and collective issued by the library on one stream) with a one-rank NCCL
+    communicator: ownership offsets, owned-range statistics, status gather and result marshalling on a one-GPU box.
+    Must equal the host-sequenced phases bit for bit, and the oracle under the usual rules."""
+    import rmi_b200
+    from rmi_b200 import sharded
+    keys = datasets.with_duplicates(datasets.uniform_u64(250_000, seed=35)) if "cubic" in spec else datasets.uniform_u64(250_000, seed=35)
+    dev = torch.device("cuda", 0)
+    local = torch.from_numpy(keys.view(np.int64).copy()).to(dev)
+    data = sharded.ShardedTrainingData(local, key_type=rmi_b200.KEY_U64, halo_capacity=16)
+    g = sharded.train_sharded(data, spec, N, native=True)
+    h = sharded.train_sharded(data, spec, N, native=False)
+    assert np.array_equal(parity.bits(g.l0_fparams), parity.bits(h.l0_fparams))
+    assert np.array_equal(parity.bits(g.l1_params), parity.bits(h.l1_params))
+    assert np.array_equal(g.last_layer_max_l1s, h.last_layer_max_l1s)
+    assert np.array_equal(g.l1_counts, h.l1_counts)
+    assert (g.model_max_error, g.model_max_error_idx, g.model_avg_error) == (h.model_max_error, h.model_max_error_idx, h.model_avg_error)
+    top = spec.split(",")[0]
+    if top in ("linear", "cubic", "normal"):
+        o = oracle.train(keys, spec, N, l0_override=g.l0_fparams)
+    else:
+        o = oracle.train(keys, spec, N)
+        if g.l0_model == "linear_spline" or o.l0.kind == "linear_spline":
+            g.l0_model = o.l0.kind
+    parity.assert_same_rmi(g, o)
 
 
 def test_sharded_single_rank_equals_plain_train(oracle):
