@@ -254,12 +254,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gen_uniform(count, seed, lo_frac, hi_frac, dtype=torch.int64):
-        """sorted uniform keys over the slice [lo_frac, hi_frac) of the key space, on the device"""
+    def gen_uniform(count, seed, lo_num, hi_num, den, dtype=torch.int64):
+        """sorted uniform keys over the slice [lo_num/den, hi_num/den) of the key space, on the device"""
         g = torch.Generator(device=dev)
         g.manual_seed(seed)
         top = (1 << 63) - 1 if dtype == torch.int64 else (1 << 31) - 1
-        lo, hi = int(top * lo_frac), int(top * hi_frac)
+        lo, hi = top * lo_num // den, top * hi_num // den            # integer arithmetic: 2^63 - 1 is not a double
         k = torch.randint(lo, max(hi, lo + 1), (count,), dtype=dtype, device=dev, generator=g)
         k, _ = torch.sort(k)
         return k
@@ -297,7 +297,7 @@ def main():
 
     # ---- synthetic workload: sorted uniform uint64 keys; rank r draws from the r-th slice of the key space so
     # that the concatenation over ranks is globally sorted ------------------------------------------------------------
-    k = gen_uniform(n, 42 + rank, rank / world, (rank + 1) / world)
+    k = gen_uniform(n, 42 + rank, rank, rank + 1, world)
     torch.cuda.synchronize()
     ppm = 2
     build, keep = make_builder(k, n, rmi_b200.KEY_U64, args.spec, N, top_flag)
@@ -421,7 +421,7 @@ def main():
         extra("cubic,linear 262144", k, n, rmi_b200.KEY_U64, "cubic,linear", 262144, 8)
         if world == 1:
             # configs[3]: radix,linear 524288 on 200M uint32
-            k32 = gen_uniform(n, 7, 0.0, 1.0, dtype=torch.int32)
+            k32 = gen_uniform(n, 7, 0, 1, 1, dtype=torch.int32)
             extra("radix,linear 524288 (uint32)", k32, n, rmi_b200.KEY_U32, "radix,linear", 524288, 4)
             del k32
             # the headline build on less friendly data: lognormal skew, 5% duplicated keys
@@ -448,7 +448,7 @@ def main():
         else:
             # strong scaling: BASELINE's 200M keys IN TOTAL over the N GPUs
             ns = n // world
-            ks = gen_uniform(ns, 4242 + rank, rank / world, (rank + 1) / world)
+            ks = gen_uniform(ns, 4242 + rank, rank, rank + 1, world)
             extra(f"strong scaling: {args.spec} {N} on {ns * world} keys in total", ks, ns, rmi_b200.KEY_U64, args.spec, N, 8,
                   steps=args.steps)
             del ks

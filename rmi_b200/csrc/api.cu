@@ -529,6 +529,131 @@ struct Arena {   // stream-ordered scratch; everything is released when the call
   ~Arena() { for (void* p : ptrs) cudaFreeAsync(p, st); }
 };
 
+// ---- RMI_FLAG_TOP_FIT_EXACT for linear / robust_linear / normal tops: the reference's serial recurrence on a HOST core ----
+// slr() (linear.rs:12-59) is a loop-carried chain — sub, div, add per item on mean_x — that no parallel schedule can
+// reproduce bit for bit.  A CPU core runs that chain at ~20 cycles per item (the division's latency); one GPU warp
+// needs ~300.  So the exact mode streams the keys back to pinned host memory (64 MiB pieces on a side stream, the copy
+// of piece c+1 behind the arithmetic on piece c: the 1.6 GB of a 200M-key set cross PCIe in 30 ms, the chain takes
+// ~1.3 s) and runs the recurrence there, exactly as the reference does; the coefficients are then injected like
+// rmi_train_with_top's.  Returns StatusBits (0 = ok).
+template <class T> inline double host_as_float(T k) { return (double)k; }
+inline uint64_t host_scale(uint64_t off, double sf, bool use_sf) { return use_sf ? (uint64_t)((double)off * sf) : off; }
+
+template <class T>
+unsigned host_exact_top(const rmi_dataset* ds, int kind, uint64_t N, double* out_f) {
+  const uint64_t n = ds->n;
+  const T* d_keys = (const T*)ds->d_keys;
+  const double sf = (double)N / (double)n;
+  const bool use_sf = std::fabs(sf - 1.0) > DBL_EPSILON;
+  uint64_t i0 = 0, i1 = n;
+  bool repeat = true;
+  if (kind == M_ROBUST_LINEAR) {   // linear.rs:239-256: skip(bnd).take(len - 2 * bnd), never drained
+    uint64_t bnd = (uint64_t)((double)n * 0.0001);
+    if (bnd < 1) bnd = 1;
+    if (!(bnd * 2 + 1 < n)) return ST_ROBUST_TOO_SMALL;
+    i0 = bnd; i1 = n - bnd; repeat = false;
+  }
+  const size_t PIECE = ((size_t)64 << 20) / sizeof(T);
+  T* stage[2] = {(T*)g_pinned.get(PIECE * sizeof(T)), (T*)g_pinned.get(PIECE * sizeof(T))};
+  cudaStream_t cs = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool ok = stage[0] && stage[1] && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) == cudaSuccess;
+  unsigned status = 0;
+  if (ok) {
+    const int passes = kind == M_NORMAL ? 2 : 1;
+    double mean_x = 0.0, mean_y = 0.0, c = 0.0, m2 = 0.0;   // slr state
+    uint64_t cnt = 0;
+    double nmean = 0.0, nstd = 0.0;                          // normal.rs:28-50 state
+    const double nf = (double)n;
+    T last_key = T();
+    uint64_t last_F = 0;
+    for (int pass = 0; pass < passes && ok; ++pass) {
+      auto issue = [&](uint64_t piece) {
+        const uint64_t a = piece * PIECE, b = std::min<uint64_t>(n, a + PIECE);
+        cudaMemcpyAsync(stage[piece & 1], d_keys + a, (b - a) * sizeof(T), cudaMemcpyDeviceToHost, cs);
+        cudaEventRecord(ev[piece & 1], cs);
+      };
+      const uint64_t npieces = (n + PIECE - 1) / PIECE;
+      if (npieces) issue(0);
+      uint64_t F = 0;
+      T prev = T();
+      for (uint64_t piece = 0; piece < npieces && ok; ++piece) {
+        if (cudaEventSynchronize(ev[piece & 1]) != cudaSuccess) { ok = false; break; }
+        if (piece + 1 < npieces) issue(piece + 1);
+        const T* kb = stage[piece & 1];
+        const uint64_t a = piece * PIECE, b = std::min<uint64_t>(n, a + PIECE);
+        for (uint64_t i = a; i < b; ++i) {
+          const T k = kb[i - a];
+          if (i == 0 || k != prev) F = i;     // FixDupsIter: offset of the first key of the run (models/mod.rs:154-185)
+          prev = k;
+          if (kind == M_NORMAL) {
+            const double x = host_as_float(k);
+            if (pass == 0) nmean = nmean + x / nf;
+            else { const double d = x - nmean; nstd = nstd + d * d; }
+          } else if (i >= i0 && i < i1) {
+            const double x = host_as_float(k), y = (double)host_scale(F, sf, use_sf);
+            cnt += 1;
+            const double dx = x - mean_x;
+            const double cf = (double)cnt;
+            mean_x = mean_x + dx / cf;
+            mean_y = mean_y + (y - mean_y) / cf;
+            c = c + dx * (y - mean_y);
+            const double dx2 = x - mean_x;
+            m2 = m2 + dx * dx2;
+          }
+        }
+        if (b == n && n > 0) { last_key = prev; last_F = F; }
+      }
+      if (!ok) break;
+      // the drained iterator repeats its final item (models/mod.rs:180)
+      if (n > 0) {
+        const double x = host_as_float(last_key);
+        if (kind == M_NORMAL) {
+          if (pass == 0) nmean = nmean + x / nf;
+          else { const double d = x - nmean; nstd = nstd + d * d; }
+        } else if (repeat) {
+          const double y = (double)host_scale(last_F, sf, use_sf);
+          cnt += 1;
+          const double dx = x - mean_x;
+          const double cf = (double)cnt;
+          mean_x = mean_x + dx / cf;
+          mean_y = mean_y + (y - mean_y) / cf;
+          c = c + dx * (y - mean_y);
+          const double dx2 = x - mean_x;
+          m2 = m2 + dx * dx2;
+        }
+      }
+    }
+    if (ok) {
+      if (kind == M_NORMAL) {
+        out_f[0] = nmean;
+        out_f[1] = std::sqrt(nstd / nf);
+        out_f[2] = n > 0 ? std::fmax(-INFINITY, (double)host_scale(last_F, sf, use_sf)) : -INFINITY;
+      } else {   // linear.rs:36-58
+        double alpha, beta;
+        if (cnt == 0) { alpha = 0.0; beta = 0.0; }
+        else if (cnt == 1) { alpha = mean_y; beta = 0.0; }
+        else {
+          const double nm1 = (double)(cnt - 1);
+          const double cov = c / nm1, var = m2 / nm1;
+          if (!(var >= 0.0)) { status |= ST_NEG_VARIANCE; alpha = 0.0; beta = 0.0; }
+          else if (var == 0.0) { alpha = mean_y; beta = 0.0; }
+          else { beta = cov / var; alpha = mean_y - beta * mean_x; }
+        }
+        out_f[0] = alpha; out_f[1] = beta;
+      }
+    }
+  }
+  if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
+  for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+  g_pinned.put(stage[0]); g_pinned.put(stage[1]);
+  if (!ok) return 0x80000000u;   // CUDA failure marker (decoded by the caller)
+  return status;
+}
+inline bool host_exact_kind(int kind) { return kind == M_LINEAR || kind == M_ROBUST_LINEAR || kind == M_NORMAL; }
+
 template <class T>
 int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& leaf, uint64_t N, uint32_t flags,
                 const double* l0_over, uint32_t n_over, rmi_result** out) {
@@ -596,16 +721,26 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
       if (top.kind == M_HISTOGRAM) h_top.ip[0] = hist_bins;
       if (l0_over) for (uint32_t q = 0; q < n_over && q < 4; ++q) h_top.f[q] = l0_over[q];
       cudaEventRecord(ev0, st);
+      unsigned host_status = 0;
+      bool exact = (flags & RMI_FLAG_TOP_FIT_EXACT) != 0;
+      // exact serial tops on large key sets: the recurrence runs on a host core (host_exact_top); small sets keep the
+      // one-warp device chain (no PCIe round trip, and the CPU tests of the chain itself stay meaningful)
+      static const uint64_t host_exact_min = [] { const char* e = getenv("RMI_DEV_HOST_EXACT_MIN"); return e ? (uint64_t)atoll(e) : (uint64_t)1 << 20; }();
+      bool host_top = false;
+      if (exact && !l0_over && host_exact_kind(top.kind) && n >= host_exact_min) {
+        cudaEventSynchronize(ev0);
+        unsigned hs = host_exact_top<T>(ds, top.kind, N, h_top.f);
+        if (hs == 0x80000000u) rc = fail(RMI_ERR_CUDA, "exact top fit: copying the keys back to the host failed");
+        else { host_status |= hs; host_top = true; }
+      }
       cudaMemcpyAsync(d_top, &h_top, sizeof(h_top), cudaMemcpyHostToDevice, st);
       cudaMemsetAsync(d_aux, 0, sizeof(BuildAux), st);
-      unsigned host_status = 0;
       bool leaf_results_copied = false;
-      bool exact = (flags & RMI_FLAG_TOP_FIT_EXACT) != 0;
-      if (!l0_over)
-        host_status = fit_top_model<T>(L, keys, n, top.kind, top.table_bits, N, exact, d_top, d_aux, d_scratch, d_table,
-                                       d_pivots, d_ri);
+      if (!l0_over && !host_top && rc == RMI_OK)
+        host_status |= fit_top_model<T>(L, keys, n, top.kind, top.table_bits, N, exact, d_top, d_aux, d_scratch, d_table,
+                                        d_pivots, d_ri);
       cudaEventRecord(evp[0], st);
-      if (host_status == 0) {
+      if (host_status == 0 && rc == RMI_OK) {
         // injected top parameters are not known to be monotone: take the streaming pass, which checks
         // (RMI_PIPELINED_BOUNDS builds: only the five boundaries needed up front are searched here, the rest slice
         //  by slice next to the leaf kernel; otherwise prepare_pipelined_bounds declines and the phase runs whole)
@@ -658,7 +793,9 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
         cudaMemcpyAsync(box->arr2.data(), d_pivots, sizeof(u64) * hist_bins, cudaMemcpyDeviceToHost, st);
       }
       cudaError_t e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) {
+      if (rc != RMI_OK) {
+        // (the exact top fit's key read-back failed: reported above)
+      } else if (e != cudaSuccess) {
         rc = fail(RMI_ERR_CUDA, std::string("rmi_train: ") + cudaGetErrorString(e));
       } else if (host_status | h_aux.status) {
         rc = fail(RMI_ERR_PANIC, status_text(host_status | h_aux.status));

@@ -179,7 +179,7 @@ constexpr int PIECE_STRIDE = 32 * 16;   // bytes between a row's consecutive pie
 #define RMI_SSTAGES 2
 #endif
 constexpr int SSTAGES = RMI_SSTAGES;
-constexpr int WARP_STREAM_BYTES = SSTAGES * STAGE_BYTES + 32 * 4 + 32 * 4;
+constexpr int WARP_STREAM_BYTES = SSTAGES * STAGE_BYTES;
 
 // createpolicy for an L2 eviction priority: 0 evict_normal, 1 evict_first, 2 evict_last.
 __device__ __forceinline__ u64 l2_policy_of(int kind) {
@@ -223,8 +223,6 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
   constexpr int SW = 8 * KPP;                // keys per row per chunk
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  u32* rowg = reinterpret_cast<u32*>(wsm + SSTAGES * STAGE_BYTES);   // first 16-byte piece of each row
-  u32* rownp = rowg + 32;                                                // pieces in each row
   const I a = b & ~(I)(KPP - 1);             // 16-byte aligned start of this lane's stream
   const I skip = b - a;
   const I rlen = e > b ? (I)(e - a) : (I)0;  // keys from a up to e
@@ -236,37 +234,42 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
   }
   if (SOLO) *solo_lane = -1;
   if (maxlen == 0) return;
-  // Piece bookkeeping in 16-byte units (32-bit: covers 64 GB of keys).  Rows longer than
-  // 2^32 pieces cannot occur below that size either.
-  __syncwarp();
-  rowg[lane] = (u32)((u64)a / KPP);
-  rownp[lane] = (u32)(((u64)rlen + KPP - 1) / KPP);
-  __syncwarp();
-  const int prow = lane >> 3, piece = lane & 7;
-  u32 g0[8], np[8];   // this lane's 8 (row, piece) streams: first piece index, pieces available
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int row = prow + 4 * q;
-    g0[q] = rowg[row] + (u32)piece;
-    const u32 rp = rownp[row];
-    np[q] = rp > (u32)piece ? (rp - (u32)piece + 7u) / 8u : 0u;   // chunks in which this piece exists
-  }
-  const unsigned char* kb = reinterpret_cast<const unsigned char*>(keys);
-  const unsigned st0 = (unsigned)__cvta_generic_to_shared(wsm) + (unsigned)(piece * PIECE_STRIDE + prow * 16);
+  // Every lane copies ITS OWN row: 8 copies of 16 bytes per chunk from one running pointer with immediate offsets
+  // (no per-copy address arithmetic, no exchange of row descriptors).  Shared memory is piece-major, so the 32
+  // lanes of one copy instruction write 512 contiguous bytes and the 32 lanes of a 128-bit read fetch 512
+  // contiguous bytes: conflict-free both ways.  (cp.async requests are not merged across lanes on the way to L2
+  // — ncu counts one sector request per 16-byte copy whichever lane issues it — so a row's 128 bytes cost the
+  // same 8 requests as when 8 neighbouring lanes covered it in one instruction.)
+  const u32 my_pieces = (u32)(((u64)rlen + KPP - 1) / KPP);   // 16-byte pieces of this lane's stream
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(keys) + (u64)a * sizeof(T);
+  const unsigned st0 = (unsigned)__cvta_generic_to_shared(wsm) + (unsigned)(lane * 16);
   const u32 nchunks = (u32)(((u64)maxlen + SW - 1) / SW);
-  // One predicated 16-byte copy per (row, piece) stream: address = chunk base + piece index * 16.
+  // chunks every lane has in full (no predicates needed while c is below this)
+  I minlen = rlen;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    I t = __shfl_xor_sync(FULL, minlen, o);
+    if (t < minlen) minlen = t;
+  }
+  const u32 full_chunks = (u32)((u64)minlen / SW);
   // Pieces are whole 16-byte units; the one that holds the array's last key may extend past it
   // (the buffer is readable up to the next 16-byte boundary, include/rmi_b200.h), and nothing
   // past a lane's range is ever consumed.
   auto issue = [&](u32 c) {
     const unsigned st = st0 + (c % SSTAGES) * STAGE_BYTES;
-    const unsigned char* cb = kb + (u64)c * 128u;
+    const unsigned char* cb = src + (u64)c * 128u;
+    if (c < full_chunks) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      u64 src;
-      asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(src) : "r"(g0[q]), "l"(cb));
-      asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %4;\n\t}\n"
-                   ::"r"(st + (unsigned)(q * 4 * 16)), "l"(src), "r"(c), "r"(np[q]), "l"(l2_policy) : "memory");
+      for (int q = 0; q < 8; ++q)
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n"
+                     ::"r"(st + (unsigned)(q * PIECE_STRIDE)), "l"(cb + q * 16), "l"(l2_policy) : "memory");
+    } else {
+      const u32 done = c * 8u;                                      // pieces before this chunk
+      const u32 left = my_pieces > done ? my_pieces - done : 0u;    // pieces of this lane in this chunk and beyond
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %2, %3;\n\t@p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %4;\n\t}\n"
+                     ::"r"(st + (unsigned)(q * PIECE_STRIDE)), "l"(cb + q * 16), "r"(left), "r"((u32)q), "l"(l2_policy) : "memory");
     }
     cp_async_commit();
   };
@@ -301,7 +304,7 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
     // matters in chunk 0 only (a stream starts at the 16-byte piece that holds index b, so up to
     // KPP-1 leading positions are not the lane's): there the first piece is walked under a per-lane
     // predicate and the other seven pieces take the vector path like any later chunk.
-    if (__all_sync(FULL, rlen >= cbase + (I)SW)) {
+    if (c < full_chunks) {   // every lane still has all SW positions of this chunk
       I idx = a + cbase;
       if (c == 0) {
         uint4 v = *reinterpret_cast<const uint4*>(row);

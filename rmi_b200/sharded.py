@@ -402,9 +402,12 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
     if comm is not None:
         # halo keys are fetched once per data set (see step 4 below), then the whole build is one call
         if getattr(data, "_halo_have", None) is None:
-            cap = _min_halo_capacity(data, group, world, dev)
-            moves = plan_halo(bases, [bases[g + 1] + cap - 1 for g in range(world)], n_global)
-            data._halo_have = _exchange_halo(eng, moves, rank, group, dev)
+            if world > 1:
+                cap = _min_halo_capacity(data, group, world, dev)
+                moves = plan_halo(bases, [bases[g + 1] + cap - 1 for g in range(world)], n_global)
+                data._halo_have = _exchange_halo(eng, moves, rank, group, dev)
+            else:
+                data._halo_have = 0
         eng.set_halo(data._halo_have or 0)
         eng.set_partition(bases, world, rank)
         try:

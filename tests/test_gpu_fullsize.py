@@ -71,11 +71,41 @@ def test_config2_cubic_linear_262144_on_200M_uint64(rmi, oracle):
     parity.assert_same_rmi(g, o)
 
 
-def test_exact_top_fit_bit_identical_at_20M(rmi, oracle):
-    """RMI_FLAG_TOP_FIT_EXACT at a size where the one-warp serial recurrence takes well under a second."""
+@pytest.mark.parametrize("spec,dups", [("linear,linear", False), ("robust_linear,linear", True), ("normal,linear", False),
+                                       ("linear,linear", True)])
+def test_exact_top_fit_bit_identical_at_20M(rmi, oracle, spec, dups):
+    """RMI_FLAG_TOP_FIT_EXACT on a key set large enough for the host-core recurrence (host_exact_top, api.cu:
+    the keys stream back over PCIe while one CPU core runs linear.rs:12-59 / normal.rs:28-50 in the reference's
+    order): bit-identical top model, hence a bit-identical RMI, including duplicate-fixed offsets."""
     k = _sorted_keys("u64", 5)[::10].contiguous()
+    if dups:
+        k = k.clone()
+        k[1000:1400] = k[1000]
+        k[5_000_000:5_000_003] = k[5_000_000]
+        k[-50:] = k[-50]
+        k, _ = torch.sort(k)
     host = k.cpu().numpy().view(np.uint64)
     ds = rmi.RMITrainingData.from_device(k.data_ptr(), host.size, rmi.KEY_U64, 0, keep_alive=k)
-    g = rmi.train(ds, "linear,linear", 1 << 17, rmi.FLAG_TOP_FIT_EXACT)
-    o = oracle.train(host, "linear,linear", 1 << 17)
+    g = rmi.train(ds, spec, 1 << 17, rmi.FLAG_TOP_FIT_EXACT)
+    assert g.top_fit_exact
+    o = oracle.train(host, spec, 1 << 17)
     parity.assert_same_rmi(g, o)
+
+
+def test_exact_top_fit_at_200M_is_not_slower_than_the_reference(rmi, oracle):
+    """The bit-exact mode of the headline configuration: same top model as the oracle's serial fit, and the whole
+    build — PCIe read-back of the keys + the serial chain on one host core + the GPU phases — within the
+    time the oracle's own build takes (the reference spends ~1.5 s in this chain alone)."""
+    import time
+    k = _sorted_keys("u64", 42)
+    host = k.cpu().numpy().view(np.uint64)
+    ds = rmi.RMITrainingData.from_device(k.data_ptr(), N_KEYS, rmi.KEY_U64, 0, keep_alive=k)
+    t0 = time.perf_counter()
+    g = rmi.train(ds, "linear,linear", 1 << 20, rmi.FLAG_TOP_FIT_EXACT)
+    t_gpu = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    o = oracle.train(host, "linear,linear", 1 << 20)
+    t_cpu = time.perf_counter() - t0
+    parity.assert_same_rmi(g, o)
+    print(f"exact-mode build {t_gpu:.2f} s, oracle build {t_cpu:.2f} s")
+    assert t_gpu < t_cpu

@@ -6,10 +6,9 @@ set -o pipefail
 #   tools/build_variants.sh s3 t64     # a subset
 declare -A DEFS=(
   [b5]="-DRMI_LEAF_MIN_BLOCKS=5"         # 5 blocks of 128 lanes per SM for every instantiation (96 registers)
+  [b4]="-DRMI_LEAF_MIN_BLOCKS=4"         # 4 blocks per SM: fewer leaves in flight between the two reads of a key
   [lsf]="-DRMI_LANE_SERIAL_FORWARD"      # round 1's lane-serial forward pass behind this round's fit pass
-  [lsf5]="-DRMI_LANE_SERIAL_FORWARD -DRMI_LEAF_MIN_BLOCKS=5"
   [d4]="-DRMI_FWD_DEPTH=4"               # forward pass: 4 loads in flight per warp instead of 8
-  [d12]="-DRMI_FWD_DEPTH=12"
   [pb]="-DRMI_PIPELINED_BOUNDS"          # leaf-boundary search sliced and overlapped with the leaf kernel's slices
 )
 names=("$@")
