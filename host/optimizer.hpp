@@ -126,29 +126,63 @@ inline std::vector<Config> second_phase_configs(const std::vector<RMIStatistics>
 inline std::vector<RMIStatistics> measure_rmis(const std::vector<const rmi_dataset*>& replicas, const std::vector<Config>& configs,
                                                uint32_t flags, bool verbose) {
   std::vector<RMIStatistics> out(configs.size());
+  // Unit of work = the configurations that share (top model, branching factor): rmi_train_stats_batch fits the top
+  // model and derives the leaf boundaries once for the whole group (several configurations
+  // per key pass).  Groups keep the order of their first member; results land at the configurations' own positions.
+  struct Group { std::string top; uint64_t bf; std::vector<std::string> leaves; std::vector<size_t> index; };
+  std::vector<Group> groups;
+  static const bool batching = [] { const char* e = std::getenv("RMI_OPTIMIZER_NO_BATCH"); return !(e && e[0] == '1'); }();
+  for (size_t i = 0; i < configs.size(); ++i) {
+    const std::string& m = configs[i].first;
+    const size_t comma = m.find(',');
+    const std::string top = m.substr(0, comma), leaf = comma == std::string::npos ? "" : m.substr(comma + 1);
+    Group* g = nullptr;
+    if (batching && comma != std::string::npos && leaf.find(',') == std::string::npos)
+      for (auto& c : groups) if (c.top == top && c.bf == configs[i].second && !c.leaves.empty()) { g = &c; break; }
+    if (!g) {
+      groups.push_back(Group{top, configs[i].second, {}, {}});
+      g = &groups.back();
+      if (!(batching && comma != std::string::npos && leaf.find(',') == std::string::npos)) g->top = m;   // not a two-layer spec: trained (and rejected) on its own
+    }
+    g->leaves.push_back(leaf);
+    g->index.push_back(i);
+  }
   std::atomic<size_t> next{0};
   std::atomic<bool> failed{false};
   std::vector<std::string> errors(replicas.size());
   auto worker = [&](size_t w) {
     const rmi_dataset* ds = replicas[w];
     for (;;) {
-      size_t i = next.fetch_add(1);
-      if (i >= configs.size() || failed.load()) return;
-      const Config& c = configs[i];
-      rmi_result* r = nullptr;
-      int rc = rmi_train(ds, c.first.c_str(), c.second, flags | RMI_FLAG_STATS_ONLY, &r);
+      size_t gi = next.fetch_add(1);
+      if (gi >= groups.size() || failed.load()) return;
+      const Group& g = groups[gi];
+      const size_t K = g.index.size();
+      std::vector<rmi_result*> res(K, nullptr);
+      int rc;
+      const bool two_layer = configs[g.index[0]].first != g.top;   // g.top holds the bare top-model name
+      if (two_layer) {
+        std::vector<const char*> names;
+        for (auto& l : g.leaves) names.push_back(l.c_str());
+        rc = rmi_train_stats_batch(ds, g.top.c_str(), names.data(), (int)K, g.bf, flags, res.data());
+      } else {
+        rc = rmi_train(ds, g.top.c_str(), g.bf, flags | RMI_FLAG_STATS_ONLY, &res[0]);
+      }
       if (rc != RMI_OK) {
-        errors[w] = "training " + c.first + " " + std::to_string(c.second) + ": " + rmi_last_error();
+        errors[w] = "training " + configs[g.index[0]].first + " " + std::to_string(g.bf) + ": " + rmi_last_error();
         failed.store(true);
         return;
       }
-      RMIStatistics& s = out[i];
-      s.models = c.first; s.branching_factor = c.second;
-      s.average_log2_error = r->model_avg_log2_error; s.max_log2_error = r->model_max_log2_error;
-      s.size = rmi_size(*r, true);
-      if (verbose) std::fprintf(stderr, "  [replica %zu] %-28s %10llu  avg_log2 %.5f  size %llu  (%.2f ms)\n", w, c.first.c_str(),
-                                (unsigned long long)c.second, s.average_log2_error, (unsigned long long)s.size, r->device_time_ns / 1e6);
-      rmi_result_free(r);
+      for (size_t k = 0; k < K; ++k) {
+        const Config& c = configs[g.index[k]];
+        rmi_result* r = res[k];
+        RMIStatistics& s = out[g.index[k]];
+        s.models = c.first; s.branching_factor = c.second;
+        s.average_log2_error = r->model_avg_log2_error; s.max_log2_error = r->model_max_log2_error;
+        s.size = rmi_size(*r, true);
+        if (verbose) std::fprintf(stderr, "  [replica %zu] %-28s %10llu  avg_log2 %.5f  size %llu  (%.2f ms)\n", w, c.first.c_str(),
+                                  (unsigned long long)c.second, s.average_log2_error, (unsigned long long)s.size, r->device_time_ns / 1e6);
+        rmi_result_free(r);
+      }
     }
   };
   if (replicas.size() == 1) worker(0);

@@ -147,6 +147,15 @@ int rmi_train_with_top(const rmi_dataset* ds, const char* model_spec, uint64_t b
                        const double* l0_fparams, uint32_t n_fparams, rmi_result** out);
 void rmi_result_free(rmi_result* r);
 
+/* The optimizer's unit of work (optimizer.rs:110-125 enumerates every leaf type for each (top, branching factor)):
+ * `num_leaf_models` configurations "top,leaf_k" with the SAME top model and branching factor in one call.  The top
+ * model is fitted once and the leaf boundaries are derived once — one pass over the keys each instead of one per
+ * configuration — then the fused leaf kernel runs once per leaf type.  Statistics only (as RMI_FLAG_STATS_ONLY): out[k]
+ * receives configuration k's result (release each with rmi_result_free); a configuration the reference would panic on
+ * fails the whole call, as it aborts the reference's sweep. */
+int rmi_train_stats_batch(const rmi_dataset* ds, const char* top_model, const char* const* leaf_models, int num_leaf_models,
+                          uint64_t branch_factor, uint32_t flags, rmi_result** out);
+
 /* ---- Range-partitioned (multi-GPU) build ----------------------------------------------------
  * One process per GPU; rank r holds the r-th contiguous slab of the globally sorted key array
  * in an rmi_dataset.  The leaf fits are independent once the top model and the leaf boundaries

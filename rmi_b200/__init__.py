@@ -15,8 +15,8 @@ or no device is present, calls raise.
 """
 from .api import (KEY_F64, KEY_U32, KEY_U64, FLAG_LEAF_COUNTS, FLAG_SHARD_ROOT_ONLY, FLAG_STATS_ONLY, FLAG_TOP_FIT_EXACT, RMIError, RMIPanic,
                   RMITrainingData, TrainedRMI, cache_fix, find_pareto_efficient_configs, kernel_launch_count, lib_path,
-                  load_data, load_library, output_rmi, rmi_size, train, train_bounded, train_for_size, version)
+                  load_data, load_library, output_rmi, rmi_size, train, train_bounded, train_for_size, train_stats_batch, version)
 
 __all__ = ["KEY_F64", "KEY_U32", "KEY_U64", "FLAG_LEAF_COUNTS", "FLAG_SHARD_ROOT_ONLY", "FLAG_STATS_ONLY", "FLAG_TOP_FIT_EXACT", "RMIError", "RMIPanic",
            "RMITrainingData", "TrainedRMI", "cache_fix", "find_pareto_efficient_configs", "kernel_launch_count", "lib_path",
-           "load_data", "load_library", "output_rmi", "rmi_size", "train", "train_bounded", "train_for_size", "version"]
+           "load_data", "load_library", "output_rmi", "rmi_size", "train", "train_bounded", "train_for_size", "train_stats_batch", "version"]

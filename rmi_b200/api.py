@@ -351,6 +351,19 @@ def train(data: RMITrainingData, model_spec: str, branch_factor: int, flags: int
     return result_from_pointer(res, model_spec)
 
 
+def train_stats_batch(data: RMITrainingData, top_model: str, leaf_models: list[str], branch_factor: int, flags: int = 0) -> list[TrainedRMI]:
+    """rmi_train_stats_batch: the configurations "top,leaf_k" of one (top model, branching factor) in one call —
+    one top-model fit and one boundary pass for all of them; statistics only (the optimizer's unit of work)."""
+    L = load_library()
+    L.rmi_train_stats_batch.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_uint64, C.c_uint32,
+                                        C.POINTER(C.POINTER(_Result))]
+    K = len(leaf_models)
+    names = (C.c_char_p * K)(*[m.encode() for m in leaf_models])
+    out = (C.POINTER(_Result) * K)()
+    _check(L.rmi_train_stats_batch(data._h, top_model.encode(), names, K, int(branch_factor), int(flags), out))
+    return [result_from_pointer(out[k], f"{top_model},{leaf_models[k]}") for k in range(K)]
+
+
 def result_from_pointer(res, model_spec: str) -> TrainedRMI:
     """Wrap a struct rmi_result* returned by the library (zero-copy views, freed with the last view)."""
     if True:

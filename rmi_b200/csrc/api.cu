@@ -856,6 +856,134 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
   return RMI_OK;
 }
 
+// Several configurations that share the top model and the branching factor (the optimizer's grid enumerates every
+// leaf type for each (top, branching factor), optimizer.rs:110-125): ONE top-model fit and ONE boundary pass over the
+// keys, then the fused leaf kernel once per leaf type.  Statistics only (what the search consumes, optimizer.rs:163-171).
+template <class T>
+int train_batch_typed(const rmi_dataset* ds, const ModelName& top, const std::vector<const ModelName*>& leaves, uint64_t N,
+                      uint32_t flags, rmi_result** out) {
+  auto t_start = std::chrono::steady_clock::now();
+  const uint64_t n = ds->n;
+  const T* keys = (const T*)ds->d_keys;
+  CUDA_TRY(cudaSetDevice(ds->device));
+  DeviceInfo di;
+  if (int rc = device_info(ds->device, &di)) return rc;
+  BuildContext* bc = t_build_ctx.get(ds->device);
+  if (!bc) return fail(RMI_ERR_CUDA, "could not create the build's CUDA streams / events");
+  cudaStream_t st = bc->st;
+  const size_t K = leaves.size();
+  std::vector<ResultBox*> boxes(K, nullptr);
+  int rc = RMI_OK;
+  {
+    Arena A(st);
+    Launch L{st, di.num_sms};
+    L.side = bc->side; L.ev_fork = bc->ev_fork; L.ev_join = bc->ev_join;
+    L.d_long = A.get<u32>(LONG_LEAF_CAP + 1);
+    int max_ppm = 2;
+    for (auto* lf : leaves) max_ppm = std::max(max_ppm, leaf_params_per_model(lf->kind));
+    TopModel* d_top = A.get<TopModel>(1);
+    BuildAux* d_aux0 = A.get<BuildAux>(1);
+    BuildAux* d_auxk = A.get<BuildAux>(K);
+    u64* d_S = A.get<u64>(N + 1);
+    double* d_params = A.get<double>(N * max_ppm);
+    u64* d_errors = A.get<u64>(N);
+    u64* d_counts = A.get<u64>(N);
+    void* d_scratch = A.get<char>(top_scratch_bytes(N));
+    void* d_stats = A.get<char>(stats_scratch_bytes(N));
+    u32* d_table = nullptr;
+    u64 *d_pivots = nullptr, *d_ri = nullptr;
+    u64 hist_bins = 0, hist_ipb = 0;
+    if (top.kind == M_RADIX_TABLE) d_table = A.get<u32>((size_t)1 << top.table_bits);
+    if (top.kind == M_HISTOGRAM) {
+      histogram_bins(n, N, &hist_bins, &hist_ipb);
+      d_pivots = A.get<u64>(hist_bins + 1);
+      d_ri = A.get<u64>(((size_t)1 << 20) + 1);
+    }
+    bool host_ok = true;
+    for (size_t k = 0; k < K; ++k) {
+      boxes[k] = new ResultBox();
+      host_ok = host_ok && boxes[k]->scalars.resize(sizeof(BuildAux) + sizeof(TopModel));
+    }
+    if (A.err != cudaSuccess) rc = fail(RMI_ERR_CUDA, std::string("scratch allocation: ") + cudaGetErrorString(A.err));
+    else if (!host_ok) rc = fail(RMI_ERR_CUDA, "pinned host allocation for the results failed");
+    else {
+      TopModel h_top;
+      memset(&h_top, 0, sizeof(h_top));
+      h_top.kind = top.kind; h_top.high = 1; h_top.table_bits = top.table_bits;
+      h_top.t32 = d_table; h_top.pivots = d_pivots; h_top.radix_index = d_ri; h_top.npivots = hist_bins;
+      if (top.kind == M_HISTOGRAM) h_top.ip[0] = hist_bins;
+      cudaEventRecord(bc->ev0, st);
+      cudaMemcpyAsync(d_top, &h_top, sizeof(h_top), cudaMemcpyHostToDevice, st);
+      cudaMemsetAsync(d_aux0, 0, sizeof(BuildAux), st);
+      const bool exact = (flags & RMI_FLAG_TOP_FIT_EXACT) != 0;
+      unsigned host_status = fit_top_model<T>(L, keys, n, top.kind, top.table_bits, N, exact, d_top, d_aux0, d_scratch, d_table,
+                                              d_pivots, d_ri);
+      if (host_status == 0) {
+        compute_leaf_bounds<T>(L, keys, n, top.kind, d_top, N, d_S, d_aux0, /*allow_search=*/true);
+        Shard<T> whole = whole_array<T>(n);
+        whole.no_dups = ds->no_dups ? 1 : 0;
+        for (size_t k = 0; k < K; ++k) {
+          BuildAux* d_aux = d_auxk + k;   // own status word, replacement counter and statistics per configuration
+          cudaMemcpyAsync(d_aux, d_aux0, sizeof(BuildAux), cudaMemcpyDeviceToDevice, st);
+          fit_leaves<T>(L, keys, whole, leaves[k]->kind, N, d_S, d_aux, d_params, d_errors, d_counts);
+          leaf_statistics(L, n, N, d_errors, d_counts, d_aux, d_stats);
+          cudaMemcpyAsync(boxes[k]->scalars.data(), d_aux, sizeof(BuildAux), cudaMemcpyDeviceToHost, st);
+          cudaMemcpyAsync(boxes[k]->scalars.data() + sizeof(BuildAux), d_top, sizeof(TopModel), cudaMemcpyDeviceToHost, st);
+        }
+      }
+      cudaEventRecord(bc->ev1, st);
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) rc = fail(RMI_ERR_CUDA, std::string("rmi_train_stats_batch: ") + cudaGetErrorString(e));
+      else if (host_status) rc = fail(RMI_ERR_PANIC, status_text(host_status));
+      else {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, bc->ev0, bc->ev1);
+        for (size_t k = 0; k < K && rc == RMI_OK; ++k) {
+          const BuildAux& h_aux = *reinterpret_cast<const BuildAux*>(boxes[k]->scalars.data());
+          const TopModel& tb = *reinterpret_cast<const TopModel*>(boxes[k]->scalars.data() + sizeof(BuildAux));
+          if (h_aux.status) { rc = fail(RMI_ERR_PANIC, std::string(top.name) + "," + leaves[k]->name + ": " + status_text(h_aux.status)); break; }
+          rmi_result& R = boxes[k]->pub;
+          memset(&R, 0, sizeof(R));
+          R.num_rmi_rows = n; R.num_data_rows = n; R.branching_factor = N;
+          R.model_max_error = h_aux.max_error;
+          R.model_max_error_idx = h_aux.max_error_idx;
+          R.model_avg_error = (double)h_aux.sum_n_err / (double)n;
+          R.model_avg_l2_error = h_aux.sum_l2;
+          R.model_avg_log2_error = h_aux.sum_log2 / (double)n;
+          R.model_max_log2_error = std::log2((double)h_aux.max_error);
+          R.device_time_ns = (uint64_t)((double)ms * 1e6 / (double)K);   // the batch's device time, shared out evenly
+          R.l0_model_id = top.kind;
+          R.l0_bradix_high = tb.high;
+          R.l0_table_bits = top.table_bits;
+          switch (top.kind) {
+            case M_CUBIC: R.l0_num_fparams = 4; break;
+            case M_NORMAL: case M_LOGNORMAL: R.l0_num_fparams = 3; break;
+            case M_LINEAR: case M_ROBUST_LINEAR: case M_LINEAR_SPLINE: case M_LOGLINEAR: R.l0_num_fparams = 2; break;
+            case M_RADIX: R.l0_num_iparams = 2; break;
+            case M_BRADIX: R.l0_num_iparams = 3; break;
+            case M_RADIX_TABLE: R.l0_num_iparams = 1; break;
+            case M_HISTOGRAM: R.l0_num_iparams = 1; break;
+          }
+          for (int q = 0; q < 4; ++q) { R.l0_fparams[q] = tb.f[q]; R.l0_iparams[q] = tb.ip[q]; }
+          // sizes of the top model's tables (rmi_model_size needs them; the tables themselves stay on the device)
+          R.l0_table32_len = top.kind == M_RADIX_TABLE ? ((uint64_t)1 << top.table_bits) : 0;
+          R.l0_array1_len = top.kind == M_HISTOGRAM ? (((uint64_t)1 << 20) + 1) : 0;
+          R.l0_array2_len = top.kind == M_HISTOGRAM ? hist_bins : 0;
+          R.l1_model_id = leaves[k]->kind;
+          R.l1_params_per_model = leaf_params_per_model(leaves[k]->kind);
+          R.could_not_replace = h_aux.could_not_replace ? 1 : 0;
+          R.top_fit_exact = exact ? 1 : 0;
+        }
+      }
+    }
+  }
+  cudaStreamSynchronize(st);
+  if (rc != RMI_OK) { for (auto* b : boxes) delete b; return rc; }
+  const uint64_t wall = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_start).count();
+  for (size_t k = 0; k < K; ++k) { boxes[k]->pub.build_time_ns = wall / K; out[k] = &boxes[k]->pub; }
+  return RMI_OK;
+}
+
 int train_entry(const rmi_dataset* ds, const char* model_spec, uint64_t N, uint32_t flags, const double* l0_over,
                 uint32_t n_over, rmi_result** out) {
   g_last_error.clear();
@@ -910,6 +1038,31 @@ extern "C" {
 
 int rmi_train(const rmi_dataset* ds, const char* model_spec, uint64_t branch_factor, uint32_t flags, rmi_result** out) {
   return train_entry(ds, model_spec, branch_factor, flags, nullptr, 0, out);
+}
+int rmi_train_stats_batch(const rmi_dataset* ds, const char* top_model, const char* const* leaf_models, int num_leaf_models,
+                          uint64_t branch_factor, uint32_t flags, rmi_result** out) {
+  g_last_error.clear();
+  if (!ds || !top_model || !leaf_models || num_leaf_models < 1 || !out) return fail(RMI_ERR_INVALID, "rmi_train_stats_batch: bad argument");
+  const ModelName* top = find_model(top_model);
+  if (!top) return fail(RMI_ERR_PANIC, std::string("Unknown model type: ") + top_model);
+  std::vector<const ModelName*> leaves;
+  for (int k = 0; k < num_leaf_models; ++k) {
+    const ModelName* m = leaf_models[k] ? find_model(leaf_models[k]) : nullptr;
+    if (!m) return fail(RMI_ERR_PANIC, std::string("Unknown model type: ") + (leaf_models[k] ? leaf_models[k] : "(null)"));
+    if (m->kind == M_RADIX || m->kind == M_BRADIX || m->kind == M_HISTOGRAM)   // train/mod.rs:59-85
+      return fail(RMI_ERR_PANIC, std::string("if used, model type ") + m->name + " must be the root model");
+    if (m->kind == M_RADIX_TABLE) return fail(RMI_ERR_UNSUPPORTED, "radix tables are only offered as the top model in this build");
+    leaves.push_back(m);
+  }
+  if (branch_factor < 1) return fail(RMI_ERR_PANIC, "branching factor must be at least 1");
+  if (ds->n == 0) return fail(RMI_ERR_PANIC, "start index was 0 but end index was 0");
+  if (!ds->sorted) return fail(RMI_ERR_PANIC, "keys are not sorted in ascending order");
+  switch (ds->key_type) {
+    case RMI_KEY_U64: return train_batch_typed<u64>(ds, *top, leaves, branch_factor, flags, out);
+    case RMI_KEY_U32: return train_batch_typed<u32>(ds, *top, leaves, branch_factor, flags, out);
+    case RMI_KEY_F64: return train_batch_typed<double>(ds, *top, leaves, branch_factor, flags, out);
+  }
+  return fail(RMI_ERR_INVALID, "bad key type");
 }
 int rmi_train_with_top(const rmi_dataset* ds, const char* model_spec, uint64_t branch_factor, uint32_t flags,
                        const double* l0_fparams, uint32_t n_fparams, rmi_result** out) {

@@ -40,14 +40,16 @@ constexpr int BOUNDS_THREADS = 256;
 #ifndef RMI_LEAF_THREADS
 #define RMI_LEAF_THREADS 128
 #endif
-// Resident blocks per SM the compiler must allow for: 24 warps (80 registers) for the duplicate-free linear
-// leaf — the kernel of the headline build, which fits — and 20 warps (96 registers) for everything else.
-#ifdef RMI_LEAF_MIN_BLOCKS
-#define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS, RMI_LEAF_MIN_BLOCKS)
-#else
-#define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS, ((LEAF == M_LINEAR && !DUPS) ? 768 : 640) / RMI_LEAF_THREADS)
+// Resident blocks per SM the compiler must allow for: 20 warps (the padded copy ring takes 41 KB of shared memory per
+// 128-lane block, so 5 blocks fit), i.e. at most 96 registers.
+#ifndef RMI_LEAF_MIN_BLOCKS
+#define RMI_LEAF_MIN_BLOCKS (640 / RMI_LEAF_THREADS)
 #endif
+#define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS, RMI_LEAF_MIN_BLOCKS)
 constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
+#ifndef RMI_FWD_BULK
+#define RMI_FWD_BULK 1   // forward pass fed by 1-D bulk copies (cp.async.bulk + mbarrier); 0 = register look-ahead
+#endif
 #ifndef RMI_FWD_DEPTH
 #define RMI_FWD_DEPTH 8   // 32-key loads in flight per warp in the forward pass
 #endif
@@ -170,16 +172,21 @@ __global__ void k_split(const T* __restrict__ keys, u64 n, const TopModel* __res
 // length, so 8-key and 8-million-key leaves take the same code path, and the keys cross
 // HBM -> L2 -> SM in full lines exactly once per pass.
 // ------------------------------------------------------------------------------------------
-// Layout of one stage: piece-major — the 32 rows' q-th 16-byte pieces are contiguous (512 B), so the
-// 8 lanes of a 128-bit shared-load phase, which read the same piece of 8 neighbouring rows, hit 8
-// distinct bank quads without any padding: 4 KB per stage.
-constexpr int STAGE_BYTES = 32 * 128;
-constexpr int PIECE_STRIDE = 32 * 16;   // bytes between a row's consecutive pieces
+// Layout of one stage: row-major, 128 B of keys + 16 B pad per row.  The copies are issued 8 lanes per row (each
+// instruction moves four contiguous 128-byte segments: 4 cycles in the load/store unit's address stage and
+// conflict-free shared-memory writes), and the pad makes the 8 lanes of a 128-bit read phase — the same piece of 8
+// neighbouring rows — hit 8 distinct bank quads.  Measured alternatives (profiles/r02_ring_layouts.md): an unpadded
+// piece-major stage turns the copies' writes into 8-way bank conflicts (leaf kernel 0.98 ms instead of 0.53), and
+// letting every lane copy its own row costs 32 address-stage cycles per copy instruction instead of 4 — the LSU
+// becomes the bottleneck (0.90 ms).
+constexpr int ROW_BYTES = 144;
+constexpr int STAGE_BYTES = 32 * ROW_BYTES;
+constexpr int PIECE_STRIDE = 16;   // bytes between a row's consecutive pieces
 #ifndef RMI_SSTAGES
 #define RMI_SSTAGES 2
 #endif
 constexpr int SSTAGES = RMI_SSTAGES;
-constexpr int WARP_STREAM_BYTES = SSTAGES * STAGE_BYTES;
+constexpr int WARP_STREAM_BYTES = SSTAGES * STAGE_BYTES + 32 * 4 + 32 * 4;
 
 // createpolicy for an L2 eviction priority: 0 evict_normal, 1 evict_first, 2 evict_last.
 __device__ __forceinline__ u64 l2_policy_of(int kind) {
@@ -234,17 +241,27 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
   }
   if (SOLO) *solo_lane = -1;
   if (maxlen == 0) return;
-  // Every lane copies ITS OWN row: 8 copies of 16 bytes per chunk from one running pointer with immediate offsets
-  // (no per-copy address arithmetic, no exchange of row descriptors).  Shared memory is piece-major, so the 32
-  // lanes of one copy instruction write 512 contiguous bytes and the 32 lanes of a 128-bit read fetch 512
-  // contiguous bytes: conflict-free both ways.  (cp.async requests are not merged across lanes on the way to L2
-  // — ncu counts one sector request per 16-byte copy whichever lane issues it — so a row's 128 bytes cost the
-  // same 8 requests as when 8 neighbouring lanes covered it in one instruction.)
-  const u32 my_pieces = (u32)(((u64)rlen + KPP - 1) / KPP);   // 16-byte pieces of this lane's stream
-  const unsigned char* src = reinterpret_cast<const unsigned char*>(keys) + (u64)a * sizeof(T);
-  const unsigned st0 = (unsigned)__cvta_generic_to_shared(wsm) + (unsigned)(lane * 16);
+  // Piece bookkeeping in 16-byte units (32-bit: covers 64 GB of keys).  Rows longer than
+  // 2^32 pieces cannot occur below that size either.
+  u32* rowg = reinterpret_cast<u32*>(wsm + SSTAGES * STAGE_BYTES);   // first 16-byte piece of each row
+  u32* rownp = rowg + 32;                                              // pieces in each row
+  __syncwarp();
+  rowg[lane] = (u32)((u64)a / KPP);
+  rownp[lane] = (u32)(((u64)rlen + KPP - 1) / KPP);
+  __syncwarp();
+  const int prow = lane >> 3, piece = lane & 7;
+  u32 g0[8], np[8];   // this lane's 8 (row, piece) streams: first piece index, pieces available
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int row = prow + 4 * q;
+    g0[q] = rowg[row] + (u32)piece;
+    const u32 rp = rownp[row];
+    np[q] = rp > (u32)piece ? (rp - (u32)piece + 7u) / 8u : 0u;   // chunks in which this piece exists
+  }
+  const unsigned char* kb = reinterpret_cast<const unsigned char*>(keys);
+  const unsigned st0 = (unsigned)__cvta_generic_to_shared(wsm) + (unsigned)(prow * ROW_BYTES + piece * 16);
   const u32 nchunks = (u32)(((u64)maxlen + SW - 1) / SW);
-  // chunks every lane has in full (no predicates needed while c is below this)
+  // chunks every lane has in full (the vector path of the consumer below)
   I minlen = rlen;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -252,24 +269,19 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
     if (t < minlen) minlen = t;
   }
   const u32 full_chunks = (u32)((u64)minlen / SW);
+  // One predicated 16-byte copy per (row, piece) stream: address = chunk base + piece index * 16.
   // Pieces are whole 16-byte units; the one that holds the array's last key may extend past it
   // (the buffer is readable up to the next 16-byte boundary, include/rmi_b200.h), and nothing
   // past a lane's range is ever consumed.
   auto issue = [&](u32 c) {
     const unsigned st = st0 + (c % SSTAGES) * STAGE_BYTES;
-    const unsigned char* cb = src + (u64)c * 128u;
-    if (c < full_chunks) {
+    const unsigned char* cb = kb + (u64)c * 128u;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n"
-                     ::"r"(st + (unsigned)(q * PIECE_STRIDE)), "l"(cb + q * 16), "l"(l2_policy) : "memory");
-    } else {
-      const u32 done = c * 8u;                                      // pieces before this chunk
-      const u32 left = my_pieces > done ? my_pieces - done : 0u;    // pieces of this lane in this chunk and beyond
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %2, %3;\n\t@p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %4;\n\t}\n"
-                     ::"r"(st + (unsigned)(q * PIECE_STRIDE)), "l"(cb + q * 16), "r"(left), "r"((u32)q), "l"(l2_policy) : "memory");
+    for (int q = 0; q < 8; ++q) {
+      u64 src;
+      asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(src) : "r"(g0[q]), "l"(cb));
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %4;\n\t}\n"
+                   ::"r"(st + (unsigned)(q * 4 * ROW_BYTES)), "l"(src), "r"(c), "r"(np[q]), "l"(l2_policy) : "memory");
     }
     cp_async_commit();
   };
@@ -298,7 +310,7 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
     if (c + (SSTAGES - 1) < nchunks) issue(c + (SSTAGES - 1)); else cp_async_commit();
     cp_async_wait<SSTAGES - 1>();
     __syncwarp();
-    const unsigned char* row = wsm + (int)(c % SSTAGES) * STAGE_BYTES + lane * 16;   // this lane's piece 0; piece q at + q * PIECE_STRIDE
+    const unsigned char* row = wsm + (int)(c % SSTAGES) * STAGE_BYTES + lane * ROW_BYTES;   // this lane's row; piece q at + q * PIECE_STRIDE
     const I cbase = (I)c * (I)SW;
     // A chunk is "full" when every lane still has all SW positions on the high side.  The low side
     // matters in chunk 0 only (a stream starts at the 16-byte piece that holds index b, so up to
@@ -973,6 +985,20 @@ __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const S
   constexpr int PPM = leaf_params_per_model(LEAF);
   constexpr int FWD_DEPTH = RMI_FWD_DEPTH;
   constexpr int REC = 16 + ((PPM * 8 + 15) / 16) * 16;   // {lo, hi} + parameters, 16-byte aligned
+#if RMI_FWD_BULK
+  // the warp's ring memory during the forward pass: FB_STAGES key tiles | 32 leaf descriptors | FB_STAGES mbarriers
+  constexpr int FB_STAGES = 3, FB_TILE_BYTES = 2048;
+  constexpr int DESC_OFF = FB_STAGES * FB_TILE_BYTES;
+  static_assert(DESC_OFF + 32 * REC + FB_STAGES * 8 <= WARP_STREAM_BYTES, "forward-pass layout exceeds the warp's ring memory");
+  unsigned char* const dsc = wsm + DESC_OFF;
+  const unsigned fb_stage0 = (unsigned)__cvta_generic_to_shared(wsm);
+  const unsigned fb_bar0 = fb_stage0 + (unsigned)(DESC_OFF + 32 * REC);
+  unsigned fb_uses = 0;   // bit s = parity of the number of completed uses of stage s
+  u64 fb_policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(fb_policy));
+#else
+  unsigned char* const dsc = wsm;
+#endif
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned le_mask = (2u << lane) - 1u;            // lanes at or below this one
@@ -981,8 +1007,15 @@ __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const S
   unsigned todo = __ballot_sync(FULL, mine);
   if (todo == 0) return;
   __syncwarp();
+#if RMI_FWD_BULK
+  if (lane == 0) {
+#pragma unroll
+    for (int sidx = 0; sidx < FB_STAGES; ++sidx) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fb_bar0 + sidx * 8u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#endif
   {
-    unsigned char* rec = wsm + lane * REC;
+    unsigned char* rec = dsc + lane * REC;
     *reinterpret_cast<ulonglong2*>(rec) = make_ulonglong2((u64)lo, (u64)hi);
 #pragma unroll
     for (int q = 0; q < PPM; ++q) reinterpret_cast<double*>(rec + 16)[q] = f[q];
@@ -1004,12 +1037,12 @@ __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const S
     const int q_last = 31 - __clz(seg_mask);
     todo &= ~seg_mask;
     unsigned left = seg_mask & ~(1u << q);               // leaves of the segment after the current one
-    const I seg_lo = (I)reinterpret_cast<const ulonglong2*>(wsm + q * REC)->x;
-    const I seg_hi = (I)reinterpret_cast<const ulonglong2*>(wsm + q_last * REC)->y;
-    I hi_q = (I)reinterpret_cast<const ulonglong2*>(wsm + q * REC)->y;
+    const I seg_lo = (I)reinterpret_cast<const ulonglong2*>(dsc + q * REC)->x;
+    const I seg_hi = (I)reinterpret_cast<const ulonglong2*>(dsc + q_last * REC)->y;
+    I hi_q = (I)reinterpret_cast<const ulonglong2*>(dsc + q * REC)->y;
     double cf[PPM];
 #pragma unroll
-    for (int t = 0; t < PPM; ++t) cf[t] = reinterpret_cast<const double*>(wsm + q * REC + 16)[t];
+    for (int t = 0; t < PPM; ++t) cf[t] = reinterpret_cast<const double*>(dsc + q * REC + 16)[t];
     I w_err = 0, w_run = 0;
     I carry_F = (I)(seg_lo + baseI);
     T carry_k = T();
@@ -1023,11 +1056,106 @@ __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const S
       if (left) {
         q = __ffs(left) - 1;
         left &= left - 1;
-        hi_q = (I)reinterpret_cast<const ulonglong2*>(wsm + q * REC)->y;
+        hi_q = (I)reinterpret_cast<const ulonglong2*>(dsc + q * REC)->y;
 #pragma unroll
-        for (int t = 0; t < PPM; ++t) cf[t] = reinterpret_cast<const double*>(wsm + q * REC + 16)[t];
+        for (int t = 0; t < PPM; ++t) cf[t] = reinterpret_cast<const double*>(dsc + q * REC + 16)[t];
       }
     };
+#if RMI_FWD_BULK
+    // ---- key tiles by 1-D bulk copy (TMA engine, cp.async.bulk + mbarrier): the segment is one contiguous byte range, so
+    // ONE elected lane moves it through shared memory in 2 KB tiles, FB_STAGES tiles in flight, and every step reads its
+    // 32 keys from the landed tile.  Unlike register look-ahead (whose loads share the warp's six scoreboards, so a wait
+    // for the oldest load also waits for the youngest) the depth here is real, and a tile costs ~10 instructions.
+    constexpr int KPP = 16 / (int)sizeof(T);
+    constexpr int FB_TILE_KEYS = FB_TILE_BYTES / (int)sizeof(T);
+    const I a0 = seg_lo & ~(I)(KPP - 1);                                  // 16-byte aligned start of the stream
+    const I end_al = (I)((seg_hi + (I)(KPP - 1)) & ~(I)(KPP - 1));        // readable up to the next 16-byte boundary (include/rmi_b200.h)
+    const u32 ntiles = (u32)(((u64)(end_al - a0) + FB_TILE_KEYS - 1) / FB_TILE_KEYS);
+    auto issue_tile = [&](u32 t) {
+      if (lane == 0) {
+        const I t0 = a0 + (I)t * (I)FB_TILE_KEYS;
+        const u32 left = (u32)((u64)(end_al - t0) * sizeof(T));
+        const u32 bytes = left < (u32)FB_TILE_BYTES ? left : (u32)FB_TILE_BYTES;
+        const unsigned bar = fb_bar0 + (t % FB_STAGES) * 8u;
+        const unsigned dst = fb_stage0 + (t % FB_STAGES) * (unsigned)FB_TILE_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(dst), "l"(keys + t0), "r"(bytes), "r"(bar), "l"(fb_policy) : "memory");
+      }
+    };
+    for (u32 t = 0; t < (u32)FB_STAGES && t < ntiles; ++t) issue_tile(t);
+    I pos = a0;
+    I Fi = (I)(a0 + (I)lane + baseI);                 // global index of this lane's key in the current step
+    for (u32 t = 0; t < ntiles; ++t) {
+      {   // wait until tile t has landed (its stage's phase parity = parity of the stage's use count)
+        const unsigned bar = fb_bar0 + (t % FB_STAGES) * 8u;
+        const unsigned parity = (fb_uses >> (t % FB_STAGES)) & 1u;
+        unsigned ok = 0;
+        do {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        } while (!ok);
+        fb_uses ^= 1u << (t % FB_STAGES);
+      }
+      const unsigned char* tile = wsm + (t % FB_STAGES) * FB_TILE_BYTES;
+#pragma unroll 4
+      for (int sidx = 0; sidx < FB_TILE_KEYS / 32; ++sidx) {
+        if (pos >= seg_hi) break;                         // warp-uniform
+        const T k = *reinterpret_cast<const T*>(tile + (sidx * 32 + lane) * (int)sizeof(T));
+        const double x = Key<T>::as_float(k);
+        if (!DUPS && pos >= seg_lo && (I)(hi_q - pos) >= (I)32) {
+          // the whole step lies inside leaf q (the common case: 5 of 6 steps at 190 keys per leaf)
+          const I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, x, nI);
+          const I e = pred > Fi ? pred - Fi : Fi - pred;
+          w_err = e > w_err ? e : w_err;
+          pos += 32;
+          Fi += 32;
+          continue;
+        }
+        const I i = pos + (I)lane;
+        const I step_end = (seg_hi - pos) > (I)32 ? (I)(pos + 32) : seg_hi;
+        const bool valid = i >= seg_lo && i < step_end;
+        I F = Fi, len = 0;
+        bool pend = valid, pend_run = false;
+        if (DUPS) {
+          T kp = __shfl_up_sync(FULL, k, 1);
+          if (lane == 0) kp = carry_k;
+          const bool starts = valid && (i == seg_lo || k != kp);   // a segment's (and every leaf's) first key starts a run
+          const unsigned sm = __ballot_sync(FULL, starts);
+          const unsigned below = sm & le_mask;
+          F = below ? (I)(pos + baseI + (I)(31 - __clz(below))) : carry_F;
+          I Fm1 = __shfl_up_sync(FULL, F, 1);
+          if (lane == 0) Fm1 = carry_F;
+          // the run BEFORE a run start ends here; its length belongs to the leaf of the key before this one
+          pend_run = starts && i != seg_lo;
+          len = (I)(Fi - Fm1);
+          const int lastv = (int)(step_end - pos) - 1;
+          carry_F = __shfl_sync(FULL, F, lastv);
+          carry_k = __shfl_sync(FULL, k, lastv);
+        }
+        for (;;) {
+          const I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(cf, x, nI);
+          I e = pred > F ? pred - F : F - pred;
+          const bool take = pend && i < hi_q;
+          e = take ? e : (I)0;
+          w_err = e > w_err ? e : w_err;
+          pend = pend && !take;
+          if (DUPS) {
+            const bool take_run = pend_run && i <= hi_q;
+            const I l = take_run ? len : (I)0;
+            w_run = l > w_run ? l : w_run;
+            pend_run = pend_run && !take_run;
+          }
+          if (hi_q >= step_end) break;                    // warp-uniform: leaf q covers the rest of the step
+          leave_leaf();
+        }
+        pos = step_end;
+        Fi += 32;
+      }
+      __syncwarp();                                        // every lane is done with the tile: its stage may be refilled
+      if (t + FB_STAGES < ntiles) issue_tile(t + FB_STAGES);
+    }
+#else
     // FWD_DEPTH + 1 register slots: the step that consumes slot u refills the slot the PREVIOUS step consumed, so a
     // load never targets the register it is just reading (with FWD_DEPTH slots the compiler loads into a temporary
     // and copies it — and the copy waits for the load: measured, it serialised every step on the load latency)
@@ -1103,6 +1231,7 @@ __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const S
         Fi += 32;
       }
     }
+#endif
     // the segment's last leaf: its final run counts only if another run follows it in the data set
     if (DUPS && (u64)seg_hi + sh.base < sh.n_global) {
       const I l = (I)((I)(seg_hi + baseI) - carry_F);

@@ -168,3 +168,35 @@ def test_python_mirrors_of_the_public_api_on_gpu(tmp_path, monkeypatch):
     out = build_and_check(work, keys)
     assert out.startswith("ok") and int(out.split()[2]) <= 8
     assert f"const size_t RMI_SIZE = {rmi_b200.rmi_size(rmi, num_spline_points=knots.shape[0])};" in open(os.path.join(work, "rmi.h")).read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("top,bf", [("radix", 1024), ("radix18", 4096), ("robust_linear", 256), ("cubic", 1000), ("bradix", 512),
+                                    ("histogram", 128)])
+def test_stats_batch_equals_separate_builds(top, bf):
+    """rmi_train_stats_batch (one top fit + one boundary pass for every leaf type of a (top, branching factor) group —
+    the optimizer's unit of work) must report exactly what separate stats-only builds report, and the oracle's numbers."""
+    import oracle
+    import rmi_b200
+    oracle.build()
+    keys = datasets.with_duplicates(datasets.lognormal_u64(300_000, seed=21))
+    ds = rmi_b200.RMITrainingData(keys)
+    leaves = ["linear", "cubic", "linear_spline"]
+    try:
+        batch = rmi_b200.train_stats_batch(ds, top, leaves, bf)
+    except rmi_b200.RMIPanic:
+        with pytest.raises(rmi_b200.RMIPanic):
+            for leaf in leaves:
+                rmi_b200.train(ds, f"{top},{leaf}", bf, rmi_b200.FLAG_STATS_ONLY, counts=False)
+        return
+    for leaf, b in zip(leaves, batch):
+        one = rmi_b200.train(ds, f"{top},{leaf}", bf, rmi_b200.FLAG_STATS_ONLY, counts=False)
+        for f in ("model_max_error", "model_max_error_idx", "model_avg_error", "model_avg_l2_error", "model_avg_log2_error",
+                  "model_max_log2_error", "branching_factor", "l0_model", "l1_model"):
+            assert getattr(b, f) == getattr(one, f), (leaf, f, getattr(b, f), getattr(one, f))
+        assert list(b.l0_fparams) == list(one.l0_fparams) and list(b.l0_iparams) == list(one.l0_iparams)
+        assert rmi_b200.rmi_size(b) == rmi_b200.rmi_size(one)
+        if top in ("radix", "radix18", "bradix", "histogram"):      # tops without an order-dependent float fit: the oracle's exact numbers
+            o = oracle.train(keys, f"{top},{leaf}", bf)
+            if leaf != "cubic":
+                assert (b.model_max_error, b.model_avg_error) == (o.max_error, o.avg_error)

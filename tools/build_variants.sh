@@ -5,10 +5,9 @@ set -o pipefail
 #   tools/build_variants.sh            # all variants below
 #   tools/build_variants.sh s3 t64     # a subset
 declare -A DEFS=(
-  [b5]="-DRMI_LEAF_MIN_BLOCKS=5"         # 5 blocks of 128 lanes per SM for every instantiation (96 registers)
-  [b4]="-DRMI_LEAF_MIN_BLOCKS=4"         # 4 blocks per SM: fewer leaves in flight between the two reads of a key
+  [rf]="-DRMI_FWD_BULK=0"                # forward pass by register look-ahead loads instead of bulk-copy tiles
   [lsf]="-DRMI_LANE_SERIAL_FORWARD"      # round 1's lane-serial forward pass behind this round's fit pass
-  [d4]="-DRMI_FWD_DEPTH=4"               # forward pass: 4 loads in flight per warp instead of 8
+  [s3]="-DRMI_SSTAGES=3 -DRMI_LEAF_MIN_BLOCKS=4"   # three copy stages in the fit ring (4 blocks per SM)
   [pb]="-DRMI_PIPELINED_BOUNDS"          # leaf-boundary search sliced and overlapped with the leaf kernel's slices
 )
 names=("$@")

@@ -10,6 +10,9 @@ tail -3 $out/${tag}_pytest_parity.log
 timeout 600 python -m pytest tests/test_gpu_sharded.py -x -q -m gpu -k "one_call or single_rank" > $out/${tag}_pytest_onecall.log 2>&1
 echo "pytest one-call exit $?" >> $out/${tag}_pytest_onecall.log
 tail -5 $out/${tag}_pytest_onecall.log
+timeout 900 python -m pytest tests/test_optimizer.py tests/test_gpu_fullsize.py -x -q -m gpu -k "stats_batch or exact" > $out/${tag}_pytest_new.log 2>&1
+echo "pytest new exit $?" >> $out/${tag}_pytest_new.log
+tail -4 $out/${tag}_pytest_new.log
 f=$out/${tag}_variants.jsonl
 : > $f
 for lib in rmi_b200/lib/librmi_b200*.so; do
