@@ -742,15 +742,7 @@ int train_typed(const rmi_dataset* ds, const ModelName& top, const ModelName& le
       cudaEventRecord(evp[0], st);
       if (host_status == 0 && rc == RMI_OK) {
         // injected top parameters are not known to be monotone: take the streaming pass, which checks
-        // (RMI_PIPELINED_BOUNDS builds: only the five boundaries needed up front are searched here, the rest slice
-        //  by slice next to the leaf kernel; otherwise prepare_pipelined_bounds declines and the phase runs whole)
-        PipelinedBounds pb;
-        if (l0_over == nullptr && prepare_pipelined_bounds<T>(L, keys, n, top.kind, d_top, N, d_S, d_aux)) {
-          pb.top_kind = top.kind; pb.d_top = d_top; pb.d_S = d_S;
-          L.pb = &pb;
-        } else {
-          compute_leaf_bounds<T>(L, keys, n, top.kind, d_top, N, d_S, d_aux, /*allow_search=*/l0_over == nullptr);
-        }
+        compute_leaf_bounds<T>(L, keys, n, top.kind, d_top, N, d_S, d_aux, /*allow_search=*/l0_over == nullptr);
         cudaEventRecord(evp[1], st);
         {
           Shard<T> whole = whole_array<T>(n);

@@ -81,20 +81,9 @@ struct LeafCopyOut {
   mutable int used = 0;                           // slices actually launched (set by fit_leaves)
 };
 
-// Optional (RMI_PIPELINED_BOUNDS builds, single GPU, monotone-by-construction tops): the leaf-boundary
-// search is not a phase of its own but is cut into the same slices as the leaf kernel and runs on the
-// slices' streams, so that the search of slice c+1 overlaps the leaf kernel of slice c.  Set by
-// prepare_pipelined_bounds(); consumed by fit_leaves().
-struct PipelinedBounds {
-  int top_kind = -1;
-  const TopModel* d_top = nullptr;
-  u64* d_S = nullptr;
-};
-
 struct Launch {
   cudaStream_t stream;
   int num_sms;
-  const PipelinedBounds* pb = nullptr;
   const LeafCopyOut* copy = nullptr;   // optional sliced launch + overlapped result copies (fit_leaves)
   // optional fork/join resources for the long-leaf kernel (kernels_leaf.cu); all null = disabled
   cudaStream_t side = nullptr;       // high-priority stream
@@ -125,12 +114,6 @@ template <class T> void check_sorted(const Launch& L, const T* keys, u64 n, u64 
 template <class T>
 void compute_leaf_bounds(const Launch& L, const T* keys, u64 n, int top_kind, const TopModel* d_top, u64 num_leaves,
                          u64* d_S, BuildAux* d_aux, bool allow_search);
-// RMI_PIPELINED_BOUNDS builds only (returns false otherwise, or when the top model is not monotone by
-// construction): writes S[0], S[1], S[N/2], S[N-1], S[N], derives the split and lists the two end leaves
-// if they are long; the remaining boundaries are searched slice by slice inside fit_leaves (L.pb).
-template <class T>
-bool prepare_pipelined_bounds(const Launch& L, const T* keys, u64 n, int top_kind, const TopModel* d_top, u64 num_leaves,
-                              u64* d_S, BuildAux* d_aux);
 // Fused per-leaf pass: closed-form fit (build_models_from), empty-leaf constants, forward
 // pass / max error, lower-bound widening (two_layer.rs:20-99, :186-259,
 // lower_bound_correction.rs:91-137).  Writes N x ppm params, N errors, N counts.

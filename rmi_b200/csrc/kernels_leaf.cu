@@ -47,6 +47,9 @@ constexpr int BOUNDS_THREADS = 256;
 #endif
 #define RMI_LEAF_BOUNDS __launch_bounds__(RMI_LEAF_THREADS, RMI_LEAF_MIN_BLOCKS)
 constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
+#ifndef RMI_COOP_FORWARD
+#define RMI_COOP_FORWARD 0   // 1 = warp-cooperative forward pass (coop_forward) instead of the lane-serial one
+#endif
 #ifndef RMI_FWD_BULK
 #define RMI_FWD_BULK 1   // forward pass fed by 1-D bulk copies (cp.async.bulk + mbarrier); 0 = register look-ahead
 #endif
@@ -1246,63 +1249,6 @@ __device__ __forceinline__ void coop_forward(const T* __restrict__ keys, const S
 constexpr u64 LONG_LEAF_KEYS = 2048;   // leaves longer than this go to the long-leaf kernel (linear leaves)
 constexpr int LONG_LEAF_SMEM = 227 * 1024;   // its blocks ask for a whole SM's shared memory: nothing else is resident beside the chain
 
-#ifdef RMI_PIPELINED_BOUNDS
-// k_bounds_search over the boundaries j_begin .. j_begin + count - 1 only (one slice of the leaf range).
-template <class T, int TOP>
-__global__ void __launch_bounds__(BOUNDS_THREADS)
-k_bounds_search_range(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr, u64 N, u64 j_begin,
-                      u64 count, u64* __restrict__ S) {
-  TopModel m = *top_ptr;
-  u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  u64 j = j_begin + t;
-  if (j > N) return;
-  u64 lo = 0, hi = n;
-  if (j == N) lo = n;
-  else if (j > 0) {
-    while (lo < hi) {
-      u64 mid = lo + ((hi - lo) >> 1);
-      if (top_predict<TOP>(m, keys[mid]) >= j) hi = mid; else lo = mid + 1;
-    }
-  }
-  S[j] = lo;
-}
-// The five boundaries everything else needs up front: S[0], S[1], S[N/2], S[N-1], S[N] (three searches on three
-// lanes), and the long-leaf list restricted to the two END leaves — the ones a regression top model overfills;
-// any other long leaf stays in the bulk kernel (its solo path), exactly as when the list overflows.
-template <class T, int TOP>
-__global__ void k_prepare_pipelined(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr, u64 N,
-                                    u64* __restrict__ S, u32* __restrict__ long_list) {
-  TopModel m = *top_ptr;
-  const int lane = threadIdx.x;
-  if (lane < 3) {
-    const u64 j = lane == 0 ? N / 2 : (lane == 1 ? (N > 1 ? 1 : N) : N - 1);
-    u64 lo = 0, hi = n;
-    if (j >= N) lo = n;
-    else if (j > 0) {
-      while (lo < hi) {
-        u64 mid = lo + ((hi - lo) >> 1);
-        if (top_predict<TOP>(m, keys[mid]) >= j) hi = mid; else lo = mid + 1;
-      }
-    }
-    S[j] = lo;
-  }
-  __syncwarp();
-  if (lane == 0) {
-    S[0] = 0;
-    S[N] = n;
-    __threadfence_block();
-    if (long_list) {
-      u32 cnt = 0;
-      const u64 first_len = S[N > 1 ? 1 : N];                // leaf 0 = [0, S[1])
-      const u64 last_len = n - S[N - 1];                      // leaf N-1 = [S[N-1], n)
-      if (first_len > LONG_LEAF_KEYS) long_list[1 + cnt++] = 0u;
-      if (N > 1 && last_len > LONG_LEAF_KEYS) long_list[1 + cnt++] = (u32)(N - 1);
-      long_list[0] = cnt;
-    }
-  }
-}
-#endif
 
 // Owned leaves longer than LONG_LEAF_KEYS -> list (count in list[0], capped at LONG_LEAF_CAP + 1).
 template <class T>
@@ -1366,15 +1312,7 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   if (!__syncthreads_or(live ? 1 : 0)) { if (bad) set_status(aux, bad); return; }
   for (int c = threadIdx.x; c < RCP_TABLE; c += blockDim.x) s_rcp[c] = c ? __drcp_rn((double)c) : 0.0;
   __syncthreads();
-#ifdef RMI_PIPELINED_BOUNDS
-  if (long_mode == 0 && long_active && live && (g_hi - g_lo) > LONG_LEAF_KEYS) {   // built by the long-leaf kernel IF it is listed
-    bool listed = false;
-    for (u32 q = 0; q < n_long; ++q) listed |= long_list[1 + q] == (u32)j;
-    if (listed) live = false;
-  }
-#else
   if (long_mode == 0 && long_active && live && (g_hi - g_lo) > LONG_LEAF_KEYS) live = false;   // built by the long-leaf kernel
-#endif
 
   // which half does leaf j belong to (two_layer.rs:147-175), in global indices
   u64 half_lo, half_hi, first_leaf;
@@ -1447,8 +1385,10 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   // row ring a second time.  Owners park their leaf's range and parameters in the warp's shared
   // memory (the ring is idle now); results return to the owner lane.
   I max_err = 0, run_max = 0;
-#ifdef RMI_LANE_SERIAL_FORWARD
-  // (experiment variant: round 1's forward pass — every lane walks its own leaf through the copy ring a second time)
+#if !RMI_COOP_FORWARD
+  // Forward pass: every lane walks its own leaf through the copy ring a second time.  Measured against the two
+  // warp-cooperative variants below (coop_forward; profiles/r02_forward_variants.md): 0.533 ms for the leaf kernel
+  // of the headline build against 0.619 (bulk-copy tiles) and 0.682 (register look-ahead).
   {
     const u64 pol_fwd = l2_policy_of((mode_word >> 6) & 3);
     T pk = (live && g_lo == 0 && g_hi > 0) ? keys[0] : prev_key;
@@ -1728,22 +1668,6 @@ void launch_bounds_impl(const Launch& L, const T* keys, u64 n, const TopModel* d
   count_launch();
 }
 
-#ifdef RMI_PIPELINED_BOUNDS
-template <class T>
-void search_bounds_range(int top_kind, cudaStream_t st, const T* keys, u64 n, const TopModel* d_top, u64 N, u64 j_begin,
-                         u64 count, u64* d_S) {
-  if (count == 0) return;
-  const unsigned g = (unsigned)((count + BOUNDS_THREADS - 1) / BOUNDS_THREADS);
-  switch (top_kind) {
-    case M_RADIX: k_bounds_search_range<T, M_RADIX><<<g, BOUNDS_THREADS, 0, st>>>(keys, n, d_top, N, j_begin, count, d_S); break;
-    case M_RADIX_TABLE: k_bounds_search_range<T, M_RADIX_TABLE><<<g, BOUNDS_THREADS, 0, st>>>(keys, n, d_top, N, j_begin, count, d_S); break;
-    case M_BRADIX: k_bounds_search_range<T, M_BRADIX><<<g, BOUNDS_THREADS, 0, st>>>(keys, n, d_top, N, j_begin, count, d_S); break;
-    case M_HISTOGRAM: k_bounds_search_range<T, M_HISTOGRAM><<<g, BOUNDS_THREADS, 0, st>>>(keys, n, d_top, N, j_begin, count, d_S); break;
-    default: k_bounds_search_range<T, M_LINEAR><<<g, BOUNDS_THREADS, 0, st>>>(keys, n, d_top, N, j_begin, count, d_S); break;
-  }
-  count_launch();
-}
-#endif
 
 // g_rcp_far is per device; filled once, synchronously, before the first leaf kernel on that device.
 void ensure_rcp_far() {
@@ -1790,11 +1714,9 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
     // outside [0, N)) are single serial chains: they get their own one-warp blocks on a
     // high-priority stream, each with an SM to itself (a serial FP64 chain slows down with
     // every co-resident warp that shares its issue port), concurrently with the bulk kernel.
-    if (!L.pb) {   // (pipelined bounds: prepare_pipelined_bounds already listed the long end leaves)
-      cudaMemsetAsync(L.d_long, 0, sizeof(u32), L.stream);
-      k_find_long<T><<<(unsigned)((N + BOUNDS_THREADS - 1) / BOUNDS_THREADS), BOUNDS_THREADS, 0, L.stream>>>(sh, N, d_S, L.d_long);
-      count_launch();
-    }
+    cudaMemsetAsync(L.d_long, 0, sizeof(u32), L.stream);
+    k_find_long<T><<<(unsigned)((N + BOUNDS_THREADS - 1) / BOUNDS_THREADS), BOUNDS_THREADS, 0, L.stream>>>(sh, N, d_S, L.d_long);
+    count_launch();
     cudaEventRecord(L.ev_fork, L.stream);
     cudaStreamWaitEvent(L.side, L.ev_fork, 0);
     k_leaf<T, I, LEAF, DUPS><<<LONG_LEAF_CAP, 32, LONG_LEAF_SMEM, L.side>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts, L.d_long,
@@ -1806,9 +1728,6 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
   const LeafCopyOut* co = L.copy;
   int K = (co && co->slices > 1) ? (co->slices < MAX_LEAF_SLICES ? co->slices : MAX_LEAF_SLICES) : 1;
   if (blocks < (u64)K * 64 || blocks >= 0xffffffffull) K = 1;   // too small to be worth slicing
-#ifdef RMI_PIPELINED_BOUNDS
-  if (L.pb && K == 1) search_bounds_range<T>(L.pb->top_kind, L.stream, keys, sh.n_global, L.pb->d_top, N, 0, N + 1, L.pb->d_S);   // unsliced: the whole search after all
-#endif
   if (K == 1) {
     k_leaf<T, I, LEAF, DUPS><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts,
                                                                                 long_list, l2_mode, 0u, (u32)blocks);
@@ -1838,20 +1757,6 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
     const u32 cnt = total - off < per ? total - off : per;
     cudaStream_t st = co->streams[c];
     cudaStreamWaitEvent(st, co->ev_ready, 0);
-#ifdef RMI_PIPELINED_BOUNDS
-    if (L.pb) {   // this slice's boundaries (front and back leaf ranges, each + the boundary that closes it)
-      const u64 pf0 = (u64)(off / 2) * LEAF_THREADS, pf1 = (u64)((off + cnt + 1) / 2) * LEAF_THREADS;
-      const u64 pnb = (off + cnt) / 2 - off / 2;
-      const u64 pb1 = ((u64)total - off / 2) * LEAF_THREADS, pb0 = ((u64)total - off / 2 - pnb) * LEAF_THREADS;
-      auto range = [&](u64 l0, u64 l1) {   // boundaries l0 .. min(l1, N) inclusive
-        if (l1 > N) l1 = N;
-        if (l0 > l1) return;
-        search_bounds_range<T>(L.pb->top_kind, st, keys, sh.n_global, L.pb->d_top, N, l0, l1 - l0 + 1, L.pb->d_S);
-      };
-      range(pf0, pf1);
-      if (pnb) range(pb0, pb1);
-    }
-#endif
     k_leaf<T, I, LEAF, DUPS><<<cnt, LEAF_THREADS, smem, st>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts, long_list,
                                                               l2_mode, off, total);
     count_launch();
@@ -1913,37 +1818,6 @@ void compute_leaf_bounds(const Launch& L, const T* keys, u64 n, int top_kind, co
     case M_HISTOGRAM: launch_bounds_impl<T, M_HISTOGRAM>(L, keys, n, d_top, N, d_S, d_aux, allow_search); break;
     default: break;
   }
-}
-
-template <class T>
-bool prepare_pipelined_bounds(const Launch& L, const T* keys, u64 n, int top_kind, const TopModel* d_top, u64 N, u64* d_S,
-                              BuildAux* d_aux) {
-#ifdef RMI_PIPELINED_BOUNDS
-  static const bool enabled = [] { const char* e = getenv("RMI_DEV_PIPELINED_BOUNDS"); return !e || atoi(e) != 0; }();
-  if (!enabled || !top_is_monotone_by_construction(top_kind) || n == 0 || N < 2 || N >= 0xffffffffull) return false;
-  u32* list = (L.side && L.ev_fork && L.ev_join) ? L.d_long : nullptr;
-  switch (top_kind) {
-    case M_RADIX: k_prepare_pipelined<T, M_RADIX><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, list); break;
-    case M_RADIX_TABLE: k_prepare_pipelined<T, M_RADIX_TABLE><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, list); break;
-    case M_BRADIX: k_prepare_pipelined<T, M_BRADIX><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, list); break;
-    case M_HISTOGRAM: k_prepare_pipelined<T, M_HISTOGRAM><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, list); break;
-    default: k_prepare_pipelined<T, M_LINEAR><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, list); break;
-  }
-  count_launch();
-  // the split (two_layer.rs:131-159) needs S[N/2] and two keys only
-  switch (top_kind) {
-    case M_RADIX: k_split<T, M_RADIX><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux, 1); break;
-    case M_RADIX_TABLE: k_split<T, M_RADIX_TABLE><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux, 1); break;
-    case M_BRADIX: k_split<T, M_BRADIX><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux, 1); break;
-    case M_HISTOGRAM: k_split<T, M_HISTOGRAM><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux, 1); break;
-    default: k_split<T, M_LINEAR><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux, 1); break;
-  }
-  count_launch();
-  return true;
-#else
-  (void)L; (void)keys; (void)n; (void)top_kind; (void)d_top; (void)N; (void)d_S; (void)d_aux;
-  return false;
-#endif
 }
 
 template <class T>
@@ -2028,7 +1902,6 @@ void leaf_statistics_merge(const Launch& L, const void* d_parts, int world, Buil
 }
 
 #define INST(T)                                                                                                  \
-  template bool prepare_pipelined_bounds<T>(const Launch&, const T*, u64, int, const TopModel*, u64, u64*, BuildAux*);   \
   template void compute_leaf_bounds<T>(const Launch&, const T*, u64, int, const TopModel*, u64, u64*, BuildAux*, bool); \
   template void fit_leaves<T>(const Launch&, const T*, const Shard<T>&, int, u64, const u64*, BuildAux*, double*, u64*, u64*);
 INST(u64)

@@ -5,10 +5,9 @@ set -o pipefail
 #   tools/build_variants.sh            # all variants below
 #   tools/build_variants.sh s3 t64     # a subset
 declare -A DEFS=(
-  [rf]="-DRMI_FWD_BULK=0"                # forward pass by register look-ahead loads instead of bulk-copy tiles
-  [lsf]="-DRMI_LANE_SERIAL_FORWARD"      # round 1's lane-serial forward pass behind this round's fit pass
-  [s3]="-DRMI_SSTAGES=3 -DRMI_LEAF_MIN_BLOCKS=4"   # three copy stages in the fit ring (4 blocks per SM)
-  [pb]="-DRMI_PIPELINED_BOUNDS"          # leaf-boundary search sliced and overlapped with the leaf kernel's slices
+  [cf]="-DRMI_COOP_FORWARD=1"                       # warp-cooperative forward pass fed by 1-D bulk copies (cp.async.bulk + mbarrier tiles)
+  [cfr]="-DRMI_COOP_FORWARD=1 -DRMI_FWD_BULK=0"     # the same fed by register look-ahead loads
+  [s3]="-DRMI_SSTAGES=3 -DRMI_LEAF_MIN_BLOCKS=4"    # three copy stages in the ring (4 blocks per SM)
 )
 names=("$@")
 [ ${#names[@]} -eq 0 ] && names=("${!DEFS[@]}")
