@@ -129,38 +129,45 @@ inline std::vector<RMIStatistics> measure_rmis(const std::vector<const rmi_datas
   // Unit of work = the configurations that share (top model, branching factor): rmi_train_stats_batch fits the top
   // model and derives the leaf boundaries once for the whole group (several configurations
   // per key pass).  Groups keep the order of their first member; results land at the configurations' own positions.
-  struct Group { std::string top; uint64_t bf; std::vector<std::string> leaves; std::vector<size_t> index; };
+  struct Group { std::string top; uint64_t bf; std::vector<std::string> leaves; std::vector<size_t> index; bool batched; };
   std::vector<Group> groups;
   static const bool batching = [] { const char* e = std::getenv("RMI_OPTIMIZER_NO_BATCH"); return !(e && e[0] == '1'); }();
   for (size_t i = 0; i < configs.size(); ++i) {
     const std::string& m = configs[i].first;
     const size_t comma = m.find(',');
     const std::string top = m.substr(0, comma), leaf = comma == std::string::npos ? "" : m.substr(comma + 1);
+    // Batching pays where the shared passes (top fit, boundary search) are a visible part of a configuration's cost:
+    // at small branching factors a configuration's time is its leaves' serial recurrences (n / bf keys per lane), and
+    // keeping such configurations apart lets the replicas balance them.
+    const bool batchable = batching && comma != std::string::npos && leaf.find(',') == std::string::npos &&
+                           configs[i].second >= 4096;
     Group* g = nullptr;
-    if (batching && comma != std::string::npos && leaf.find(',') == std::string::npos)
-      for (auto& c : groups) if (c.top == top && c.bf == configs[i].second && !c.leaves.empty()) { g = &c; break; }
+    if (batchable)
+      for (auto& c : groups) if (c.batched && c.top == top && c.bf == configs[i].second) { g = &c; break; }
     if (!g) {
-      groups.push_back(Group{top, configs[i].second, {}, {}});
+      groups.push_back(Group{batchable ? top : m, configs[i].second, {}, {}, batchable});
       g = &groups.back();
-      if (!(batching && comma != std::string::npos && leaf.find(',') == std::string::npos)) g->top = m;   // not a two-layer spec: trained (and rejected) on its own
     }
     g->leaves.push_back(leaf);
     g->index.push_back(i);
   }
+  // longest first: the smaller the branching factor, the longer the per-lane chains (results keep their own positions)
+  std::vector<size_t> order(groups.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return groups[a].bf < groups[b].bf; });
   std::atomic<size_t> next{0};
   std::atomic<bool> failed{false};
   std::vector<std::string> errors(replicas.size());
   auto worker = [&](size_t w) {
     const rmi_dataset* ds = replicas[w];
     for (;;) {
-      size_t gi = next.fetch_add(1);
-      if (gi >= groups.size() || failed.load()) return;
-      const Group& g = groups[gi];
+      size_t oi = next.fetch_add(1);
+      if (oi >= groups.size() || failed.load()) return;
+      const Group& g = groups[order[oi]];
       const size_t K = g.index.size();
       std::vector<rmi_result*> res(K, nullptr);
       int rc;
-      const bool two_layer = configs[g.index[0]].first != g.top;   // g.top holds the bare top-model name
-      if (two_layer) {
+      if (g.batched) {   // g.top holds the bare top-model name
         std::vector<const char*> names;
         for (auto& l : g.leaves) names.push_back(l.c_str());
         rc = rmi_train_stats_batch(ds, g.top.c_str(), names.data(), (int)K, g.bf, flags, res.data());
@@ -188,7 +195,7 @@ inline std::vector<RMIStatistics> measure_rmis(const std::vector<const rmi_datas
   if (replicas.size() == 1) worker(0);
   else {
     std::vector<std::thread> th;
-    for (size_t w = 0; w < replicas.size(); ++w) th.emplace_back(worker, w);
+    for (size_t w = 0; w < replicas.size(); ++w) th.emplace_back([&worker, w] { worker(w); rmi_thread_release(); });
     for (auto& t : th) t.join();
   }
   for (auto& e : errors) if (!e.empty()) throw std::runtime_error(e);

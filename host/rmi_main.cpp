@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -115,11 +116,13 @@ int main(int argc, char** argv) {
     std::stringstream dl(a.opt["--devices"]);
     std::string tok;
     std::map<int, const rmi_dataset*> on_device{{device, ds}};
-    bool first_tok = true;
+    bool loaded_counted = false;
     while (std::getline(dl, tok, ',')) {
       if (tok.empty()) continue;
       int d = std::atoi(tok.c_str());
-      if (first_tok) { first_tok = false; if (d == device) continue; }   // the loaded copy already has its worker
+      // the loaded copy already has its worker (replicas[0]): the FIRST mention of its device, wherever it
+      // stands in the list, is that worker; further mentions add workers on the same resident copy
+      if (d == device && !loaded_counted) { loaded_counted = true; continue; }
       auto it = on_device.find(d);
       if (it == on_device.end()) {
         rmi_dataset* rep = nullptr;
@@ -155,9 +158,12 @@ int main(int argc, char** argv) {
     return 0;
   }
 
-  struct stat st;
-  if (stat(data_dir.c_str(), &st) != 0) {   // main.rs:164-169
-    if (mkdir(data_dir.c_str(), 0777) != 0 && errno != EEXIST) die("The RMI data directory did not exist, and it could not be created.");
+  {   // main.rs:164-169: create_dir_all
+    std::error_code ec;
+    if (!std::filesystem::exists(data_dir, ec)) {
+      std::filesystem::create_directories(data_dir, ec);
+      if (ec) die("The RMI data directory did not exist, and it could not be created.");
+    }
   }
 
   auto train_one = [&](const std::string& models, uint64_t bf, rmi_result** out) {
@@ -193,10 +199,11 @@ int main(int argc, char** argv) {
     rmi_result* r = nullptr;
     CacheFixInfo cf;
     std::vector<SplinePoint> spline;
-    bool bounded = false;
+    bool bounded = false, sized = false;
     uint64_t bounded_build_ns = 0;
     if (a.has("--max-size")) {   // train_for_size, train/mod.rs:128-154
       uint64_t max_size = std::strtoull(a.opt["--max-size"].c_str(), nullptr, 10);
+      auto t0 = std::chrono::steady_clock::now();   // train_for_size times the sweep AND the final build (train/mod.rs:131-152)
       std::vector<RMIStatistics> pareto;
       try { pareto = find_pareto_efficient_configs(replicas, 1000, flags, verbose); } catch (std::exception& e) { die(e.what()); }
       free_replicas();
@@ -206,6 +213,8 @@ int main(int argc, char** argv) {
       std::fprintf(stderr, "Found RMI config %s %llu with size %llu and average log2 %g\n", pick->models.c_str(),
                    (unsigned long long)pick->branching_factor, (unsigned long long)pick->size, pick->average_log2_error);
       train_one(pick->models, pick->branching_factor, &r);
+      bounded_build_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+      sized = true;
     } else if (a.has("--bounded")) {
       // train_bounded (train/mod.rs:156-184): the serial cache-fix scan on the host, then the
       // ordinary GPU build with the spline's knots as the data set (their offsets are 0, 1, 2, ...)
@@ -244,7 +253,7 @@ int main(int argc, char** argv) {
     }
     print_stats(*r, num_rows);
     if (!a.has("--no-code")) {
-      const uint64_t bt = a.has("--zero-build-time") ? 0 : (bounded ? bounded_build_ns : r->build_time_ns);
+      const uint64_t bt = a.has("--zero-build-time") ? 0 : ((bounded || sized) ? bounded_build_ns : r->build_time_ns);
       try { output_rmi(ns, *r, data_dir, code_kt, !a.has("--no-errors"), bt, ".", bounded ? &cf : nullptr); }
       catch (std::exception& e) { die(e.what()); }
     }

@@ -63,7 +63,12 @@ enum {
   RMI_FLAG_LEAF_COUNTS = 8u,    /* also return l1_counts (keys per leaf as the error pass counts them,
                                    two_layer.rs:207-217); not part of TrainedRMI, used by parity checks */
   RMI_FLAG_SHARD_ROOT_ONLY = 16u /* rmi_shard_train: only rank 0 receives the leaf tables in host memory (every rank still
-                                   holds them on its device and gets the top model and the statistics) */
+                                   holds them on its device and gets the top model and the statistics).  When all ranks
+                                   run on one node, each rank copies the records of the leaves it owns straight into a
+                                   host region the ranks share (POSIX shared memory registered with CUDA): world PCIe
+                                   links in parallel.  Rank 0's l1_* pointers then point into that region, which has two
+                                   halves used alternately: they stay valid until the NEXT-BUT-ONE rmi_shard_train with
+                                   this flag on the same communicator (copy them if they must live longer). */
 };
 
 /* A device-resident sorted key set.  Replaces src/load.rs:132-157 load_data + the mmap
@@ -291,6 +296,11 @@ typedef struct {
 } rmi_config_stats;
 int rmi_find_pareto_efficient_configs(const rmi_dataset* const* replicas, int num_replicas, uint64_t restrict_to,
                                       uint32_t flags, rmi_config_stats* out, uint64_t capacity, uint64_t* out_count);
+
+/* rmi_train keeps one CUDA stream set per host thread and device (created on first use, reused by later builds).
+ * A worker thread that will not build again releases them with this call before it exits (the optimizer's per-replica
+ * workers do); the main thread's are reclaimed at process exit. */
+void rmi_thread_release(void);
 
 /* Message of the last failure on the calling thread ("" if none). */
 const char* rmi_last_error(void);

@@ -6,6 +6,9 @@
 // configurations on one shared RMITrainingData).  No host synchronisation happens between
 // the first kernel and the final result copy.
 #include <algorithm>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <atomic>
 #include <chrono>
 #include <cstdlib>
@@ -178,7 +181,15 @@ class PinnedCache {
         live_.erase(live_.begin() + i);
         break;
       }
-    while (free_.size() > 16) { cudaFreeHost(free_.front().first); free_.erase(free_.begin()); }
+    // keep at most 16 buffers AND at most 256 MiB of page-locked memory in the free list (a radix26/28 or histogram
+    // sweep would otherwise pin gigabytes for good)
+    size_t bytes = 0;
+    for (auto& e : free_) bytes += e.second;
+    while (!free_.empty() && (free_.size() > 16 || bytes > ((size_t)256 << 20))) {
+      bytes -= free_.front().second;
+      cudaFreeHost(free_.front().first);
+      free_.erase(free_.begin());
+    }
   }
  private:
   std::mutex mu_;
@@ -1028,6 +1039,13 @@ int train_entry(const rmi_dataset* ds, const char* model_spec, uint64_t N, uint3
 
 extern "C" {
 
+void rmi_thread_release(void) {
+  // streams / events this host thread created for its builds (kept per thread and device so that repeated builds do
+  // not re-create them): a worker thread that is about to exit hands them back here
+  t_build_ctx.release();
+  t_slices.release();
+}
+
 int rmi_train(const rmi_dataset* ds, const char* model_spec, uint64_t branch_factor, uint32_t flags, rmi_result** out) {
   return train_entry(ds, model_spec, branch_factor, flags, nullptr, 0, out);
 }
@@ -1106,6 +1124,18 @@ struct rmi_shard_build {
 struct rmi_shard_comm {
   ncclComm_t comm = nullptr;
   int world = 0, rank = 0, device = 0;
+  // Node-local shared result memory (RMI_FLAG_SHARD_ROOT_ONLY): a POSIX shared-memory region every rank maps and
+  // registers with CUDA, so that each rank copies the leaf records IT OWNS straight to the host buffer rank 0 reads —
+  // world PCIe links in parallel instead of rank 0 pulling all N records through its own.  Two halves, used alternately.
+  bool single_node = false;
+  uint32_t uid_hash = 0;
+  int shm_gen = 0;
+  unsigned char* shm = nullptr;
+  size_t shm_half = 0;            // bytes of one half
+  int parity = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_leaf_done = nullptr, ev_copy_done = nullptr;
+  unsigned* d_token = nullptr;    // 4 bytes: the payload of the "copies have landed" all-reduce
 };
 
 namespace {
@@ -1299,6 +1329,7 @@ int rmi_shard_build_create(const rmi_dataset* local, const rmi_shard_info* info,
 
 int rmi_shard_phase(rmi_shard_build* b, int phase) {
   if (!b) return fail(RMI_ERR_INVALID, "rmi_shard_phase: null build");
+  b->gather_mode = false;   // host-driven flow: the caller combines the leaf records with an all-reduce SUM of zero-filled arrays
   CUDA_TRY(cudaSetDevice(b->ds->device));
   switch (b->ds->key_type) {
     case RMI_KEY_U64: return shard_phase_typed<u64>(b, phase);
@@ -1434,12 +1465,98 @@ int rmi_shard_comm_create(const void* id128, int world, int rank, int device, rm
   c->world = world; c->rank = rank; c->device = device;
   ncclResult_t r = nc.CommInitRank(&c->comm, world, id, rank);
   if (r != ncclSuccess) { delete c; return fail(RMI_ERR_CUDA, std::string("ncclCommInitRank: ") + nc.GetErrorString(r)); }
+  for (size_t i = 0; i < sizeof(id); ++i) c->uid_hash = c->uid_hash * 16777619u ^ (unsigned char)id.internal[i];
+  // are all ranks on this host?  (all-gather of a host-name hash; the shared result region needs one node)
+  {
+    char host[256] = {0};
+    gethostname(host, sizeof(host) - 1);
+    unsigned long long hh = 1469598103934665603ull;
+    for (const char* p = host; *p; ++p) hh = (hh ^ (unsigned char)*p) * 1099511628211ull;
+    unsigned long long* d_h = nullptr;
+    std::vector<unsigned long long> all(world, 0);
+    bool ok = cudaMalloc((void**)&d_h, sizeof(unsigned long long) * world) == cudaSuccess &&
+              cudaMemcpy(d_h + rank, &hh, sizeof(hh), cudaMemcpyHostToDevice) == cudaSuccess &&
+              nc.AllGather(d_h + rank, d_h, 1, ncclUint64, c->comm, nullptr) == ncclSuccess &&
+              cudaDeviceSynchronize() == cudaSuccess &&
+              cudaMemcpy(all.data(), d_h, sizeof(unsigned long long) * world, cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(d_h);
+    c->single_node = ok;
+    for (int q = 0; q < world && ok; ++q) if (all[q] != hh) c->single_node = false;
+    ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_leaf_done, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming) == cudaSuccess &&
+         cudaMalloc((void**)&c->d_token, sizeof(unsigned)) == cudaSuccess && cudaMemset(c->d_token, 0, sizeof(unsigned)) == cudaSuccess;
+    if (!ok) { c->single_node = false; cudaGetLastError(); }
+  }
   *out = c;
+  return RMI_OK;
+}
+
+static void comm_release_shared(rmi_shard_comm* c) {
+  if (c->shm) {
+    cudaHostUnregister(c->shm);
+    munmap(c->shm, 2 * c->shm_half);
+    c->shm = nullptr; c->shm_half = 0;
+  }
+}
+
+// Collective over the communicator: make sure a shared, CUDA-registered host region of 2 x `half` bytes exists.
+static int comm_ensure_shared(rmi_shard_comm* c, size_t half, cudaStream_t st) {
+  if (c->shm && c->shm_half >= half) return RMI_OK;
+  const NcclApi& nc = nccl_api();
+  comm_release_shared(c);
+  half = (half + 4095) & ~(size_t)4095;
+  char name[64];
+  std::snprintf(name, sizeof name, "/rmi_b200_%08x_%d", c->uid_hash, ++c->shm_gen);
+  auto barrier = [&]() -> bool {
+    return nc.AllReduce(c->d_token, c->d_token, 1, ncclUint32, ncclMax, c->comm, st) == ncclSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+  };
+  void* base = MAP_FAILED;
+  bool ok = true;
+  if (c->rank == 0) {
+    shm_unlink(name);
+    int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    ok = fd >= 0 && ftruncate(fd, (off_t)(2 * half)) == 0;
+    if (ok) base = mmap(nullptr, 2 * half, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (fd >= 0) close(fd);
+    ok = ok && base != MAP_FAILED;
+  }
+  if (!barrier()) ok = false;          // the region exists (or rank 0 failed: found out below)
+  if (c->rank != 0) {
+    int fd = shm_open(name, O_RDWR, 0600);
+    ok = fd >= 0;
+    if (ok) base = mmap(nullptr, 2 * half, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (fd >= 0) close(fd);
+    ok = ok && base != MAP_FAILED;
+  }
+  if (!barrier()) ok = false;          // everyone has mapped it: the name can go
+  if (c->rank == 0) shm_unlink(name);
+  if (ok && cudaHostRegister(base, 2 * half, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); ok = false; }
+  // agree on the outcome (a rank that failed must not leave the others copying into a region it cannot see)
+  unsigned mine = ok ? 0u : 1u, any = 1u;
+  if (cudaMemcpy(c->d_token, &mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess && barrier() &&
+      cudaMemcpy(&any, c->d_token, sizeof(any), cudaMemcpyDeviceToHost) == cudaSuccess) {
+    unsigned zero = 0;
+    cudaMemcpy(c->d_token, &zero, sizeof(zero), cudaMemcpyHostToDevice);
+  }
+  if (any != 0) {
+    if (ok) cudaHostUnregister(base);
+    if (base != MAP_FAILED) munmap(base, 2 * half);
+    c->single_node = false;   // fall back for good: rank 0 pulls the whole result through its own link
+    return RMI_OK;
+  }
+  c->shm = (unsigned char*)base;
+  c->shm_half = half;
   return RMI_OK;
 }
 
 void rmi_shard_comm_destroy(rmi_shard_comm* c) {
   if (!c) return;
+  comm_release_shared(c);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev_leaf_done) cudaEventDestroy(c->ev_leaf_done);
+  if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
+  cudaFree(c->d_token);
   if (c->comm && nccl_api().ok) nccl_api().CommDestroy(c->comm);
   delete c;
 }
@@ -1450,6 +1567,9 @@ int rmi_shard_set_partition(rmi_shard_build* b, const uint64_t* bases, int world
     return fail(RMI_ERR_INVALID, "rmi_shard_set_partition: bad argument (1 <= world <= 63)");
   if (bases[rank] != b->info.base || bases[world] != b->info.n_global)
     return fail(RMI_ERR_INVALID, "rmi_shard_set_partition: bases do not agree with this rank's rmi_shard_info");
+  if (b->world == world && b->rank == rank && b->d_off && b->bases.size() == (size_t)world + 1 &&
+      std::equal(bases, bases + world + 1, b->bases.begin()))
+    return RMI_OK;   // unchanged: nothing to (re)allocate — this is called before every build
   CUDA_TRY(cudaSetDevice(b->ds->device));
   b->bases.assign(bases, bases + world + 1);
   b->world = world; b->rank = rank;
@@ -1485,9 +1605,21 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
   const int W = b->world, rank = b->rank;
   const bool stats_only = (flags & RMI_FLAG_STATS_ONLY) != 0;
   const bool want_counts = !stats_only && (flags & RMI_FLAG_LEAF_COUNTS) != 0;
-  const bool leaves_to_host = !stats_only && (rank == 0 || (flags & RMI_FLAG_SHARD_ROOT_ONLY) == 0);
   cudaStream_t st = b->st;
   ncclComm_t comm = c->comm;
+  // RMI_FLAG_SHARD_ROOT_ONLY on one node: every rank copies the records of the leaves it owns into a host region all
+  // ranks share (comm_ensure_shared) — rank 0's result points into it — instead of rank 0 copying all N records itself
+  bool shared = !stats_only && (flags & RMI_FLAG_SHARD_ROOT_ONLY) != 0 && W > 1 && c->single_node;
+  const size_t shared_bytes = sizeof(double) * N * ppm + sizeof(u64) * N * (want_counts ? 2 : 1);
+  if (shared) {
+    if (int rcs = comm_ensure_shared(c, shared_bytes, st)) return rcs;
+    shared = c->single_node && c->shm != nullptr;
+  }
+  unsigned char* const region = shared ? c->shm + (size_t)c->parity * c->shm_half : nullptr;
+  double* const sh_params = (double*)region;
+  u64* const sh_errors = shared ? (u64*)(region + sizeof(double) * N * ppm) : nullptr;
+  u64* const sh_counts = (shared && want_counts) ? sh_errors + N : nullptr;
+  const bool leaves_to_host = !shared && !stats_only && (rank == 0 || (flags & RMI_FLAG_SHARD_ROOT_ONLY) == 0);
   Launch L{st, b->num_sms};
   double* sums = (double*)b->buf.sums;
   // pinned host memory for the results first (nothing below waits for the host except the owner offsets)
@@ -1531,8 +1663,20 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
     // statistics of the owned leaves (needs only local results), gathered below
     leaf_statistics_owned(L, b->info.n_global, N, (const u64*)b->buf.errors, (const u64*)b->buf.counts, b->d_off, rank, W,
                           (char*)b->d_parts + stats_partial_bytes() * rank, b->d_stats);
+    if (shared) cudaEventRecord(c->ev_leaf_done, st);
     cudaError_t e = cudaEventSynchronize(b->ev_off);
     if (e != cudaSuccess) rc = fail(RMI_ERR_CUDA, std::string("rmi_shard_train: ") + cudaGetErrorString(e));
+    if (shared && rc == RMI_OK) {
+      // this rank's own leaf range goes to the shared host region on a side stream, next to the exchange below
+      const uint64_t j0 = b->h_off[rank], cnt = b->h_off[rank + 1] - b->h_off[rank];
+      cudaStreamWaitEvent(c->copy_stream, c->ev_leaf_done, 0);
+      if (cnt) {
+        cudaMemcpyAsync(sh_params + j0 * ppm, (double*)b->buf.params + j0 * ppm, sizeof(double) * cnt * ppm, cudaMemcpyDeviceToHost, c->copy_stream);
+        cudaMemcpyAsync(sh_errors + j0, (u64*)b->buf.errors + j0, sizeof(u64) * cnt, cudaMemcpyDeviceToHost, c->copy_stream);
+        if (sh_counts) cudaMemcpyAsync(sh_counts + j0, (u64*)b->buf.counts + j0, sizeof(u64) * cnt, cudaMemcpyDeviceToHost, c->copy_stream);
+      }
+      cudaEventRecord(c->ev_copy_done, c->copy_stream);
+    }
   }
   // ---- every owner publishes its leaf range: an all-gather with per-rank counts (grouped broadcasts) ----------
   if (rc == RMI_OK && W > 1) {
@@ -1560,6 +1704,11 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
     if (b->ran[RMI_PHASE_STATS] == false) { cudaEventRecord(b->ev_begin[RMI_PHASE_STATS], st); b->ran[RMI_PHASE_STATS] = true; }
     leaf_statistics_merge(L, b->d_parts, W, b->d_aux);
     cudaEventRecord(b->ev_end[RMI_PHASE_STATS], st);
+    if (shared) {
+      // "every rank's copy has landed": an all-reduce each rank enqueues behind its own copy
+      cudaStreamWaitEvent(st, c->ev_copy_done, 0);
+      nccl(nc.AllReduce(c->d_token, c->d_token, 1, ncclUint32, ncclMax, comm, st), "ncclAllReduce(result copies landed)");
+    }
   }
   cudaEventRecord(b->ev_t1, st);
   if (rc != RMI_OK) { cudaStreamSynchronize(st); delete box; return rc; }
@@ -1582,7 +1731,17 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
   float ms = 0.f;
   cudaEventElapsedTime(&ms, b->ev_t0, b->ev_t1);
   const uint64_t total_ns = (uint64_t)((double)ms * 1e6);
-  return shard_fill_result(b, box, flags, st_all, cnr, leaves_to_host, &total_ns, out);
+  int rcf = shard_fill_result(b, box, flags, st_all, cnr, leaves_to_host, &total_ns, out);
+  if (rcf == RMI_OK && shared) {
+    if (rank == 0) {   // the leaf tables live in the shared region (valid until the next-but-one call, see the header)
+      rmi_result* R = *out;
+      R->l1_params = sh_params;
+      R->l1_errors = reinterpret_cast<const uint64_t*>(sh_errors);
+      R->l1_counts = reinterpret_cast<const uint64_t*>(sh_counts);
+    }
+    c->parity ^= 1;
+  }
+  return rcf;
 }
 
 extern "C" {

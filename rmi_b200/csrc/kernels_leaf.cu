@@ -1389,12 +1389,20 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   // Forward pass: every lane walks its own leaf through the copy ring a second time.  Measured against the two
   // warp-cooperative variants below (coop_forward; profiles/r02_forward_variants.md): 0.533 ms for the leaf kernel
   // of the headline build against 0.619 (bulk-copy tiles) and 0.682 (register look-ahead).
+  // Leaves much longer than their warp's other leaves skip the lane-serial walk (one lane would walk it alone while 31
+  // wait): the whole warp evaluates them afterwards with coop_forward, 32 keys per step from bulk-copied tiles.  Worth it
+  // only when a few lanes are long (when all 32 are, the lane-serial walks are balanced already).
+  constexpr u64 LONG_FWD = 1024;
+  const bool is_long = live && (g_hi - g_lo) > LONG_FWD;
+  const unsigned long_mask = __ballot_sync(0xffffffffu, is_long);   // (all lanes vote: no short-circuit)
+  const bool long_fwd = is_long && __popc(long_mask) <= 4;
   {
     const u64 pol_fwd = l2_policy_of((mode_word >> 6) & 3);
+    const I fwd_hi = long_fwd ? r.lo : r.hi;
     T pk = (live && g_lo == 0 && g_hi > 0) ? keys[0] : prev_key;
     I F = (I)g_lo, run = 0;
     if (DUPS) {
-      stream_pass<T, I>(keys, pol_fwd, wsm, r.lo, r.hi, [&](T k, I i) {
+      stream_pass<T, I>(keys, pol_fwd, wsm, r.lo, fwd_hi, [&](T k, I i) {
         if (k != pk) { run_max = run > run_max ? run : run_max; run = 0; F = (I)(i + baseI); }
         run += 1;
         pk = k;
@@ -1404,7 +1412,7 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
       });
       if (g_hi < n && run > run_max) run_max = run;
     } else {
-      stream_pass<T, I>(keys, pol_fwd, wsm, r.lo, r.hi, [&](T k, I i) {
+      stream_pass<T, I>(keys, pol_fwd, wsm, r.lo, fwd_hi, [&](T k, I i) {
         I Fi = (I)(i + baseI);
         I pred = leaf_predict_clamped<LEAF, I, NANCHECK>(f, Key<T>::as_float(k), nI);
         I e = pred > Fi ? pred - Fi : Fi - pred;
@@ -1413,6 +1421,7 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
       (void)pk; (void)F; (void)run;
     }
   }
+  coop_forward<T, I, LEAF, DUPS, NANCHECK>(keys, sh, wsm, long_fwd && r.hi > r.lo, r.lo, r.hi, f, max_err, run_max);
 #else
   coop_forward<T, I, LEAF, DUPS, NANCHECK>(keys, sh, wsm, live && r.hi > r.lo, r.lo, r.hi, f, max_err, run_max);
 #endif

@@ -77,6 +77,17 @@ def _worker(rank, world, port, kind, n, spec, N, backend, q):
             assert np.array_equal(g3.last_layer_max_l1s, g.last_layer_max_l1s)
             assert np.array_equal(g3.l1_counts, g.l1_counts)
             assert g3.model_max_error == g.model_max_error and g3.model_avg_error == g.model_avg_error
+            # RMI_FLAG_SHARD_ROOT_ONLY: every rank copies the leaves it owns into the shared host region; rank 0 reads all of
+            # them there, the other ranks receive the statistics only.  Three builds in a row: both halves of the region.
+            for _ in range(3):
+                g4 = sharded.train_sharded(data, spec, N, rmi_b200.FLAG_SHARD_ROOT_ONLY)
+                assert g4.model_max_error == g.model_max_error and g4.model_avg_error == g.model_avg_error
+                if rank == 0:
+                    assert np.array_equal(parity.bits(g4.l1_params), parity.bits(g.l1_params))
+                    assert np.array_equal(g4.last_layer_max_l1s, g.last_layer_max_l1s)
+                    assert np.array_equal(g4.l1_counts, g.l1_counts)
+                else:
+                    assert g4.l1_params is None and g4.last_layer_max_l1s is None
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         import traceback
