@@ -521,7 +521,7 @@ struct BuildContext {
 thread_local BuildContext t_build_ctx;
 
 int leaf_slices_default() {
-  static const int k = [] { const char* e = getenv("RMI_DEV_LEAF_SLICES"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > MAX_LEAF_SLICES ? MAX_LEAF_SLICES : v); }();
+  static const int k = [] { const char* e = getenv("RMI_DEV_LEAF_SLICES"); int v = e ? atoi(e) : 5; return v < 1 ? 1 : (v > MAX_LEAF_SLICES ? MAX_LEAF_SLICES : v); }();
   return k;
 }
 
