@@ -69,9 +69,12 @@ def workload_config(args, world):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled every 20 ms while the timed regions run: NVML in a thread of this process
-    (a freshly spawned `nvidia-smi -lms` takes tens of milliseconds of driver work to start, which landed INSIDE a 30 ms
-    timed region and cost ~0.4 ms per step in round 2's first measurements); nvidia-smi is the fallback."""
+    """SM clock and throttle reasons while the timed regions run: NVML in a thread of this process, one query every 200 ms
+    (as round 1's `nvidia-smi -lms 200`), plus one query taken by the main thread right after the last step of each timed
+    region (sample_now).  Two things round 2 measured the hard way: a freshly spawned `nvidia-smi` takes tens of
+    milliseconds of driver work to start, which can land INSIDE a 30 ms timed region (+0.4 ms per step); and NVML queries
+    take the driver's lock, so polling every 20 ms nearly doubled the step time (2.36 instead of 1.28 ms).
+    nvidia-smi is the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -92,14 +95,18 @@ class ClockSampler:
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
 
+            def one():
+                try:
+                    self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                         int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                except Exception:
+                    pass
+            self._one = one
+
             def pump():
                 while not self._stop.is_set():
-                    try:
-                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
-                                             int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
-                    except Exception:
-                        pass
-                    self._stop.wait(0.02)
+                    one()
+                    self._stop.wait(0.2)
             self.t = threading.Thread(target=pump, daemon=True)
             self.t.start()
             return
@@ -119,6 +126,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def sample_now(self):
+        """one query from the calling thread (right after a timed region's last step: the clock has not moved yet)"""
+        if self.nvml is not None:
+            self._one()
+
     def mark(self):
         """samples taken from here on are 'under load' (the timed regions)"""
         self.mark_at = len(self.samples)
@@ -136,7 +148,8 @@ class ClockSampler:
             names = {"hw_slowdown": p.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": p.nvmlClocksEventReasonHwThermalSlowdown,
                      "sw_thermal_slowdown": p.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": p.nvmlClocksEventReasonSwPowerCap}
             return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
-                    "reasons": sorted(k for k, v in names.items() if bits & v), "samples": len(sm), "source": "nvml, 20 ms"}
+                    "reasons": sorted(k for k, v in names.items() if bits & v), "samples": len(sm),
+                    "source": "nvml: every 200 ms + right after each timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -358,6 +371,8 @@ def main():
     t_wall0 = time.perf_counter()
     ms_per_step, res, phase_ms, dev_ns = timed(build, args.steps, warmup=0)
     wall = time.perf_counter() - t_wall0
+    if rank == 0:
+        clocks.sample_now()
     launches = rmi_b200.kernel_launch_count() - launches0
     phase_ms = phase_ms / 1e6
     value = (n * world) / (ms_per_step / 1e3)
@@ -394,6 +409,8 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_ms = float(t_e2e.item()) / args.e2e_steps
     e2e_val = (n * world) / (e2e_ms / 1e3)
+    if rank == 0:
+        clocks.sample_now()
     clk = clocks.stop() if rank == 0 else None
 
     # ---- parity of what was timed (outside the timed regions) ---------------------------------------------------
