@@ -88,7 +88,12 @@ class ClockSampler:
         self.nvml = None
 
     def start(self):
+        mode = os.environ.get("RMI_BENCH_SAMPLER", "nvml")     # nvml | smi | none (diagnostic knob)
+        if mode == "none":
+            return
         try:
+            if mode == "smi":
+                raise RuntimeError("nvidia-smi sampler requested")
             import pynvml
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
@@ -340,11 +345,15 @@ def main():
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
+        walls = []
         for _ in range(steps):
+            t0 = time.perf_counter()
             res = build()      # synchronous: returns with results on the host
+            walls.append(((time.perf_counter() - t0) * 1e3, res.build_time / 1e6))
             phase += np.array(res.phase_device_ns, dtype=np.float64)
             dev_ns += res.device_time_ns
         e1.record()
+        timed.last_walls = walls
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if dist is not None:
@@ -364,6 +373,7 @@ def main():
     res = None
     for _ in range(max(args.warmup, 3)):
         res = build()
+    res = None          # (a third live result would make the timed region's second step allocate 24 MiB of pinned memory: ~10-30 ms)
     if rank == 0:
         clocks.mark()
     # ---- timed region: K resident builds ------------------------------------------------------------------------
@@ -371,6 +381,7 @@ def main():
     t_wall0 = time.perf_counter()
     ms_per_step, res, phase_ms, dev_ns = timed(build, args.steps, warmup=0)
     wall = time.perf_counter() - t_wall0
+    step_walls = [(round(a, 3), round(b, 3)) for a, b in timed.last_walls]   # (python wall, library wall) per step
     if rank == 0:
         clocks.sample_now()
     launches = rmi_b200.kernel_launch_count() - launches0
@@ -561,7 +572,7 @@ def main():
                                 "per build (their results cross PCIe while the next slice computes): achieved = algorithmic bytes of "
                                 "all slices / the leaf phase's device time; traffic = ncu DRAM bytes summed over the slices of one "
                                 "build, from the committed capture profiles/dominant_kernel_traffic.json (N = 1 only)",
-               "wall_ms_per_step": 1e3 * wall / args.steps},
+               "wall_ms_per_step": 1e3 * wall / args.steps, "step_wall_ms": step_walls},
            "clocks": clk,
            "e2e": {"value": e2e_val, "unit": "keys/s", "h2d_bytes_per_step": n * key_bytes * world,
                    "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms},

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=0, help="0 = all visible")
     ap.add_argument("--sample", type=float, default=4e6)
     ap.add_argument("--dist", default="uniform", choices=["uniform", "lognormal"])
+    ap.add_argument("--skip-single", action="store_true", help="do not time the one-replica sweep as well")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -60,7 +61,7 @@ def main():
     first = topt.first_phase("")
     out["phase1_configs"] = len(first)
     f_n = sweep(reps, f"sweep_{ngpu}_replicas_batched")
-    if ngpu > 1:
+    if ngpu > 1 and not args.skip_single:
         sweep(reps[:1], "sweep_1_replica_batched")
     os.environ["RMI_OPTIMIZER_NO_BATCH"] = "1"   # read once per process by the library: only effective in a fresh process
     out["note_unbatched"] = "the unbatched sweep is timed by a second invocation with RMI_OPTIMIZER_NO_BATCH=1 (see *_nobatch.json)"
