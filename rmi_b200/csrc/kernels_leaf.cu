@@ -117,29 +117,18 @@ k_bounds(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr
 // keys.  ~28 probes per leaf instead of a pass over all n keys; neighbouring leaves share
 // the upper levels of the search in L1/L2.  Sortedness (and with it monotonicity of the
 // targets) is verified by k_leaf, which visits every consecutive key pair anyway.
-// Two levels: level 0 searches every BOUNDS_COARSE-th boundary over the whole array (N / 32 searches of ~28 probes);
-// level 1 searches the others between their two bracketing coarse boundaries (~13 probes inside a window of a few tens
-// of KB that neighbouring threads share) — about half the DRAM sectors per boundary of a flat search.
-constexpr u64 BOUNDS_COARSE = 32;
 template <class T, int TOP>
 __global__ void __launch_bounds__(BOUNDS_THREADS)
 k_bounds_search(const T* __restrict__ keys, u64 n, const TopModel* __restrict__ top_ptr, u64 N,
-                u64* __restrict__ S, int level) {
+                u64* __restrict__ S) {
   TopModel m = *top_ptr;
-  u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  u64 j, lo = 0, hi = n;
-  if (level == 0) {
-    j = t * BOUNDS_COARSE;                       // 0, 32, 64, ...; the thread after the last multiple takes j = N
-    if (j > N) { if (j - N >= BOUNDS_COARSE) return; j = N; }
-  } else {
-    j = t;
-    if (j >= N || (j % BOUNDS_COARSE) == 0) return;
-    const u64 j0 = j - (j % BOUNDS_COARSE), j1 = j0 + BOUNDS_COARSE < N ? j0 + BOUNDS_COARSE : N;
-    lo = S[j0]; hi = S[j1];
-  }
+  u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > N) return;
+  u64 lo = 0, hi = n;
   if (j == N) lo = n;
   else if (j > 0) {
-    // (measured alternatives, both dropped: galloping outwards from the interpolated index j*n/N
+    // (measured alternatives, all dropped: a two-level search — every 32nd boundary first, the others between their
+    //  brackets, ~13 probes in a 48 KB window — 0.141 ms against 0.144, round 2; galloping outwards from the interpolated index j*n/N
     //  — 0.22 ms instead of 0.14 at 200M keys / 2^20 leaves, the divergent gallop loops cost more
     //  than the saved probes — and a 4-ary search with three independent probes per level — no
     //  change: the phase is bound by DRAM sectors per boundary, not by levels of latency)
@@ -1674,12 +1663,8 @@ template <class T, int TOP>
 void launch_bounds_impl(const Launch& L, const T* keys, u64 n, const TopModel* d_top, u64 N, u64* d_S, BuildAux* d_aux,
                    bool allow_search) {
   if (allow_search && top_is_monotone_by_construction(TOP)) {
-    const u64 coarse = N / BOUNDS_COARSE + 2;
-    k_bounds_search<T, TOP><<<(unsigned)((coarse + BOUNDS_THREADS - 1) / BOUNDS_THREADS), BOUNDS_THREADS, 0, L.stream>>>(
-        keys, n, d_top, N, d_S, 0);
-    count_launch();
-    k_bounds_search<T, TOP><<<(unsigned)((N + BOUNDS_THREADS - 1) / BOUNDS_THREADS), BOUNDS_THREADS, 0, L.stream>>>(
-        keys, n, d_top, N, d_S, 1);
+    k_bounds_search<T, TOP><<<(unsigned)((N + 1 + BOUNDS_THREADS - 1) / BOUNDS_THREADS), BOUNDS_THREADS, 0, L.stream>>>(
+        keys, n, d_top, N, d_S);
     count_launch();
     k_split<T, TOP><<<1, 32, 0, L.stream>>>(keys, n, d_top, N, d_S, d_aux, 1);
     count_launch();
