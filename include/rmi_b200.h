@@ -179,8 +179,7 @@ int rmi_train_stats_batch(const rmi_dataset* ds, const char* top_model, const ch
  * All phases are enqueued on the caller's CUDA stream and do not synchronise.  The result is
  * identical on every rank and equal to a single-GPU build of the concatenated array (same
  * tolerance rules).  Offered for the top models linear, robust_linear, linear_spline, cubic,
- * normal, lognormal, radix (the table / histogram tops need a table-sized exchange and are
- * single-GPU only). */
+ * normal, lognormal, radix, radix8..28 and histogram (bradix and loglinear are single-GPU only). */
 typedef struct {          /* what a rank publishes about its slab (host struct) */
   uint64_t first_key_bits, last_key_bits;  /* raw key bits (u32 zero-extended, f64 bit pattern) */
   uint64_t last_run_start;                 /* local index of the first key equal to the last key */
@@ -219,7 +218,10 @@ enum { RMI_PHASE_TOP_LOCAL = 0, RMI_PHASE_TOP_FINISH = 1, RMI_PHASE_BOUNDS = 2, 
  *    2  TOP_LOCAL -> SUM f64 sums[0,8) -> TOP_MID -> SUM f64 sums[0,8) -> TOP_FINISH
  *                                                                       (normal, lognormal)
  *    3  TOP_LOCAL -> all-reduce MIN of sums[8,12) as SIGNED 64-bit integers -> TOP_MID
- *                 -> SUM f64 sums[0,8) -> TOP_FINISH                    (cubic) */
+ *                 -> SUM f64 sums[0,8) -> TOP_FINISH                    (cubic)
+ *    4  TOP_LOCAL -> all-reduce MAX of the top model's table (rmi_shard_top_table: 2^bits u32 hints of a radix
+ *                 table, or the u64 pivots of a histogram; every entry has one writer, the others hold 0)
+ *                 -> TOP_FINISH                                          (radix8..28, histogram) */
 int rmi_shard_top_rounds(const char* top_model_name);
 
 typedef struct rmi_shard_build rmi_shard_build;
@@ -227,6 +229,9 @@ int rmi_shard_build_create(const rmi_dataset* local, const rmi_shard_info* info,
                            uint64_t branch_factor, const rmi_shard_buffers* buffers, void* cuda_stream,
                            rmi_shard_build** out);
 int rmi_shard_phase(rmi_shard_build* b, int phase);
+/* The device buffer a rounds-4 top model needs all-reduced with MAX between TOP_LOCAL and TOP_FINISH (elem_bytes 4 or 8;
+ * count 0 for the other top models).  rmi_shard_train does this itself. */
+int rmi_shard_top_table(rmi_shard_build* b, void** device_ptr, uint64_t* count, int* elem_bytes);
 int rmi_shard_set_halo(rmi_shard_build* b, uint64_t halo_keys);
 int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out);
 void rmi_shard_build_destroy(rmi_shard_build* b);

@@ -1118,6 +1118,11 @@ struct rmi_shard_build {
   unsigned* d_flags_all = nullptr;      // world x 2
   unsigned* h_flags_all = nullptr;      // pinned mirror
   bool gather_mode = false;             // rmi_shard_train: owners broadcast their leaf ranges, nothing is zero-filled
+  // table tops (radix8..28, histogram): the table every rank fills its part of, merged by an all-reduce MAX
+  u32* d_table32 = nullptr;             // 2^table_bits hints
+  u64* d_pivots = nullptr;              // hist_bins + 1
+  u64* d_ri = nullptr;                  // 2^20 + 1
+  u64 hist_bins = 0, hist_ipb = 0;
   cudaEvent_t ev_off = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_leaf0 = nullptr, ev_leaf1 = nullptr;
 };
 
@@ -1210,10 +1215,17 @@ template <class T> int shard_phase_typed(rmi_shard_build* b, int phase) {
         TopModel h;
         memset(&h, 0, sizeof(h));
         h.kind = b->top->kind; h.high = 1;
+        h.table_bits = b->top->table_bits;
+        h.t32 = b->d_table32; h.pivots = b->d_pivots; h.radix_index = b->d_ri; h.npivots = b->hist_bins;
+        if (b->top->kind == M_HISTOGRAM) h.ip[0] = b->hist_bins;
         cudaMemcpyAsync(b->d_top, &h, sizeof(h), cudaMemcpyHostToDevice, b->st);
       }
+      if (b->top->kind == M_HISTOGRAM && (b->hist_bins == 0 || b->hist_ipb < 1)) b->host_status |= ST_HIST_BINS;   // histogram.rs:25-27
       b->host_status |= shard_top_local<T>(L, keys, sh, b->top->kind, b->N, b->info.pivot_x, b->info.pivot_y, first_key,
                                            last_key, b->d_scratch, (double*)b->buf.sums);
+      if ((b->top->kind == M_RADIX_TABLE || b->top->kind == M_HISTOGRAM) && b->host_status == 0)
+        shard_table_local<T>(L, keys, sh, b->top->kind, b->top->table_bits, b->N, first_key, last_key, b->d_aux, b->d_table32,
+                             b->d_pivots, b->hist_bins, b->hist_ipb);
       break;
     case RMI_PHASE_TOP_MID:
       shard_top_mid<T>(L, keys, sh, b->top->kind, b->N, first_key, last_key, b->d_scratch, (double*)b->buf.sums, b->d_aux);
@@ -1221,6 +1233,8 @@ template <class T> int shard_phase_typed(rmi_shard_build* b, int phase) {
     case RMI_PHASE_TOP_FINISH:
       shard_top_finish<T>(L, sh, b->top->kind, b->N, b->info.pivot_x, b->info.pivot_y, (const double*)b->buf.sums,
                           first_key, last_key, b->info.last_F, b->d_scratch, b->d_top, b->d_aux);
+      if (b->top->kind == M_RADIX_TABLE && b->host_status == 0) shard_table_decode(L, b->top->table_bits, b->d_table32);
+      if (b->top->kind == M_HISTOGRAM && b->host_status == 0) hist_radix_index(L, b->d_pivots, b->hist_bins, b->d_ri);
       break;
     case RMI_PHASE_BOUNDS:
       shard_bounds<T>(L, keys, sh, b->top->kind, b->d_top, b->N, (u64*)b->buf.S, b->d_aux);
@@ -1267,6 +1281,7 @@ int rmi_shard_top_rounds(const char* top_model_name) {
     case M_LINEAR: case M_ROBUST_LINEAR: return 1;
     case M_NORMAL: case M_LOGNORMAL: return 2;
     case M_CUBIC: return 3;
+    case M_RADIX_TABLE: case M_HISTOGRAM: return 4;
     default: return -1;
   }
 }
@@ -1298,7 +1313,7 @@ int rmi_shard_build_create(const rmi_dataset* local, const rmi_shard_info* info,
     return fail(RMI_ERR_PANIC, "if used, model type " + s.substr(c + 1) + " must be the root model");
   if (rmi_shard_top_rounds(top->name) < 0)
     return fail(RMI_ERR_UNSUPPORTED, "range-partitioned builds offer the top models linear, robust_linear, linear_spline, "
-                                     "cubic, normal, lognormal, radix");
+                                     "cubic, normal, lognormal, radix, radix8..28, histogram");
   if (leaf->kind == M_RADIX_TABLE) return fail(RMI_ERR_UNSUPPORTED, "radix tables are only offered as the top model");
   if (branch_factor < 1) return fail(RMI_ERR_PANIC, "branching factor must be at least 1");
   if (info->n_global == 0) return fail(RMI_ERR_PANIC, "start index was 0 but end index was 0");
@@ -1322,8 +1337,22 @@ int rmi_shard_build_create(const rmi_dataset* local, const rmi_shard_info* info,
          cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) == cudaSuccess &&
          cudaMalloc((void**)&b->d_long, sizeof(u32) * (LONG_LEAF_CAP + 1)) == cudaSuccess;
   }
+  if (ok && top->kind == M_RADIX_TABLE) ok = cudaMalloc((void**)&b->d_table32, sizeof(u32) << top->table_bits) == cudaSuccess;
+  if (ok && top->kind == M_HISTOGRAM) {
+    histogram_bins(info->n_global, branch_factor, &b->hist_bins, &b->hist_ipb);
+    ok = cudaMalloc((void**)&b->d_pivots, sizeof(u64) * (b->hist_bins + 1)) == cudaSuccess &&
+         cudaMalloc((void**)&b->d_ri, sizeof(u64) * (((size_t)1 << 20) + 1)) == cudaSuccess;
+  }
   if (!ok) { rmi_shard_build_destroy(b); return fail(RMI_ERR_CUDA, "rmi_shard_build_create: device allocation failed"); }
   *out = b;
+  return RMI_OK;
+}
+
+int rmi_shard_top_table(rmi_shard_build* b, void** device_ptr, uint64_t* count, int* elem_bytes) {
+  if (!b || !device_ptr || !count || !elem_bytes) return fail(RMI_ERR_INVALID, "rmi_shard_top_table: null argument");
+  if (b->top->kind == M_RADIX_TABLE) { *device_ptr = b->d_table32; *count = (uint64_t)1 << b->top->table_bits; *elem_bytes = 4; return RMI_OK; }
+  if (b->top->kind == M_HISTOGRAM) { *device_ptr = b->d_pivots; *count = b->hist_bins; *elem_bytes = 8; return RMI_OK; }
+  *device_ptr = nullptr; *count = 0; *elem_bytes = 0;
   return RMI_OK;
 }
 
@@ -1375,8 +1404,16 @@ static int shard_fill_result(rmi_shard_build* b, ResultBox* box, uint32_t flags,
   R.model_max_log2_error = std::log2((double)h_aux.max_error);
   R.l0_model_id = b->top->kind;
   R.l0_bradix_high = 1;
+  R.l0_table_bits = b->top->table_bits;
   if (b->top->kind == M_RADIX) R.l0_num_iparams = 2;
+  else if (b->top->kind == M_RADIX_TABLE || b->top->kind == M_HISTOGRAM) R.l0_num_iparams = 1;
   else R.l0_num_fparams = b->top->kind == M_CUBIC ? 4 : ((b->top->kind == M_NORMAL || b->top->kind == M_LOGNORMAL) ? 3 : 2);
+  R.l0_table32_len = box->table32.size();
+  R.l0_table32 = box->table32.empty() ? nullptr : box->table32.data();
+  R.l0_array1_len = box->arr1.size();
+  R.l0_array1 = box->arr1.empty() ? nullptr : box->arr1.data();
+  R.l0_array2_len = box->arr2.size();
+  R.l0_array2 = box->arr2.empty() ? nullptr : box->arr2.data();
   for (int q = 0; q < 4; ++q) { R.l0_fparams[q] = h_top.f[q]; R.l0_iparams[q] = h_top.ip[q]; }
   R.l1_model_id = b->leaf->kind;
   R.l1_params_per_model = ppm;
@@ -1420,6 +1457,12 @@ int rmi_shard_finish(rmi_shard_build* b, uint32_t flags, rmi_result** out) {
   unsigned h_status = 0;
   cudaMemcpyAsync(&h_aux, b->d_aux, sizeof(BuildAux), cudaMemcpyDeviceToHost, b->st);
   cudaMemcpyAsync(&h_top, b->d_top, sizeof(TopModel), cudaMemcpyDeviceToHost, b->st);
+  if (b->top->kind == M_RADIX_TABLE && box->table32.resize((size_t)1 << b->top->table_bits))
+    cudaMemcpyAsync(box->table32.data(), b->d_table32, sizeof(u32) << b->top->table_bits, cudaMemcpyDeviceToHost, b->st);
+  if (b->top->kind == M_HISTOGRAM && box->arr1.resize(((size_t)1 << 20) + 1) && box->arr2.resize(b->hist_bins)) {
+    cudaMemcpyAsync(box->arr1.data(), b->d_ri, sizeof(u64) * box->arr1.size(), cudaMemcpyDeviceToHost, b->st);
+    cudaMemcpyAsync(box->arr2.data(), b->d_pivots, sizeof(u64) * b->hist_bins, cudaMemcpyDeviceToHost, b->st);
+  }
   if (!stats_only) {
     cudaMemcpyAsync(box->l1_params.data(), b->buf.params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, b->st);
     cudaMemcpyAsync(box->l1_errors.data(), b->buf.errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, b->st);
@@ -1641,6 +1684,12 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
   if (W > 1 && rc == RMI_OK) {
     if (rounds == 1 || rounds == 2) nccl(nc.AllReduce(sums, sums, 8, ncclFloat64, ncclSum, comm, st), "ncclAllReduce(top sums)");
     if (rounds == 3) nccl(nc.AllReduce(sums + 8, sums + 8, 4, ncclInt64, ncclMin, comm, st), "ncclAllReduce(cubic interior points)");
+    if (rounds == 4 && b->host_status == 0) {   // table tops: merge the ranks' partial tables (one writer per entry, zero elsewhere)
+      if (b->top->kind == M_RADIX_TABLE)
+        nccl(nc.AllReduce(b->d_table32, b->d_table32, (size_t)1 << b->top->table_bits, ncclUint32, ncclMax, comm, st), "ncclAllReduce(radix table)");
+      else
+        nccl(nc.AllReduce(b->d_pivots, b->d_pivots, b->hist_bins, ncclUint64, ncclMax, comm, st), "ncclAllReduce(histogram pivots)");
+    }
   }
   if (rounds >= 2) {
     phase(RMI_PHASE_TOP_MID);
@@ -1718,6 +1767,12 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
   cudaMemcpyAsync(&h_aux, b->d_aux, sizeof(BuildAux), cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(&h_top, b->d_top, sizeof(TopModel), cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(b->h_flags_all, b->d_flags_all, 2 * sizeof(unsigned) * W, cudaMemcpyDeviceToHost, st);
+  if (b->top->kind == M_RADIX_TABLE && box->table32.resize((size_t)1 << b->top->table_bits))
+    cudaMemcpyAsync(box->table32.data(), b->d_table32, sizeof(u32) << b->top->table_bits, cudaMemcpyDeviceToHost, st);
+  if (b->top->kind == M_HISTOGRAM && box->arr1.resize(((size_t)1 << 20) + 1) && box->arr2.resize(b->hist_bins)) {
+    cudaMemcpyAsync(box->arr1.data(), b->d_ri, sizeof(u64) * box->arr1.size(), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(box->arr2.data(), b->d_pivots, sizeof(u64) * b->hist_bins, cudaMemcpyDeviceToHost, st);
+  }
   if (leaves_to_host) {
     cudaMemcpyAsync(box->l1_params.data(), b->buf.params, sizeof(double) * N * ppm, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(box->l1_errors.data(), b->buf.errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, st);
@@ -1768,6 +1823,7 @@ void rmi_shard_build_destroy(rmi_shard_build* b) {
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->side) cudaStreamDestroy(b->side);
   cudaFree(b->d_long);
+  cudaFree(b->d_table32); cudaFree(b->d_pivots); cudaFree(b->d_ri);
   cudaFree(b->d_bases); cudaFree(b->d_off); cudaFree(b->d_parts); cudaFree(b->d_flags_mine); cudaFree(b->d_flags_all);
   if (b->h_off) cudaFreeHost(b->h_off);
   if (b->h_flags_all) cudaFreeHost(b->h_flags_all);

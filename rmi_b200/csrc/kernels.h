@@ -155,6 +155,13 @@ void shard_bounds(const Launch& L, const T* keys, const Shard<T>& sh, int kind, 
 template <class T>
 void shard_split(const Launch& L, const T* keys, const Shard<T>& sh, int kind, const TopModel* d_top, u64 N,
                  const u64* d_S, BuildAux* d_aux);
+// Table tops (radix8..28, histogram): every rank fills the entries its slab decides (zero elsewhere; hint entries as
+// value + 1), the caller all-reduces the table with MAX, then shard_table_decode / hist_radix_index finish it.
+template <class T>
+void shard_table_local(const Launch& L, const T* keys, const Shard<T>& sh, int kind, int table_bits, u64 N, T first_key,
+                       T last_key, BuildAux* d_aux, u32* d_table32, u64* d_pivots, u64 num_bins, u64 items_per_bin);
+void shard_table_decode(const Launch& L, int table_bits, u32* d_table32);
+void hist_radix_index(const Launch& L, const u64* d_pivots, u64 num_bins, u64* d_radix_index);   // kernels_top.cu
 void shard_copy_status(const Launch& L, const BuildAux* d_aux, unsigned* d_out);
 // {status word, could_not_replace != 0} of this rank, for the cross-rank gather (two_layer.rs:199-203 warns if ANY leaf could not be replaced)
 void shard_copy_flags(const Launch& L, const BuildAux* d_aux, unsigned* d_out2);

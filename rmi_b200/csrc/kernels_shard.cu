@@ -173,6 +173,54 @@ __global__ void k_shard_top_from_ends(int kind, T first_key, T last_key, u64 las
     int bits = num_bits_of(largest);
     if (bits < 1) set_status(aux, ST_NUM_BITS);
     top->ip[0] = (u64)prefix; top->ip[1] = (u64)bits;
+  } else if (kind == M_RADIX_TABLE) {   // radix.rs:90-100: the prefix; the table's width is fixed by the model name
+    int prefix = common_prefix_sorted(Key<T>::as_int(first_key), Key<T>::as_int(last_key));
+    aux->max_scaled_y = scale_offset(last_F, sf, use_sf);
+    top->ip[0] = (u64)prefix;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Table tops over a range-partitioned array (radix8..28: radix.rs:90-134; histogram: histogram.rs:20-61).
+// Both are "one writer per entry": a hint-table entry is written at the one key where the radix steps past
+// it, a pivot is the key at one global index.  Every rank fills the entries its slab decides into a
+// zero-initialised table (hint entries as value + 1), ONE all-reduce MAX merges the ranks' tables, and a
+// decode pass restores the reference's values for the entries nobody wrote.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_table_fill(const T* __restrict__ keys, const Shard<T> sh, T first_key, T last_key, int bits, double sf, int use_sf,
+                   u32* __restrict__ table, BuildAux* aux) {
+  const unsigned prefix = (unsigned)common_prefix_sorted(Key<T>::as_int(first_key), Key<T>::as_int(last_key));
+  const unsigned nb = (prefix + (unsigned)bits > 64u) ? 0u : 64u - (prefix + (unsigned)bits);
+  const u64 len = 1ull << bits;
+  auto radix_of = [&](T k) { return shr64(shr64(shl64(Key<T>::as_int(k), prefix), prefix), nb); };
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < sh.n_local; i += stride) {
+    const u64 r = radix_of(keys[i]);
+    const u64 rp = i > 0 ? radix_of(keys[i - 1]) : (sh.has_prev ? radix_of(sh.prev_key) : 0ull);
+    if (r > rp) {
+      if (r >= len) { atomicOr(&aux->status, (unsigned)ST_RADIX_TABLE_OOB); continue; }
+      const u32 y = (u32)scale_offset(sh.base + i, sf, use_sf);   // a radix change implies a key change: F_i = i
+      for (u64 q = rp + 1; q <= r; ++q) table[q] = y + 1u;
+    }
+  }
+}
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_table_decode(u32* __restrict__ table, u64 len) {
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < len; q += stride) {
+    const u32 v = table[q];
+    table[q] = v ? v - 1u : (q == 0 ? 0u : (u32)len);   // hint[0] = 0; entries past the last key's radix = 2^bits
+  }
+}
+template <class T>
+__global__ void __launch_bounds__(SH_THREADS)
+k_shard_hist_pivots(const T* __restrict__ keys, const Shard<T> sh, u64 num_bins, u64 items_per_bin, u64* __restrict__ pivots) {
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x; b < num_bins; b += stride) {
+    const u64 g = b * items_per_bin;
+    if (g >= sh.base && g < sh.base + sh.n_local) pivots[b] = Key<T>::as_int(keys[g - sh.base]);
   }
 }
 
@@ -586,6 +634,8 @@ void shard_bounds(const Launch& L, const T* keys, const Shard<T>& sh, int kind, 
   unsigned blocks = (unsigned)((N + 1 + SH_THREADS - 1) / SH_THREADS);
   switch (kind) {
     case M_RADIX: k_shard_bounds_search<T, M_RADIX><<<blocks, SH_THREADS, 0, L.stream>>>(keys, sh, d_top, N, d_S); count_launch(); break;
+    case M_RADIX_TABLE: k_shard_bounds_search<T, M_RADIX_TABLE><<<blocks, SH_THREADS, 0, L.stream>>>(keys, sh, d_top, N, d_S); count_launch(); break;
+    case M_HISTOGRAM: k_shard_bounds_search<T, M_HISTOGRAM><<<blocks, SH_THREADS, 0, L.stream>>>(keys, sh, d_top, N, d_S); count_launch(); break;
     case M_CUBIC: shard_bounds_stream<T, M_CUBIC>(L, keys, sh, d_top, N, d_S, d_aux); break;
     case M_NORMAL: shard_bounds_stream<T, M_NORMAL>(L, keys, sh, d_top, N, d_S, d_aux); break;
     case M_LOGNORMAL: shard_bounds_stream<T, M_LOGNORMAL>(L, keys, sh, d_top, N, d_S, d_aux); break;
@@ -598,6 +648,8 @@ void shard_split(const Launch& L, const T* keys, const Shard<T>& sh, int kind, c
                  const u64* d_S, BuildAux* d_aux) {
   switch (kind) {
     case M_RADIX: k_split_from_S<T, M_RADIX><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
+    case M_RADIX_TABLE: k_split_from_S<T, M_RADIX_TABLE><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
+    case M_HISTOGRAM: k_split_from_S<T, M_HISTOGRAM><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
     case M_CUBIC: k_split_from_S<T, M_CUBIC><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
     case M_NORMAL: k_split_from_S<T, M_NORMAL><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
     case M_LOGNORMAL: k_split_from_S<T, M_LOGNORMAL><<<1, 32, 0, L.stream>>>(keys, sh, d_top, N, d_S, d_aux); break;
@@ -608,6 +660,31 @@ void shard_split(const Launch& L, const T* keys, const Shard<T>& sh, int kind, c
 
 void shard_copy_status(const Launch& L, const BuildAux* d_aux, unsigned* d_out) {
   k_copy_status<<<1, 32, 0, L.stream>>>(d_aux, d_out);
+  count_launch();
+}
+
+template <class T>
+void shard_table_local(const Launch& L, const T* keys, const Shard<T>& sh, int kind, int table_bits, u64 N, T first_key,
+                       T last_key, BuildAux* d_aux, u32* d_table32, u64* d_pivots, u64 num_bins, u64 items_per_bin) {
+  double sf = (double)N / (double)sh.n_global;
+  int use_sf = std::fabs(sf - 1.0) > DBL_EPSILON ? 1 : 0;
+  if (kind == M_RADIX_TABLE) {
+    cudaMemsetAsync(d_table32, 0, sizeof(u32) << table_bits, L.stream);
+    if (sh.n_local) {
+      k_shard_table_fill<T><<<sh_grid(sh.n_local, L.num_sms), SH_THREADS, 0, L.stream>>>(keys, sh, first_key, last_key, table_bits, sf,
+                                                                                        use_sf, d_table32, d_aux);
+      count_launch();
+    }
+  } else if (kind == M_HISTOGRAM) {
+    cudaMemsetAsync(d_pivots, 0, sizeof(u64) * (num_bins + 1), L.stream);
+    if (sh.n_local && num_bins) {
+      k_shard_hist_pivots<T><<<sh_grid(num_bins, L.num_sms), SH_THREADS, 0, L.stream>>>(keys, sh, num_bins, items_per_bin, d_pivots);
+      count_launch();
+    }
+  }
+}
+void shard_table_decode(const Launch& L, int table_bits, u32* d_table32) {
+  k_shard_table_decode<<<sh_grid(1ull << table_bits, L.num_sms), SH_THREADS, 0, L.stream>>>(d_table32, 1ull << table_bits);
   count_launch();
 }
 
@@ -622,7 +699,8 @@ void shard_copy_flags(const Launch& L, const BuildAux* d_aux, unsigned* d_out2) 
   template void shard_top_finish<T>(const Launch&, const Shard<T>&, int, u64, double, double, const double*, T, T, u64,   \
                                     const void*, TopModel*, BuildAux*);                                             \
   template void shard_bounds<T>(const Launch&, const T*, const Shard<T>&, int, const TopModel*, u64, u64*, BuildAux*); \
-  template void shard_split<T>(const Launch&, const T*, const Shard<T>&, int, const TopModel*, u64, const u64*, BuildAux*);
+  template void shard_split<T>(const Launch&, const T*, const Shard<T>&, int, const TopModel*, u64, const u64*, BuildAux*); \
+  template void shard_table_local<T>(const Launch&, const T*, const Shard<T>&, int, int, u64, T, T, BuildAux*, u32*, u64*, u64, u64);
 INST(u64)
 INST(u32)
 INST(double)

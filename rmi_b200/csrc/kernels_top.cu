@@ -586,6 +586,11 @@ int grid_for(u64 n, int num_sms) {
 
 }  // namespace
 
+void hist_radix_index(const Launch& L, const u64* d_pivots, u64 num_bins, u64* d_radix_index) {
+  k_hist_radix_index<<<grid_for((1ull << 20) + 1, L.num_sms), TOP_THREADS, 0, L.stream>>>(d_pivots, num_bins, d_radix_index);
+  count_launch();
+}
+
 size_t top_scratch_bytes(u64 num_leaves) {
   // partials (5 doubles per block) + candidates + state + bradix boundaries (N+2 u64) + best cand
   return (size_t)MAX_PARTIAL_BLOCKS * 5 * sizeof(double) + 64 * sizeof(double) + (size_t)(num_leaves + 2) * sizeof(u64) + 256;

@@ -35,7 +35,10 @@ PHASE_TOP_LOCAL, PHASE_TOP_FINISH, PHASE_BOUNDS, PHASE_SPLIT, PHASE_LEAF, PHASE_
 # as f64; "min": all-reduce MIN of sums[8:12] as signed 64-bit integers.
 TOP_ROUNDS = {"linear_spline": (), "radix": (), "linear": ("sum",), "robust_linear": ("sum",),
               "normal": ("sum", "sum"), "lognormal": ("sum", "sum"), "cubic": ("min", "sum")}
-SHARDED_TOPS = tuple(TOP_ROUNDS)
+# Table tops (rmi_shard_top_rounds == 4: one all-reduce MAX of the hint table / the pivots): offered by the one-call path
+# (rmi_shard_train, NCCL) only — this host-driven orchestrator has no view of the library-owned table.
+NATIVE_ONLY_TOPS = ("radix8", "radix18", "radix22", "radix26", "radix28", "histogram")
+SHARDED_TOPS = tuple(TOP_ROUNDS) + NATIVE_ONLY_TOPS
 _PPM = {"linear": 2, "robust_linear": 2, "linear_spline": 2, "loglinear": 2, "cubic": 4, "normal": 3, "lognormal": 3}
 _TORCH_OF_KEY = {api.KEY_U64: torch.int64, api.KEY_U32: torch.int32, api.KEY_F64: torch.float64}
 
@@ -417,6 +420,9 @@ def train_sharded(data, model_spec: str, num_leaves: int, flags: int = 0, group=
                 raise
         return _retry_with_larger_halo(data, bufs, bases, n_global, N, model_spec, num_leaves, flags, group, world, dev, counts, native)
 
+    if parts[0] in NATIVE_ONLY_TOPS:
+        raise api.RMIError(f"a range-partitioned build with the top model {parts[0]} needs the one-call path "
+                           "(rmi_shard_train over an NCCL process group, or native=True with a single rank)")
     # 2. top model: local part -> tiny all-reduce(s) -> closed form (identical on every rank)
     def top_collective(kind):
         if world <= 1:

@@ -62,5 +62,5 @@ def test_shard_top_rounds_agree_with_the_orchestrator():
     code = {(): 0, ("sum",): 1, ("sum", "sum"): 2, ("min", "sum"): 3}
     for name in ("linear", "robust_linear", "linear_spline", "cubic", "loglinear", "normal", "lognormal", "radix",
                  "radix18", "bradix", "histogram", "no_such_model"):
-        want = code[sharded.TOP_ROUNDS[name]] if name in sharded.TOP_ROUNDS else -1
+        want = code[sharded.TOP_ROUNDS[name]] if name in sharded.TOP_ROUNDS else (4 if name in sharded.NATIVE_ONLY_TOPS else -1)
         assert lib.rmi_shard_top_rounds(name.encode()) == want, name

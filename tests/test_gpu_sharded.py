@@ -68,7 +68,7 @@ def _worker(rank, world, port, kind, n, spec, N, backend, q):
         g2 = sharded.train_sharded(data, spec, N)
         assert np.array_equal(parity.bits(g2.l1_params), parity.bits(g.l1_params))
         assert np.array_equal(g2.last_layer_max_l1s, g.last_layer_max_l1s)
-        if backend == "nccl":
+        if backend == "nccl" and top not in sharded.NATIVE_ONLY_TOPS:
             # over NCCL the default is the one-call path (rmi_shard_train: collectives issued by the library, leaf
             # records all-gathered by ownership range); the host-sequenced path must give the same bits
             g3 = sharded.train_sharded(data, spec, N, native=False)
@@ -99,7 +99,9 @@ def _worker(rank, world, port, kind, n, spec, N, backend, q):
 CASES = [("uniform", "linear,linear", 1024), ("uniform", "radix,linear", 4096), ("dups", "linear_spline,linear", 512),
          ("lognormal", "radix,linear_spline", 1000), ("dups", "robust_linear,cubic", 256), ("uniform", "linear,cubic", 333),
          ("uniform", "cubic,linear", 1024), ("dups", "cubic,linear", 300), ("lognormal", "cubic,linear_spline", 128),
-         ("uniform", "normal,linear", 256), ("lognormal", "lognormal,linear", 200)]
+         ("uniform", "normal,linear", 256), ("lognormal", "lognormal,linear", 200),
+         ("uniform", "radix18,linear", 2048), ("dups", "radix8,linear", 200), ("lognormal", "histogram,linear", 512),
+         ("uniform", "histogram,linear_spline", 1000)]
 
 
 @pytest.mark.parametrize("kind,spec,N", CASES, ids=[f"{c[0]}-{c[1]}-{c[2]}" for c in CASES])
@@ -112,6 +114,8 @@ def test_sharded_cuda_build_equals_oracle(oracle, world, kind, spec, N):
     except oracle.OraclePanic as e:
         pytest.skip(f"reference panics on this configuration: {e}")
     backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
+    if backend == "gloo" and spec.split(",")[0] in ("radix8", "radix18", "histogram"):
+        pytest.skip("table tops are offered by the one-call path only (needs one GPU per rank for NCCL)")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -126,7 +130,8 @@ def test_sharded_cuda_build_equals_oracle(oracle, world, kind, spec, N):
 
 
 @pytest.mark.parametrize("spec,N", [("linear,linear", 4096), ("radix,linear", 2048), ("cubic,linear", 1000),
-                                    ("linear_spline,cubic", 512), ("normal,linear", 256)])
+                                    ("linear_spline,cubic", 512), ("normal,linear", 256), ("radix18,linear", 1024),
+                                    ("radix8,linear_spline", 300), ("histogram,linear", 512)])
 def test_one_call_path_single_rank(oracle, spec, N):
     """rmi_shard_train (every phase and collective issued by the library on one stream) with a one-rank NCCL
     communicator: ownership offsets, owned-range statistics, status gather and result marshalling on a one-GPU box.
@@ -138,7 +143,13 @@ def test_one_call_path_single_rank(oracle, spec, N):
     local = torch.from_numpy(keys.view(np.int64).copy()).to(dev)
     data = sharded.ShardedTrainingData(local, key_type=rmi_b200.KEY_U64, halo_capacity=16)
     g = sharded.train_sharded(data, spec, N, native=True)
-    h = sharded.train_sharded(data, spec, N, native=False)
+    if spec.split(",")[0] in sharded.NATIVE_ONLY_TOPS:     # table tops: one-call path only; compare with rmi_train and the oracle
+        h = rmi_b200.train(data.engine.ds, spec, N)
+        assert np.array_equal(g.l0_table32, h.l0_table32) if h.l0_table32 is not None else g.l0_table32 is None
+        assert (g.l0_pivots is None and h.l0_pivots is None) or np.array_equal(g.l0_pivots, h.l0_pivots)
+        assert (g.l0_radix_index is None and h.l0_radix_index is None) or np.array_equal(g.l0_radix_index, h.l0_radix_index)
+    else:
+        h = sharded.train_sharded(data, spec, N, native=False)
     assert np.array_equal(parity.bits(g.l0_fparams), parity.bits(h.l0_fparams))
     assert np.array_equal(parity.bits(g.l1_params), parity.bits(h.l1_params))
     assert np.array_equal(g.last_layer_max_l1s, h.last_layer_max_l1s)
