@@ -56,6 +56,9 @@ constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
 #ifndef RMI_FWD_DEPTH
 #define RMI_FWD_DEPTH 8   // 32-key loads in flight per warp in the forward pass
 #endif
+#ifndef RMI_RC_PREFETCH
+#define RMI_RC_PREFETCH 1
+#endif
 #ifndef RMI_RCP_TABLE
 #define RMI_RCP_TABLE 512
 #endif
@@ -469,24 +472,42 @@ template <bool CHECKED> struct LeafWelford {
     ra = (unsigned)__cvta_generic_to_shared(table);
     ra_end = ra + (unsigned)((RCP_TABLE - 1) * sizeof(double));
   }
-  // 1/(items pushed + 1): shared table, then the global table, then a division.  `ra` keeps counting
-  // past the shared table's end (it is the item count in bytes, relative to the table's start).
-  __device__ __forceinline__ double next_rc() {
-    ra += (unsigned)sizeof(double);
+  // 1/(items pushed + 1): shared table, then the global table, then a division.  `ra` keeps counting past the shared
+  // table's end (it is the item count in bytes, relative to the table's start).  Like table_rc() the value is fetched
+  // ONE STEP AHEAD (rc_next, primed by table_begin()): the reciprocal sits at the head of the step's dependent chain,
+  // so a load issued in the step that consumes it adds its whole latency to every item — which is what made builds with
+  // long training vectors (2^18 leaves on 200M keys; 2^20 leaves over eight GPUs' keys) slower per key than short ones.
+  __device__ __forceinline__ double fetch_rc(unsigned at, double count) const {   // reciprocal of `count`, stored at table address `at`
     double rc;
-    if (ra <= ra_end) {
-      asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(ra));
+    if (at <= ra_end) {
+      asm("ld.shared.f64 %0, [%1];" : "=d"(rc) : "r"(at));
     } else {
-      const unsigned off = ra - (ra_end - (unsigned)((RCP_TABLE - 1) * sizeof(double)));   // count * 8
+      const unsigned off = at - (ra_end - (unsigned)((RCP_TABLE - 1) * sizeof(double)));   // count * 8
       if (off < RCP_FAR * (unsigned)sizeof(double))
         rc = __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(g_rcp_far) + off));
       else
-        rc = rcp_beyond_table(__dadd_rn(nf, 1.0));   // a real call, so it is not if-converted
+        rc = rcp_beyond_table(count);   // a real call, so it is not if-converted
     }
     return rc;
   }
+  __device__ __forceinline__ double next_rc() {
+#if RMI_RC_PREFETCH
+    const double rc = rc_next;
+    ra += (unsigned)sizeof(double);
+    rc_next = fetch_rc(ra + (unsigned)sizeof(double), __dadd_rn(nf, 2.0));   // this step divides by nf + 1, the next by nf + 2
+    return rc;
+#else   // experiment knob: the load issued in the step that uses it (round 1's behaviour)
+    ra += (unsigned)sizeof(double);
+    return fetch_rc(ra, __dadd_rn(nf, 1.0));
+#endif
+  }
   // after a stretch in which `ra` was not advanced (solo mode): later steps divide
-  __device__ __forceinline__ void rc_cursor_off() { ra = ra_end + RCP_FAR * (unsigned)sizeof(double); }
+  __device__ __forceinline__ void rc_cursor_off() {
+    ra = ra_end + RCP_FAR * (unsigned)sizeof(double);
+#if RMI_RC_PREFETCH
+    rc_next = rcp_beyond_table(__dadd_rn(nf, 1.0));
+#endif
+  }
   __device__ __forceinline__ double dv(double a, double rc) const {
     if (CHECKED) return div_by_count(a, nf, rc);
     double q0 = __dmul_rn(a, rc);
@@ -719,6 +740,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     // linear.rs:79-83 / :61-72,169-173 — drained stream: vector + repeat of the final item
     LeafWelford<CHECKED> w;
     w.init(rcp);
+    w.table_begin();
     ItemTracker<T, DUPS> it;
     it.init(kfirst, vsd, f0d);
     auto item = [&](T k, I) {
@@ -747,7 +769,6 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     };
     if (ND) w.nd_init();
     if (LEAF == M_LINEAR && all_short) {
-      w.table_begin();
       if (ND) {
         FitStepND<T, CHECKED> item_nd{w};
         if (r.p_remote) item_nd(r.pkey, (I)0);
@@ -798,6 +819,7 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     if (!ok) bad |= ST_ROBUST_TOO_SMALL;
     LeafWelford<CHECKED> w;
     w.init(rcp);
+    w.table_begin();
     ItemTracker<T, DUPS> it;
     it.init(kfirst, vsd, f0d);
     u64 pos = 0;

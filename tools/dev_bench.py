@@ -18,6 +18,9 @@ configs = [("linear,linear", 1 << 20, 0), ("radix,linear", 1 << 19, 0), ("cubic,
            ("radix18,linear", 1 << 16, 0), ("bradix,linear", 1 << 18, 0), ("histogram,linear", 1 << 16, 0)]
 if "--quick" in opt:
     configs = configs[:3]
+if "--long" in opt:   # long training vectors: what each GPU of an 8-GPU sharded build sees (1525 keys per leaf), and beyond
+    configs = [("linear,linear", 1 << 20, 0), ("linear,linear", 1 << 18, 0), ("linear,linear", 1 << 17, 0),
+               ("linear,linear", 1 << 14, 0), ("cubic,linear", 1 << 18, 0), ("linear,cubic", 1 << 17, 0)]
 if "--one" in opt:
     configs = configs[:1]
 if "--exact" in opt:

@@ -20,7 +20,9 @@ for n in $(seq 2 $N | awk -v N=$N '{ if ($1==2 || $1==4 || $1==8) print $1 }'); 
   cut -c1-2500 $out/${tag}_bench_n$n.json
   tail -3 $out/${tag}_bench_n$n.err
 done
+if [ "$okeys" != "0" ]; then
 timeout 900 python tools/optimize_bench.py --keys $okeys --gpus $N --sample 2e6 > $out/${tag}_optimize_${N}gpu.json 2> $out/${tag}_optimize_${N}gpu.err
 echo "optimize exit $?"; cut -c1-1500 $out/${tag}_optimize_${N}gpu.json; tail -3 $out/${tag}_optimize_${N}gpu.err
 RMI_OPTIMIZER_NO_BATCH=1 timeout 900 python tools/optimize_bench.py --keys $okeys --gpus $N --sample 0 > $out/${tag}_optimize_${N}gpu_nobatch.json 2> $out/${tag}_optimize_${N}gpu_nobatch.err
 echo "optimize (unbatched) exit $?"; cut -c1-600 $out/${tag}_optimize_${N}gpu_nobatch.json
+fi
