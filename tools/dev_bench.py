@@ -21,6 +21,8 @@ if "--quick" in opt:
 if "--long" in opt:   # long training vectors: what each GPU of an 8-GPU sharded build sees (1525 keys per leaf), and beyond
     configs = [("linear,linear", 1 << 20, 0), ("linear,linear", 1 << 18, 0), ("linear,linear", 1 << 17, 0),
                ("linear,linear", 1 << 14, 0), ("cubic,linear", 1 << 18, 0), ("linear,cubic", 1 << 17, 0)]
+if "--spec" in opt:
+    configs = [(opt["--spec"], int(opt.get("--bf", 1 << 20)), 0)]
 if "--one" in opt:
     configs = configs[:1]
 if "--exact" in opt:
