@@ -56,9 +56,6 @@ constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
 #ifndef RMI_FWD_DEPTH
 #define RMI_FWD_DEPTH 8   // 32-key loads in flight per warp in the forward pass
 #endif
-#ifndef RMI_FAR_STEP
-#define RMI_FAR_STEP 1
-#endif
 #ifndef RMI_RC_PREFETCH
 #define RMI_RC_PREFETCH 1
 #endif
@@ -536,33 +533,6 @@ template <bool CHECKED> struct LeafWelford {
     return rc;
   }
   __device__ __forceinline__ void push_t(double x, double y) { push_rc(x, y, table_rc()); }
-  // The same for warps whose longest vector ends past the shared table but inside the global one (RCP_FAR): the
-  // cursor is a pointer into g_rcp_far, the value is fetched TWO steps ahead (an L1 hit takes about one step of the
-  // chain, and the lanes of a warp are within 16 counts of each other, so the lines they touch stay L1-resident), and
-  // the step has no branch — the general step's shared/global/division selection costs ~11 instructions per item.
-  // far_begin() after table_begin()'s owner has pushed nothing yet or a few items (count = nf); far_end() hands the
-  // count back to the general cursor (ra / rc_next) for the steps that follow (the repeated final item).
-  const double* gp;
-  double rc_next2;
-  __device__ __forceinline__ void far_begin() {
-    gp = g_rcp_far + (unsigned)__double2uint_rn(nf);
-    rc_next = __ldg(gp + 1);
-    rc_next2 = __ldg(gp + 2);
-  }
-  __device__ __forceinline__ double far_rc() {
-    const double rc = rc_next;
-    rc_next = rc_next2;
-    ++gp;
-    rc_next2 = __ldg(gp + 2);
-    return rc;
-  }
-  __device__ __forceinline__ void far_end() {
-    ra = (ra_end - (unsigned)((RCP_TABLE - 1) * sizeof(double))) + (unsigned)__double2uint_rn(nf) * (unsigned)sizeof(double);
-#if RMI_RC_PREFETCH
-    rc_next = fetch_rc(ra + (unsigned)sizeof(double), __dadd_rn(nf, 1.0));
-#endif
-  }
-  __device__ __forceinline__ void push_f(double x, double y) { push_rc(x, y, far_rc()); }
   // Items whose y are CONSECUTIVE integers y0, y0+1, ... (a data set without equal keys): the
   // reference's mean_y recurrence is then exact at every step — dy = k/2, dy/k = 0.5, mean_y =
   // y0 + (k-1)/2, y - mean_y' = (k-1)/2, all representable — so the y chain collapses to one
@@ -581,7 +551,6 @@ template <bool CHECKED> struct LeafWelford {
   }
   __device__ __forceinline__ void push_nd(double x) { push_rc_nd(x, next_rc()); }
   __device__ __forceinline__ void push_t_nd(double x) { push_rc_nd(x, table_rc()); }
-  __device__ __forceinline__ void push_f_nd(double x) { push_rc_nd(x, far_rc()); }
   __device__ __forceinline__ void nd_finish(double y0) {
     mean_y = nf > 0.0 ? __dadd_rn(y0, __dadd_rn(hy, -0.5)) : 0.0;
   }
@@ -734,19 +703,19 @@ __device__ __forceinline__ void solo_chain(const T* __restrict__ keys, I s_b, I 
 // Item functors of the hot fit loops.  A functor with prep()/step() lets stream_pass() convert the keys
 // of the NEXT 16-byte piece (prep: int -> double on the XU pipe, ~20 cycles) while the dependent chain of the
 // current piece runs (step), instead of starting every key's chain with its own conversion.
-template <class T, bool CHECKED, bool FAR = false> struct FitStepND {
+template <class T, bool CHECKED> struct FitStepND {
   LeafWelford<CHECKED>& w;
   typedef double Prepared;
   __device__ __forceinline__ Prepared prep(T k) const { return Key<T>::as_float(k); }
-  __device__ __forceinline__ void step(Prepared x) { if (FAR) w.push_f_nd(x); else w.push_t_nd(x); }
+  __device__ __forceinline__ void step(Prepared x) { w.push_t_nd(x); }
   template <class I> __device__ __forceinline__ void operator()(T k, I) { step(prep(k)); }
 };
-template <class T, bool CHECKED, bool DUPS, bool FAR = false> struct FitStepDups {
+template <class T, bool CHECKED, bool DUPS> struct FitStepDups {
   LeafWelford<CHECKED>& w;
   ItemTracker<T, DUPS>& it;
   struct Prepared { double x; T k; };
   __device__ __forceinline__ Prepared prep(T k) const { Prepared p; p.x = Key<T>::as_float(k); p.k = k; return p; }
-  __device__ __forceinline__ void step(const Prepared& p) { if (FAR) w.push_f(p.x, it.next(p.k)); else w.push_t(p.x, it.next(p.k)); }
+  __device__ __forceinline__ void step(const Prepared& p) { w.push_t(p.x, it.next(p.k)); }
   template <class I> __device__ __forceinline__ void operator()(T k, I) { step(prep(k)); }
 };
 // train_model(layer2, vector) for every leaf model type, as warp-synchronous stream passes.
@@ -813,27 +782,6 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
       finalize();
       return;
     }
-#if RMI_FAR_STEP
-    // Warps whose longest vector ends inside the global reciprocal table (763-key vectors: 2^18 leaves on 200M keys;
-    // 1525-key vectors: one GPU's share of a 2^20-leaf build over eight GPUs' keys): the same branch-free step, fed
-    // from g_rcp_far.  The look-ahead reads two entries past the last count used (+1 for the repeated final item).
-    if (LEAF == M_LINEAR && !__any_sync(0xffffffffu, (u64)L + 4 >= (u64)RCP_FAR)) {
-      w.far_begin();
-      if (ND) {
-        FitStepND<T, CHECKED, true> item_nd{w};
-        if (r.p_remote) item_nd(r.pkey, (I)0);
-        stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item_nd);
-        nd_materialise(r.ve);
-      } else {
-        FitStepDups<T, CHECKED, DUPS, true> item_t{w, it};
-        if (r.p_remote) item_t(r.pkey, (I)0);
-        stream_pass<T, I>(keys, n_keys, wsm, r.vs, r.ve, item_t);
-      }
-      w.far_end();
-      finalize();
-      return;
-    }
-#endif
     int solo_lane;
     I solo_at;
     if (ND) {

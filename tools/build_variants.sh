@@ -8,7 +8,6 @@ declare -A DEFS=(
   [cf]="-DRMI_COOP_FORWARD=1"                       # warp-cooperative forward pass fed by 1-D bulk copies (cp.async.bulk + mbarrier tiles)
   [cfr]="-DRMI_COOP_FORWARD=1 -DRMI_FWD_BULK=0"     # the same fed by register look-ahead loads
   [rc0]="-DRMI_RC_PREFETCH=0"                       # general fit step loads 1/n in the step that uses it (no look-ahead)
-  [far0]="-DRMI_FAR_STEP=0"                         # no branch-free step for 512..65532-key vectors (general step instead)
   [s3]="-DRMI_SSTAGES=3 -DRMI_LEAF_MIN_BLOCKS=4"    # three copy stages in the ring (4 blocks per SM)
 )
 names=("$@")
