@@ -1728,9 +1728,11 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
     }
   }
   // ---- every owner publishes its leaf range: an all-gather with per-rank counts (grouped broadcasts) ----------
+  // Not when the records go to the host region all ranks share: each owner has just sent its own range there, nobody
+  // reads another rank's records on the device, and 2-3 broadcasts per rank are the longest part of the exchange.
   if (rc == RMI_OK && W > 1) {
     nccl(nc.GroupStart(), "ncclGroupStart");
-    for (int r = 0; r < W && rc == RMI_OK; ++r) {
+    for (int r = 0; r < W && rc == RMI_OK && !shared; ++r) {
       const uint64_t j0 = b->h_off[r], cnt = b->h_off[r + 1] - b->h_off[r];
       if (cnt == 0) continue;
       double* pp = (double*)b->buf.params + j0 * ppm;

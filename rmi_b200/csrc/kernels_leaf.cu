@@ -56,6 +56,12 @@ constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
 #ifndef RMI_FWD_DEPTH
 #define RMI_FWD_DEPTH 8   // 32-key loads in flight per warp in the forward pass
 #endif
+#ifndef RMI_LONG_FWD_ALL
+#define RMI_LONG_FWD_ALL 1
+#endif
+#ifndef RMI_LONG_FWD_MIN
+#define RMI_LONG_FWD_MIN 1024
+#endif
 #ifndef RMI_RC_PREFETCH
 #define RMI_RC_PREFETCH 1
 #endif
@@ -1415,10 +1421,19 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   // Leaves much longer than their warp's other leaves skip the lane-serial walk (one lane would walk it alone while 31
   // wait): the whole warp evaluates them afterwards with coop_forward, 32 keys per step from bulk-copied tiles.  Worth it
   // only when a few lanes are long (when all 32 are, the lane-serial walks are balanced already).
-  constexpr u64 LONG_FWD = 1024;
+  constexpr u64 LONG_FWD = RMI_LONG_FWD_MIN;
   const bool is_long = live && (g_hi - g_lo) > LONG_FWD;
   const unsigned long_mask = __ballot_sync(0xffffffffu, is_long);   // (all lanes vote: no short-circuit)
+#if RMI_LONG_FWD_ALL
+  // ... or when (nearly) all are: lane-serial walks over vectors this long are balanced but DRAM-latency bound (two 16-key
+  // stages per lane are consumed faster than a copy returns, nothing is left in L2 of a 390 KB warp span), while the
+  // cooperative walk streams 2 KB tiles two ahead and its per-leaf bookkeeping is amortised over 32+ steps.
+  // Measured (profiles/r02_leaf_kernel_experiments.md, 1525-key vectors): cubic leaves 1.10 ms against 1.40 lane-serial;
+  // linear leaves 0.84 against 0.80 — so only where the evaluation is the longer part of a step.
+  const bool long_fwd = is_long && (__popc(long_mask) <= 4 || (LEAF == M_CUBIC && __popc(long_mask) >= 28));
+#else
   const bool long_fwd = is_long && __popc(long_mask) <= 4;
+#endif
   {
     const u64 pol_fwd = l2_policy_of((mode_word >> 6) & 3);
     const I fwd_hi = long_fwd ? r.lo : r.hi;

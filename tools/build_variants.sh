@@ -8,6 +8,8 @@ declare -A DEFS=(
   [cf]="-DRMI_COOP_FORWARD=1"                       # warp-cooperative forward pass fed by 1-D bulk copies (cp.async.bulk + mbarrier tiles)
   [cfr]="-DRMI_COOP_FORWARD=1 -DRMI_FWD_BULK=0"     # the same fed by register look-ahead loads
   [rc0]="-DRMI_RC_PREFETCH=0"                       # general fit step loads 1/n in the step that uses it (no look-ahead)
+  [lfa0]="-DRMI_LONG_FWD_ALL=0"                     # warps whose leaves are all long keep the lane-serial forward pass
+  [lfa512]="-DRMI_LONG_FWD_MIN=512"                 # "long" from 512 keys on
   [s3]="-DRMI_SSTAGES=3 -DRMI_LEAF_MIN_BLOCKS=4"    # three copy stages in the ring (4 blocks per SM)
 )
 names=("$@")

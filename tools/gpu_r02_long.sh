@@ -5,7 +5,7 @@ tag=${1:-r02n}
 out=gpurun_out
 mkdir -p $out
 export PYTHONUNBUFFERED=1
-for lib in librmi_b200.so librmi_b200_far0.so librmi_b200_rc0.so; do
+for lib in $(cd rmi_b200/lib && ls librmi_b200*.so); do
   [ -f rmi_b200/lib/$lib ] || continue
   RMI_B200_LIB=$PWD/rmi_b200/lib/$lib timeout 300 python tools/dev_bench.py --long --iters=6 2>&1 | grep '^{' | sed "s#^{#{\"lib\": \"$lib\", #" >> $out/${tag}_long.jsonl
 done
