@@ -1118,6 +1118,8 @@ struct rmi_shard_build {
   unsigned* d_flags_all = nullptr;      // world x 2
   unsigned* h_flags_all = nullptr;      // pinned mirror
   bool gather_mode = false;             // rmi_shard_train: owners broadcast their leaf ranges, nothing is zero-filled
+  const LeafCopyOut* leaf_copy = nullptr;   // rmi_shard_train with a shared result region: sliced launch of the owned leaf window,
+  u64 leaf_lo = 0, leaf_hi = 0;             //   each slice's records copied to the host while the next slice computes
   // table tops (radix8..28, histogram): the table every rank fills its part of, merged by an all-reduce MAX
   u32* d_table32 = nullptr;             // 2^table_bits hints
   u64* d_pivots = nullptr;              // hist_bins + 1
@@ -1248,8 +1250,10 @@ template <class T> int shard_phase_typed(rmi_shard_build* b, int phase) {
         cudaMemsetAsync(b->buf.errors, 0, sizeof(u64) * b->N, b->st);
         cudaMemsetAsync(b->buf.counts, 0, sizeof(u64) * b->N, b->st);
       }
+      L.copy = b->leaf_copy; L.leaf_lo = b->leaf_lo; L.leaf_hi = b->leaf_hi;
       fit_leaves<T>(L, keys, sh, b->leaf->kind, b->N, (const u64*)b->buf.S, b->d_aux, (double*)b->buf.params,
                     (u64*)b->buf.errors, (u64*)b->buf.counts);
+      L.copy = nullptr; L.leaf_lo = L.leaf_hi = 0;
       shard_copy_status(L, b->d_aux, (unsigned*)b->buf.status);
       break;
     case RMI_PHASE_STATS:
@@ -1705,18 +1709,38 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
     cudaMemcpyAsync(b->h_off, b->d_off, sizeof(u64) * (W + 1), cudaMemcpyDeviceToHost, st);
     cudaEventRecord(b->ev_off, st);
   }
-  // ---- leaves owned by this rank (the host learns the ownership ranges while this runs) ----------------------
+  // ---- leaves owned by this rank ---------------------------------------------------------------------------------
+  // With a shared result region the host waits for the ownership ranges first (a few microseconds of idle GPU) and
+  // launches only the owned leaf window, in slices whose records cross PCIe while the next slice computes — after the
+  // kernel that copy would be exposed (12 MiB at two ranks: 0.2 ms).  Otherwise the whole leaf range is launched at
+  // once (blocks without an owned leaf return immediately) and the host learns the ranges while it runs.
+  LeafCopyOut* co = nullptr;
+  if (shared && rc == RMI_OK) {
+    cudaError_t e = cudaEventSynchronize(b->ev_off);
+    if (e != cudaSuccess) rc = fail(RMI_ERR_CUDA, std::string("rmi_shard_train: ") + cudaGetErrorString(e));
+    co = rc == RMI_OK ? t_slices.get(b->ds->device) : nullptr;
+    if (co) {
+      co->h_params = sh_params; co->h_errors = sh_errors; co->h_counts = sh_counts;
+      co->slices = leaf_slices_default(); co->used = 0;
+      b->leaf_copy = co;
+      b->leaf_lo = b->h_off[rank]; b->leaf_hi = b->h_off[rank + 1];
+      if (b->leaf_hi == 0) b->leaf_lo = b->leaf_hi = N;   // owns nothing (0 would mean "no window")
+    }
+  }
   phase(RMI_PHASE_LEAF);
+  b->leaf_copy = nullptr; b->leaf_lo = b->leaf_hi = 0;
   if (rc == RMI_OK) {
     shard_copy_flags(L, b->d_aux, b->d_flags_mine);
     // statistics of the owned leaves (needs only local results), gathered below
     leaf_statistics_owned(L, b->info.n_global, N, (const u64*)b->buf.errors, (const u64*)b->buf.counts, b->d_off, rank, W,
                           (char*)b->d_parts + stats_partial_bytes() * rank, b->d_stats);
-    if (shared) cudaEventRecord(c->ev_leaf_done, st);
-    cudaError_t e = cudaEventSynchronize(b->ev_off);
-    if (e != cudaSuccess) rc = fail(RMI_ERR_CUDA, std::string("rmi_shard_train: ") + cudaGetErrorString(e));
-    if (shared && rc == RMI_OK) {
-      // this rank's own leaf range goes to the shared host region on a side stream, next to the exchange below
+    if (shared && !co) cudaEventRecord(c->ev_leaf_done, st);
+    if (!shared) {
+      cudaError_t e = cudaEventSynchronize(b->ev_off);
+      if (e != cudaSuccess) rc = fail(RMI_ERR_CUDA, std::string("rmi_shard_train: ") + cudaGetErrorString(e));
+    }
+    if (shared && !co && rc == RMI_OK) {
+      // (no slice streams: copy the owned range after the kernel, on the communicator's side stream)
       const uint64_t j0 = b->h_off[rank], cnt = b->h_off[rank + 1] - b->h_off[rank];
       cudaStreamWaitEvent(c->copy_stream, c->ev_leaf_done, 0);
       if (cnt) {
@@ -1756,8 +1780,9 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
     leaf_statistics_merge(L, b->d_parts, W, b->d_aux);
     cudaEventRecord(b->ev_end[RMI_PHASE_STATS], st);
     if (shared) {
-      // "every rank's copy has landed": an all-reduce each rank enqueues behind its own copy
-      cudaStreamWaitEvent(st, c->ev_copy_done, 0);
+      // "every rank's copy has landed": an all-reduce each rank enqueues behind its own copy (or slice copies)
+      if (co) for (int q = 0; q < co->used; ++q) cudaStreamWaitEvent(st, co->ev_copied[q], 0);
+      else cudaStreamWaitEvent(st, c->ev_copy_done, 0);
       nccl(nc.AllReduce(c->d_token, c->d_token, 1, ncclUint32, ncclMax, comm, st), "ncclAllReduce(result copies landed)");
     }
   }

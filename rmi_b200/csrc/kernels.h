@@ -85,6 +85,10 @@ struct Launch {
   cudaStream_t stream;
   int num_sms;
   const LeafCopyOut* copy = nullptr;   // optional sliced launch + overlapped result copies (fit_leaves)
+  // optional leaf window [leaf_lo, leaf_hi) (leaf_hi == 0: all leaves): fit_leaves launches blocks only for the leaf
+  // groups that intersect it and copies only its records — a rank of a range-partitioned build that already knows
+  // which leaves it owns (the other lanes of the boundary groups are not its leaves and stay idle)
+  u64 leaf_lo = 0, leaf_hi = 0;
   // optional fork/join resources for the long-leaf kernel (kernels_leaf.cu); all null = disabled
   cudaStream_t side = nullptr;       // high-priority stream
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

@@ -1301,7 +1301,7 @@ template <class T, class I, int LEAF, bool DUPS>
 __global__ void RMI_LEAF_BOUNDS
 k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restrict__ S, BuildAux* aux,
        double* __restrict__ params, u64* __restrict__ errors, u64* __restrict__ counts,
-       const u32* __restrict__ long_list, int mode_word, u32 block_offset, u32 total_blocks) {
+       const u32* __restrict__ long_list, int mode_word, u32 block_offset, u32 total_blocks, u32 group_base) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_rcp = reinterpret_cast<double*>(smem_raw);
   unsigned char* wsm = smem_raw + (size_t)RCP_TABLE * sizeof(double) + (size_t)(threadIdx.x >> 5) * WARP_STREAM_BYTES;
@@ -1320,7 +1320,8 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   // [block_offset, block_offset + gridDim.x) of total_blocks (results of a slice are copied to
   // the host while the next slice computes); slice 0 starts with the outermost groups.
   const u32 gb = blockIdx.x + block_offset;
-  const u64 group = (gb & 1u) ? (u64)total_blocks - 1 - (gb >> 1) : (u64)(gb >> 1);
+  // (group_base: the launch covers the leaf groups [group_base, group_base + total_blocks) only)
+  const u64 group = (u64)group_base + ((gb & 1u) ? (u64)total_blocks - 1 - (gb >> 1) : (u64)(gb >> 1));
   const u64 j = long_mode == 1 ? (threadIdx.x == 0 ? (u64)long_list[1 + blockIdx.x] : N)
                                : group * blockDim.x + threadIdx.x;
   constexpr int PPM = leaf_params_per_model(LEAF);
@@ -1733,7 +1734,11 @@ void ensure_rcp_far() {
 template <class T, class I, int LEAF, bool DUPS>
 void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N, const u64* d_S, BuildAux* d_aux,
                       double* d_params, u64* d_errors, u64* d_counts) {
-  u64 blocks = (N + LEAF_THREADS - 1) / LEAF_THREADS;
+  // leaf window of this launch (Launch::leaf_lo/hi), in leaf groups of LEAF_THREADS leaves
+  const u64 win_lo = L.leaf_hi ? (L.leaf_lo < N ? L.leaf_lo : N) : 0, win_hi = L.leaf_hi ? (L.leaf_hi < N ? L.leaf_hi : N) : N;
+  const u64 G0 = win_lo / LEAF_THREADS, G1 = win_hi > win_lo ? (win_hi + LEAF_THREADS - 1) / LEAF_THREADS : G0;
+  u64 blocks = G1 - G0;
+  const u32 gbase = (u32)G0;
   static const size_t pad = [] { const char* e = getenv("RMI_DEV_LEAF_SMEM_PAD"); return e ? (size_t)atol(e) : (size_t)0; }();
   const size_t smem = leaf_smem_bytes() + pad;   // dev knob: extra shared memory = fewer resident blocks
   // L2 eviction priority of the key copies: fit pass (bits 4-5), forward pass (bits 6-7);
@@ -1767,7 +1772,7 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
     cudaEventRecord(L.ev_fork, L.stream);
     cudaStreamWaitEvent(L.side, L.ev_fork, 0);
     k_leaf<T, I, LEAF, DUPS><<<LONG_LEAF_CAP, 32, LONG_LEAF_SMEM, L.side>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts, L.d_long,
-                                                                            1 | l2_mode, 0u, LONG_LEAF_CAP);
+                                                                            1 | l2_mode, 0u, LONG_LEAF_CAP, 0u);
     count_launch();
     cudaEventRecord(L.ev_join, L.side);
   }
@@ -1776,17 +1781,20 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
   int K = (co && co->slices > 1) ? (co->slices < MAX_LEAF_SLICES ? co->slices : MAX_LEAF_SLICES) : 1;
   if (blocks < (u64)K * 64 || blocks >= 0xffffffffull) K = 1;   // too small to be worth slicing
   if (K == 1) {
-    k_leaf<T, I, LEAF, DUPS><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts,
-                                                                                long_list, l2_mode, 0u, (u32)blocks);
-    count_launch();
+    if (blocks) {
+      k_leaf<T, I, LEAF, DUPS><<<(unsigned)blocks, LEAF_THREADS, smem, L.stream>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts,
+                                                                                  long_list, l2_mode, 0u, (u32)blocks, gbase);
+      count_launch();
+    }
     if (fork) cudaStreamWaitEvent(L.stream, L.ev_join, 0);
     if (co) {
       co->used = 0;
-      if (co->h_params) {   // unsliced, but the caller still expects the results on the host
+      if (co->h_params && win_hi > win_lo) {   // unsliced, but the caller still expects the results on the host
         constexpr int PPM = leaf_params_per_model(LEAF);
-        cudaMemcpyAsync(co->h_params, d_params, sizeof(double) * N * PPM, cudaMemcpyDeviceToHost, L.stream);
-        cudaMemcpyAsync(co->h_errors, d_errors, sizeof(u64) * N, cudaMemcpyDeviceToHost, L.stream);
-        if (co->h_counts) cudaMemcpyAsync(co->h_counts, d_counts, sizeof(u64) * N, cudaMemcpyDeviceToHost, L.stream);
+        const u64 cnt = win_hi - win_lo;
+        cudaMemcpyAsync(co->h_params + win_lo * PPM, d_params + win_lo * PPM, sizeof(double) * cnt * PPM, cudaMemcpyDeviceToHost, L.stream);
+        cudaMemcpyAsync(co->h_errors + win_lo, d_errors + win_lo, sizeof(u64) * cnt, cudaMemcpyDeviceToHost, L.stream);
+        if (co->h_counts) cudaMemcpyAsync(co->h_counts + win_lo, d_counts + win_lo, sizeof(u64) * cnt, cudaMemcpyDeviceToHost, L.stream);
       }
     }
     return;
@@ -1822,7 +1830,7 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
     cudaStream_t st = co->streams[used];
     cudaStreamWaitEvent(st, co->ev_ready, 0);
     k_leaf<T, I, LEAF, DUPS><<<cnt, LEAF_THREADS, smem, st>>>(keys, sh, N, d_S, d_aux, d_params, d_errors, d_counts, long_list,
-                                                              l2_mode, off, total);
+                                                              l2_mode, off, total, gbase);
     count_launch();
     cudaEventRecord(co->ev_kernel[used], st);
     cudaStreamWaitEvent(L.stream, co->ev_kernel[used], 0);
@@ -1831,9 +1839,10 @@ void launch_leaf_inst(const Launch& L, const T* keys, const Shard<T>& sh, u64 N,
     const u64 f0 = off / 2, f1 = (off + cnt + 1) / 2;                 // front groups [f0, f1)
     const u64 nb = (off + cnt) / 2 - off / 2;                          // number of odd ids in [off, off+cnt) (off is even)
     const u64 b1 = (u64)total - off / 2, b0 = b1 - nb;                 // back groups [b0, b1)
-    auto copy_groups = [&](u64 g0, u64 g1) {
-      u64 l0 = g0 * LEAF_THREADS, l1 = g1 * LEAF_THREADS;
-      if (l1 > N) l1 = N;
+    auto copy_groups = [&](u64 g0, u64 g1) {   // groups relative to the window's first group
+      u64 l0 = (G0 + g0) * LEAF_THREADS, l1 = (G0 + g1) * LEAF_THREADS;
+      if (l0 < win_lo) l0 = win_lo;
+      if (l1 > win_hi) l1 = win_hi;
       if (l0 >= l1) return;
       cudaMemcpyAsync(co->h_params + l0 * PPM, d_params + l0 * PPM, sizeof(double) * (l1 - l0) * PPM, cudaMemcpyDeviceToHost, st);
       cudaMemcpyAsync(co->h_errors + l0, d_errors + l0, sizeof(u64) * (l1 - l0), cudaMemcpyDeviceToHost, st);
