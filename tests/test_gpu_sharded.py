@@ -101,7 +101,9 @@ CASES = [("uniform", "linear,linear", 1024), ("uniform", "radix,linear", 4096), 
          ("uniform", "cubic,linear", 1024), ("dups", "cubic,linear", 300), ("lognormal", "cubic,linear_spline", 128),
          ("uniform", "normal,linear", 256), ("lognormal", "lognormal,linear", 200),
          ("uniform", "radix18,linear", 2048), ("dups", "radix8,linear", 200), ("lognormal", "histogram,linear", 512),
-         ("uniform", "histogram,linear_spline", 1000)]
+         ("uniform", "histogram,linear_spline", 1000),
+         # enough leaves per rank for the sliced launch of the owned leaf window (shared result region, one-call path)
+         ("uniform", "linear,linear", 131072), ("dups", "linear_spline,linear", 98304)]
 
 
 @pytest.mark.parametrize("kind,spec,N", CASES, ids=[f"{c[0]}-{c[1]}-{c[2]}" for c in CASES])

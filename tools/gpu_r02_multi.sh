@@ -9,8 +9,8 @@ mkdir -p $out
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm --format=csv > $out/${tag}_smi.txt 2>&1
 nvidia-smi topo -m >> $out/${tag}_smi.txt 2>&1
-timeout 300 python tools/dev_shard_time.py > $out/${tag}_shard_time.json 2> $out/${tag}_shard_time.err; cat $out/${tag}_shard_time.json
-timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q -m gpu > $out/${tag}_pytest_sharded.log 2>&1
+[ "$4" = shardtime ] && timeout 300 python tools/dev_shard_time.py > $out/${tag}_shard_time.json 2> $out/${tag}_shard_time.err; cat $out/${tag}_shard_time.json
+timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q -m gpu ${PYTEST_K:+-k "$PYTEST_K"} > $out/${tag}_pytest_sharded.log 2>&1
 echo "pytest sharded exit $?" >> $out/${tag}_pytest_sharded.log
 tail -4 $out/${tag}_pytest_sharded.log
 for n in $(seq 2 $N | awk -v N=$N '{ if ($1==2 || $1==4 || $1==8) print $1 }'); do
