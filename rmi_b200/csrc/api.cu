@@ -1681,9 +1681,22 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
   auto nccl = [&](ncclResult_t r, const char* what) {
     if (rc == RMI_OK && r != ncclSuccess) rc = fail(RMI_ERR_CUDA, std::string(what) + ": " + nc.GetErrorString(r));
   };
+  // RMI_DEV_SHARD_TRACE=1: device time between the marks below, printed per build by every rank (developer probe)
+  static const bool trace = [] { const char* e = getenv("RMI_DEV_SHARD_TRACE"); return e && e[0] == '1'; }();
+  struct Mark { const char* what; cudaEvent_t ev; };
+  static thread_local std::vector<Mark> marks;
+  size_t n_marks = 0;
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    if (n_marks == marks.size()) { Mark m{what, nullptr}; cudaEventCreate(&m.ev); marks.push_back(m); }
+    marks[n_marks].what = what;
+    cudaEventRecord(marks[n_marks++].ev, st);
+  };
   cudaEventRecord(b->ev_t0, st);
+  mark("start");
   // ---- top model: local part, 0-2 tiny all-reduces, closed form (identical on every rank) -----------------
   phase(RMI_PHASE_TOP_LOCAL);
+  mark("top local");
   const int rounds = rmi_shard_top_rounds(b->top->name);
   if (W > 1 && rc == RMI_OK) {
     if (rounds == 1 || rounds == 2) nccl(nc.AllReduce(sums, sums, 8, ncclFloat64, ncclSum, comm, st), "ncclAllReduce(top sums)");
@@ -1699,16 +1712,21 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
     phase(RMI_PHASE_TOP_MID);
     if (W > 1 && rc == RMI_OK) nccl(nc.AllReduce(sums, sums, 8, ncclFloat64, ncclSum, comm, st), "ncclAllReduce(top sums, round 2)");
   }
+  mark("top all-reduces");
   phase(RMI_PHASE_TOP_FINISH);
+  mark("top finish");
   // ---- leaf boundaries: local lower bounds -> all-reduce MIN; split; who owns which leaves -----------------
   phase(RMI_PHASE_BOUNDS);
+  mark("bounds");
   if (W > 1 && rc == RMI_OK) nccl(nc.AllReduce(b->buf.S, b->buf.S, N + 1, ncclUint64, ncclMin, comm, st), "ncclAllReduce(leaf boundaries)");
+  mark("bounds all-reduce");
   phase(RMI_PHASE_SPLIT);
   if (rc == RMI_OK) {
     shard_owner_offsets(L, (const u64*)b->buf.S, N, b->d_bases, W, b->r_last, b->d_off);
     cudaMemcpyAsync(b->h_off, b->d_off, sizeof(u64) * (W + 1), cudaMemcpyDeviceToHost, st);
     cudaEventRecord(b->ev_off, st);
   }
+  mark("split + owner offsets");
   // ---- leaves owned by this rank ---------------------------------------------------------------------------------
   // With a shared result region the host waits for the ownership ranges first (a few microseconds of idle GPU) and
   // launches only the owned leaf window, in slices whose records cross PCIe while the next slice computes — after the
@@ -1728,6 +1746,7 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
     }
   }
   phase(RMI_PHASE_LEAF);
+  mark("leaf (incl. host wait for the offsets)");
   b->leaf_copy = nullptr; b->leaf_lo = b->leaf_hi = 0;
   if (rc == RMI_OK) {
     shard_copy_flags(L, b->d_aux, b->d_flags_mine);
@@ -1751,6 +1770,7 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
       cudaEventRecord(c->ev_copy_done, c->copy_stream);
     }
   }
+  mark("flags + owned statistics");
   // ---- every owner publishes its leaf range: an all-gather with per-rank counts (grouped broadcasts) ----------
   // Not when the records go to the host region all ranks share: each owner has just sent its own range there, nobody
   // reads another rank's records on the device, and 2-3 broadcasts per rank are the longest part of the exchange.
@@ -1775,10 +1795,12 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
   } else if (rc == RMI_OK) {
     cudaMemcpyAsync(b->d_flags_all, b->d_flags_mine, 2 * sizeof(unsigned), cudaMemcpyDeviceToDevice, st);
   }
+  mark("gather group");
   if (rc == RMI_OK) {
     if (b->ran[RMI_PHASE_STATS] == false) { cudaEventRecord(b->ev_begin[RMI_PHASE_STATS], st); b->ran[RMI_PHASE_STATS] = true; }
     leaf_statistics_merge(L, b->d_parts, W, b->d_aux);
     cudaEventRecord(b->ev_end[RMI_PHASE_STATS], st);
+    mark("statistics merge");
     if (shared) {
       // "every rank's copy has landed": an all-reduce each rank enqueues behind its own copy (or slice copies)
       if (co) for (int q = 0; q < co->used; ++q) cudaStreamWaitEvent(st, co->ev_copied[q], 0);
@@ -1786,6 +1808,7 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
       nccl(nc.AllReduce(c->d_token, c->d_token, 1, ncclUint32, ncclMax, comm, st), "ncclAllReduce(result copies landed)");
     }
   }
+  mark("copies landed + barrier");
   cudaEventRecord(b->ev_t1, st);
   if (rc != RMI_OK) { cudaStreamSynchronize(st); delete box; return rc; }
   // ---- results to the host ------------------------------------------------------------------------------------
@@ -1807,6 +1830,17 @@ static int shard_train_typed(rmi_shard_build* b, rmi_shard_comm* c, uint32_t fla
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) { delete box; return fail(RMI_ERR_CUDA, std::string("rmi_shard_train: ") + cudaGetErrorString(e)); }
+  if (trace && n_marks > 1) {
+    std::string line = "[rmi_b200 shard trace] rank " + std::to_string(rank) + ":";
+    char buf[96];
+    for (size_t q = 1; q < n_marks; ++q) {
+      float dt = 0.f;
+      cudaEventElapsedTime(&dt, marks[q - 1].ev, marks[q].ev);
+      std::snprintf(buf, sizeof buf, " | %s %.3f", marks[q].what, dt);
+      line += buf;
+    }
+    std::fprintf(stderr, "%s\n", line.c_str());
+  }
   unsigned st_all = b->host_status;
   bool cnr = false;
   for (int r = 0; r < W; ++r) { st_all |= b->h_flags_all[2 * r]; cnr = cnr || b->h_flags_all[2 * r + 1] != 0; }
