@@ -62,6 +62,9 @@ constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
 #ifndef RMI_LONG_FWD_MIN
 #define RMI_LONG_FWD_MIN 1024
 #endif
+#ifndef RMI_RCP_RING
+#define RMI_RCP_RING 1
+#endif
 #ifndef RMI_RC_PREFETCH
 #define RMI_RC_PREFETCH 1
 #endif
@@ -235,6 +238,13 @@ template <class F> struct has_prep {
   static constexpr bool value = sizeof(test<F>(nullptr)) == sizeof(char);
 };
 
+// item functors with a chunk_begin(active) member are called once per chunk, by the whole warp, before the chunk's items
+template <class F> struct has_chunk_hook {
+  template <class U> static char test(typename U::ChunkHook*);
+  template <class U> static long test(...);
+  static constexpr bool value = sizeof(test<F>(nullptr)) == sizeof(char);
+};
+
 constexpr int SOLO_MIN = 384;
 template <class T, class I, class Fn, bool SOLO = false>
 __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_policy, unsigned char* wsm, I b, I e,
@@ -325,6 +335,7 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
     __syncwarp();
     const unsigned char* row = wsm + (int)(c % SSTAGES) * STAGE_BYTES + lane * ROW_BYTES;   // this lane's row; piece q at + q * PIECE_STRIDE
     const I cbase = (I)c * (I)SW;
+    if constexpr (has_chunk_hook<typename std::remove_reference<Fn>::type>::value) fn.chunk_begin(rlen > cbase);
     // A chunk is "full" when every lane still has all SW positions on the high side.  The low side
     // matters in chunk 0 only (a stream starts at the 16-byte piece that holds index b, so up to
     // KPP-1 leading positions are not the lane's): there the first piece is walked under a per-lane
@@ -539,6 +550,52 @@ template <bool CHECKED> struct LeafWelford {
     return rc;
   }
   __device__ __forceinline__ void push_t(double x, double y) { push_rc(x, y, table_rc()); }
+  // Vectors that outgrow the shared table: a 64-entry ring of reciprocals per WARP, refilled once per 16-key chunk.
+  // The lanes of a warp walk their vectors in lockstep (every stream starts at a 16-byte boundary: their item counts
+  // differ by at most 2, plus a remote first item), so one window of counts serves all of them; a chunk needs 16 new
+  // entries, computed by lanes 0-15 (one __drcp_rn each — the values of the shared table, for any count).  The step
+  // is then the table step: no branch, the value fetched one step ahead.  (The general step's selection between the
+  // shared table, the global table and a division cost ~11 instructions per item and 19% of the stall samples of a
+  // build with 1525-key vectors.)
+  unsigned ring;       // shared address of the warp's ring, 512-byte aligned
+  unsigned rq;         // 8 x (items pushed + 1): byte offset of the next step's entry, before wrapping
+  unsigned ring_hi;    // warp-uniform: entries [.., ring_hi) are in the ring
+  static constexpr unsigned RING_MASK = 63u * 8u;
+  __device__ __forceinline__ void ring_fill(unsigned upto) {   // whole warp
+    for (unsigned e = ring_hi + (threadIdx.x & 31); e < upto; e += 32) {
+      const double v = __drcp_rn((double)e);
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(ring | ((e * 8u) & RING_MASK)), "d"(v) : "memory");
+    }
+    if (upto > ring_hi) ring_hi = upto;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void ring_begin(unsigned ring_addr) {   // whole warp, before the first push
+    ring = ring_addr;
+    ring_hi = 1;
+    rq = ((unsigned)__double2uint_rn(nf) + 1u) * 8u;
+    ring_fill(48);
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rc_next) : "r"(ring | (rq & RING_MASK)) : "memory");
+  }
+  // whole warp, once per chunk; `active` = this lane still has items in the chunk
+  __device__ __forceinline__ void ring_chunk(bool active) {
+    const unsigned cmin = __reduce_min_sync(0xffffffffu, active ? (rq >> 3) : 0xffffffffu);   // next count of the slowest lane
+    if (cmin == 0xffffffffu) return;
+    // this chunk uses counts up to cmin + 2 + 16 (+1 fetched ahead); entries below cmin are dead: 64 slots cover both
+    ring_fill(cmin + 40);
+  }
+  __device__ __forceinline__ double ring_rc() {
+    const double rc = rc_next;
+    rq += (unsigned)sizeof(double);
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rc_next) : "r"(ring | (rq & RING_MASK)) : "memory");
+    return rc;
+  }
+  // back to the general cursor (ra, rc_next stays valid: it is the reciprocal of items + 1)
+  __device__ __forceinline__ void ring_end() {
+    ra = (ra_end - (unsigned)((RCP_TABLE - 1) * sizeof(double))) + (rq - (unsigned)sizeof(double));
+#if !RMI_RC_PREFETCH
+    (void)0;
+#endif
+  }
   // Items whose y are CONSECUTIVE integers y0, y0+1, ... (a data set without equal keys): the
   // reference's mean_y recurrence is then exact at every step — dy = k/2, dy/k = 0.5, mean_y =
   // y0 + (k-1)/2, y - mean_y' = (k-1)/2, all representable — so the y chain collapses to one
@@ -724,13 +781,33 @@ template <class T, bool CHECKED, bool DUPS> struct FitStepDups {
   __device__ __forceinline__ void step(const Prepared& p) { w.push_t(p.x, it.next(p.k)); }
   template <class I> __device__ __forceinline__ void operator()(T k, I) { step(prep(k)); }
 };
+// The same steps fed from the warp's reciprocal ring (vectors of any length), with the per-chunk refill hook.
+template <class T, bool CHECKED> struct RingStepND {
+  LeafWelford<CHECKED>& w;
+  typedef double Prepared;
+  typedef void ChunkHook;
+  __device__ __forceinline__ void chunk_begin(bool active) { w.ring_chunk(active); }
+  __device__ __forceinline__ Prepared prep(T k) const { return Key<T>::as_float(k); }
+  __device__ __forceinline__ void step(Prepared x) { w.push_rc_nd(x, w.ring_rc()); }
+  template <class I> __device__ __forceinline__ void operator()(T k, I) { step(prep(k)); }
+};
+template <class T, bool CHECKED, bool DUPS> struct RingStepDups {
+  LeafWelford<CHECKED>& w;
+  ItemTracker<T, DUPS>& it;
+  struct Prepared { double x; T k; };
+  typedef void ChunkHook;
+  __device__ __forceinline__ void chunk_begin(bool active) { w.ring_chunk(active); }
+  __device__ __forceinline__ Prepared prep(T k) const { Prepared p; p.x = Key<T>::as_float(k); p.k = k; return p; }
+  __device__ __forceinline__ void step(const Prepared& p) { w.push_rc(p.x, it.next(p.k), w.ring_rc()); }
+  template <class I> __device__ __forceinline__ void operator()(T k, I) { step(prep(k)); }
+};
 // train_model(layer2, vector) for every leaf model type, as warp-synchronous stream passes.
 // f receives Model::params().  Every lane of the warp must call this (with vs == ve if it has
 // no leaf or an empty vector).
 template <class T, class I, int LEAF, bool DUPS>
 __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard<T>& sh, unsigned char* wsm,
                                          const LeafRange<T, I>& r, const double* rcp, double* f, unsigned& bad,
-                                         u64 l2_policy) {
+                                         u64 l2_policy, unsigned rcp_ring) {
   const u64 n_keys = l2_policy;   // handed to every stream_pass below
   const I L = (I)(r.ve - r.vs) + (r.p_remote ? (I)1 : (I)0);
   const T kfirst = r.p_remote ? r.pkey : (L ? keys[r.vs] : T());
@@ -790,7 +867,27 @@ __device__ __forceinline__ void fit_leaf(const T* __restrict__ keys, const Shard
     }
     int solo_lane;
     I solo_at;
-    if (ND) {
+#if RMI_RCP_RING
+    // vectors below 2^28 items (the ring's 32-bit cursor); a warp with a longer one takes the general step
+    const bool ring_ok = LEAF == M_LINEAR && !__any_sync(0xffffffffu, (u64)L >= (1ull << 28));
+#else
+    const bool ring_ok = false;
+#endif
+    if (ring_ok) {
+      w.ring_begin(rcp_ring);
+      if (ND) {
+        RingStepND<T, CHECKED> item_r{w};
+        if (r.p_remote) item_r(r.pkey, (I)0);
+        stream_pass<T, I, RingStepND<T, CHECKED>&, true>(keys, n_keys, wsm, r.vs, r.ve, item_r, &solo_lane, &solo_at);
+        w.ring_end();
+        nd_materialise((solo_lane == (int)(threadIdx.x & 31)) ? solo_at : r.ve);
+      } else {
+        RingStepDups<T, CHECKED, DUPS> item_r{w, it};
+        if (r.p_remote) item_r(r.pkey, (I)0);
+        stream_pass<T, I, RingStepDups<T, CHECKED, DUPS>&, true>(keys, n_keys, wsm, r.vs, r.ve, item_r, &solo_lane, &solo_at);
+        w.ring_end();
+      }
+    } else if (ND) {
       auto item_nd = [&](T k, I) { w.push_nd(Key<T>::as_float(k)); };
       if (r.p_remote) item_nd(r.pkey, (I)0);
       stream_pass<T, I, decltype(item_nd)&, true>(keys, n_keys, wsm, r.vs, r.ve, item_nd, &solo_lane, &solo_at);
@@ -1293,8 +1390,10 @@ k_find_long(const Shard<T> sh, u64 N, const u64* __restrict__ S, u32* __restrict
   }
 }
 
+constexpr int RCP_RING_BYTES = 64 * 8;   // per warp (LeafWelford::ring), 512-byte aligned: one extra ring of slack per block
 constexpr size_t leaf_smem_bytes() {
-  return (size_t)RCP_TABLE * sizeof(double) + (size_t)(LEAF_THREADS / 32) * WARP_STREAM_BYTES;
+  return (size_t)RCP_TABLE * sizeof(double) + (size_t)(LEAF_THREADS / 32) * WARP_STREAM_BYTES +
+         (size_t)(LEAF_THREADS / 32 + 1) * RCP_RING_BYTES;
 }
 
 template <class T, class I, int LEAF, bool DUPS>
@@ -1387,7 +1486,11 @@ k_leaf(const T* __restrict__ keys, const Shard<T> sh, u64 N, const u64* __restri
   if (live && g_hi > sh.base + sh.n_avail) { bad |= ST_HALO_TOO_SMALL; r.hi = r.lo; }
 
   double f[4] = {0.0, 0.0, 0.0, 0.0};
-  fit_leaf<T, I, LEAF, DUPS>(keys, sh, wsm, r, s_rcp, f, bad, l2_policy_of((mode_word >> 4) & 3));
+  // the warp's reciprocal ring: behind every warp's copy ring, aligned up to 512 bytes
+  const unsigned rings0 = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)RCP_TABLE * sizeof(double) +
+                                                             (size_t)(blockDim.x >> 5) * WARP_STREAM_BYTES);
+  const unsigned rcp_ring = ((rings0 + (unsigned)RCP_RING_BYTES - 1u) & ~((unsigned)RCP_RING_BYTES - 1u)) + (threadIdx.x >> 5) * (unsigned)RCP_RING_BYTES;
+  fit_leaf<T, I, LEAF, DUPS>(keys, sh, wsm, r, s_rcp, f, bad, l2_policy_of((mode_word >> 4) & 3), rcp_ring);
 
   // two_layer.rs:186-197: empty leaves (lower-bound-correction sense) except the last
   const u64 next_idx = g_hi;                                        // lb.next_index(j) = S[j+1]

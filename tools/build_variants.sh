@@ -10,6 +10,7 @@ declare -A DEFS=(
   [rc0]="-DRMI_RC_PREFETCH=0"                       # general fit step loads 1/n in the step that uses it (no look-ahead)
   [lfa0]="-DRMI_LONG_FWD_ALL=0"                     # warps whose leaves are all long keep the lane-serial forward pass
   [lfa512]="-DRMI_LONG_FWD_MIN=512"                 # "long" from 512 keys on
+  [ring0]="-DRMI_RCP_RING=0"                        # vectors past the shared table: general step (table / global table / division per item)
   [s3]="-DRMI_SSTAGES=3 -DRMI_LEAF_MIN_BLOCKS=4"    # three copy stages in the ring (4 blocks per SM)
 )
 names=("$@")
