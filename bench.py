@@ -565,10 +565,12 @@ def main():
                "parallelism": "1 GPU" if world == 1 else
                f"range-partitioned over {world} GPUs: ONE RMI with {N} leaves over {n * world} keys; per build, all on one stream in "
                "one library call (rmi_shard_train): all-reduce of the top-model sums (64 B) and of the leaf boundaries ((N+1)*8 B), "
-               "all-gather of the leaf records by ownership range (N*24 B), all-gather of the per-rank statistics; the leaf tables "
-               "are copied to the host on rank 0; halo keys between neighbours are fetched once per data set",
+               "all-gather of the per-rank statistics and status words, a one-word all-reduce when every rank's result copy has "
+               "landed; every rank launches only the leaves it owns, in slices whose records (N*24 B in total) go straight into a "
+               "pinned host region shared by the ranks of the node while the next slice computes — rank 0's result points into it "
+               "(RMI_FLAG_SHARD_ROOT_ONLY); halo keys between neighbours are fetched once per data set",
                "timing": "CUDA events around K synchronous builds, max over ranks",
-               "roofline_note": "dominant kernel = the fused leaf fit + forward pass (k_leaf); on one GPU it runs as 4 launch slices "
+               "roofline_note": "dominant kernel = the fused leaf fit + forward pass (k_leaf); it runs as 5 launch slices "
                                 "per build (their results cross PCIe while the next slice computes): achieved = algorithmic bytes of "
                                 "all slices / the leaf phase's device time; traffic = ncu DRAM bytes summed over the slices of one "
                                 "build, from the committed capture profiles/dominant_kernel_traffic.json (N = 1 only)",
