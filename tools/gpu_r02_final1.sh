@@ -14,10 +14,12 @@ echo "smoke exit $?" >> $out/${tag}_smoke.log
 tail -2 $out/${tag}_smoke.log
 timeout 900 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
 echo "bench exit $?"; cut -c1-600 $out/${tag}_bench_n1.json
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
+echo "reference arm exit $?"; cut -c1-500 $out/${tag}_bench_ref.json
 timeout 300 python tools/dev_bench.py --iters=5 > $out/${tag}_dev_bench.jsonl 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
    --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > $out/${tag}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_leaf -s 10 -c 6 \
    -o $out/${tag}_k_leaf_full -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > $out/${tag}_ncu_full.log 2>&1
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
-echo "reference arm exit $?"; cut -c1-500 $out/${tag}_bench_ref.json
+timeout 600 python tools/optimize_bench.py --keys 200e6 --gpus 1 --sample 0 > $out/${tag}_optimize_1gpu.json 2> $out/${tag}_optimize_1gpu.err
+echo "optimize exit $?"; cut -c1-400 $out/${tag}_optimize_1gpu.json
