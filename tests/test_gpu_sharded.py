@@ -107,7 +107,7 @@ CASES = [("uniform", "linear,linear", 1024), ("uniform", "radix,linear", 4096), 
 
 
 @pytest.mark.parametrize("kind,spec,N", CASES, ids=[f"{c[0]}-{c[1]}-{c[2]}" for c in CASES])
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [int(w) for w in os.environ.get("RMI_TEST_WORLDS", "2,3").split(",")])
 def test_sharded_cuda_build_equals_oracle(oracle, world, kind, spec, N):
     import torch.multiprocessing as mp
     n = 150_000
