@@ -65,6 +65,9 @@ constexpr int LEAF_THREADS = RMI_LEAF_THREADS;
 #ifndef RMI_RCP_RING
 #define RMI_RCP_RING 1
 #endif
+#ifndef RMI_PARTIAL_UNROLLED
+#define RMI_PARTIAL_UNROLLED 0
+#endif
 #ifndef RMI_RC_PREFETCH
 #define RMI_RC_PREFETCH 1
 #endif
@@ -406,8 +409,33 @@ __device__ __forceinline__ void stream_pass(const T* __restrict__ keys, u64 l2_p
       // own [p0, p1), whole 16-byte pieces with one 128-bit shared load each, single keys at the ends
       const I lo_k = (c == 0) ? skip : (I)0;
       const I rem = rlen > cbase ? (I)(rlen - cbase) : (I)0;
-      int pos = (int)lo_k;
       const int p1 = rem < (I)SW ? (int)rem : SW;
+#if RMI_PARTIAL_UNROLLED
+      // The lanes of a warp end in different chunks (190 +- 14 keys per leaf: the last three or four chunks of a warp
+      // each hold some lane's end), so about a quarter of all keys pass through here, most of them on lanes that still
+      // have the whole chunk.  Fixed trip count and compile-time shared-memory offsets like the vector path, with one
+      // predicate per piece and one per further key of the piece, instead of three position-driven loops.
+      {
+        const int lo = (int)lo_k;
+        const I idx0 = a + cbase;
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          if (pp * KPP < p1) {
+            uint4 v = *reinterpret_cast<const uint4*>(row + pp * PIECE_STRIDE);
+            T kk[KPP];
+            memcpy(kk, &v, 16);
+#pragma unroll
+            for (int t = 0; t < KPP; ++t) {
+              const int q = pp * KPP + t;
+              if ((pp > 0 || q >= lo) && (t == 0 || q < p1)) fn(kk[t], (I)(idx0 + (I)q));
+            }
+          }
+        }
+      }
+      __syncwarp();
+      continue;
+#endif
+      int pos = (int)lo_k;
       auto key_at = [&](int q) {   // key at position q of this lane's row
         return *reinterpret_cast<const T*>(row + (q / KPP) * PIECE_STRIDE + (q % KPP) * (int)sizeof(T));
       };

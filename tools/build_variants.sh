@@ -11,6 +11,7 @@ declare -A DEFS=(
   [lfa0]="-DRMI_LONG_FWD_ALL=0"                     # warps whose leaves are all long keep the lane-serial forward pass
   [lfa512]="-DRMI_LONG_FWD_MIN=512"                 # "long" from 512 keys on
   [ring0]="-DRMI_RCP_RING=0"                        # vectors past the shared table: general step (table / global table / division per item)
+  [pu]="-DRMI_PARTIAL_UNROLLED=1"                   # chunks in which some lane ends: unrolled, predicated pieces instead of position-driven loops
   [s3]="-DRMI_SSTAGES=3 -DRMI_LEAF_MIN_BLOCKS=4"    # three copy stages in the ring (4 blocks per SM)
 )
 names=("$@")
