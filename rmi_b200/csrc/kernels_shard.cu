@@ -468,13 +468,22 @@ k_shard_bounds_search(const T* __restrict__ keys, const Shard<T> sh, const TopMo
   u64 v;
   if (j == N) v = sh.n_global;
   else if (j == 0) v = 0;
+  else if (sh.n_local == 0) v = sh.n_global;
   else {
-    u64 lo = 0, hi = sh.n_local;
-    while (lo < hi) {
-      u64 mid = lo + ((hi - lo) >> 1);
-      if (top_predict<TOP>(m, keys[mid]) >= j) hi = mid; else lo = mid + 1;
+    // Predictions are non-decreasing over the sorted keys (these tops are monotone by construction), so only the
+    // leaves between the slab's first and last prediction can begin inside it: the others get what the search would
+    // return without running it — on W ranks each rank searches about N / W boundaries instead of N.
+    const u64 p_first = top_predict<TOP>(m, keys[0]), p_last = top_predict<TOP>(m, keys[sh.n_local - 1]);
+    if (j <= p_first) v = sh.base;
+    else if (j > p_last) v = sh.n_global;
+    else {
+      u64 lo = 1, hi = sh.n_local - 1;   // keys[0] predicts < j, keys[n_local - 1] predicts >= j
+      while (lo < hi) {
+        u64 mid = lo + ((hi - lo) >> 1);
+        if (top_predict<TOP>(m, keys[mid]) >= j) hi = mid; else lo = mid + 1;
+      }
+      v = sh.base + lo;
     }
-    v = lo < sh.n_local ? sh.base + lo : sh.n_global;
   }
   S[j] = v;
 }
