@@ -500,8 +500,9 @@ template <class T, class I> struct LeafRange {
 __device__ __noinline__ double rcp_beyond_table(double nf) { return __drcp_rn(nf); }
 // Reciprocals of the counts RCP_TABLE .. RCP_FAR-1 live in global memory (512 KB, filled once per
 // device; neighbouring lanes ask for neighbouring counts, so a warp's load touches one or two L1
-// sectors): training vectors longer than the shared table — 2^18 leaves on 200M keys, or 2^20
-// leaves on a key set spread over eight GPUs — pay one cached load per item, not a division.
+// sectors): the GENERAL step's second source (LeafWelford::fetch_rc).  Linear leaves with vectors
+// longer than the shared table no longer come here — they use the per-warp ring (ring_rc below) —
+// so this serves the loglinear / robust_linear leaves and vectors of 2^28 items and more.
 constexpr unsigned RCP_FAR = 1u << 16;
 __device__ double g_rcp_far[RCP_FAR];
 __global__ void k_init_rcp_far() {
