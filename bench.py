@@ -518,6 +518,20 @@ def main():
                   flags=rmi_b200.FLAG_TOP_FIT_EXACT, steps=1)
             if "linear,linear 1048576, exact (serial) top fit" in extras:
                 parity["exact_top_ms_per_step"] = extras["linear,linear 1048576, exact (serial) top fit"].get("ms_per_step")
+            # BASELINE.json configs[4] in miniature: the reference's --optimize search (optimizer.rs:233-249, default profile,
+            # both phases, statistics-only builds) over this GPU's 200M keys.  The configuration itself — 800M f64 keys on the
+            # replicas of 8 GPUs — is measured by tools/optimize_bench.py (profiles/r02j_optimize_8gpu.json: 8.9 s).
+            oname = "--optimize (default profile, two phases) on the same 200M keys, 1 GPU"
+            try:
+                l0 = rmi_b200.kernel_launch_count()
+                t0 = time.perf_counter()
+                front = rmi_b200.find_pareto_efficient_configs([keep], 10)
+                dt = time.perf_counter() - t0
+                extras[oname] = {"seconds": dt, "kernel_launches": int(rmi_b200.kernel_launch_count() - l0),
+                                 "front": [[c.get("models"), int(c.get("branching_factor", 0)), float(c.get("average_log2_error", 0.0)),
+                                            int(c.get("size", 0))] for c in front]}
+            except Exception as e:  # noqa: BLE001 - an extra must never cost the contract line
+                extras[oname] = {"error": str(e)[:200]}
         else:
             # strong scaling: BASELINE's 200M keys IN TOTAL over the N GPUs
             ns = n // world
